@@ -1,0 +1,80 @@
+"""Pins the oracle (oracle/orlg_oracle.c) to golden vectors recorded from the live reference
+(tests/golden/make_golden.py).  Bit-exact on every integer field, bit-exact on float64
+observations / rewards (same operation order as deeprmsa_env.py:60-121)."""
+import numpy as np
+import pytest
+
+import helpers
+from oracle import oracle
+
+
+def replay(g, i, use_heuristic=False):
+    meta = g["meta"]
+    kind, T = meta["kind"], meta["T"]
+    e = oracle.OracleEnv(kind, helpers.golden_tables(), **helpers.sim_kwargs(meta))
+    e.set_trace(g["req_arrival"][i], g["req_holding"][i], g["req_src"][i], g["req_dst"][i], g["req_bit_rate"][i])
+    e.reset(full=True)
+    e.reset(full=False)         # evaluate_heuristic's reset() before the first episode
+    hid = helpers.HEURISTIC_ID.get(meta["policy"]) if use_heuristic else None
+    Cc, E, S = e.cells
+    for t in range(T):
+        r = e.request()
+        assert r["arrival"] == g["req_arrival"][i, t] and r["src"] == g["req_src"][i, t]
+        assert r["service_id"] == g["req_id"][i, t], (t, r)
+        if "obs" in g:
+            assert np.array_equal(e.observation(), g["obs"][i, t]), ("obs", t)
+        a = e.heuristic(hid) if hid is not None else g["actions"][i, t]
+        if hid is not None:
+            assert np.array_equal(a, g["actions"][i, t]), ("heuristic action", t, a, g["actions"][i, t])
+        o, rc = e.step(a)
+        assert rc == 0
+        assert o.accepted == g["accepted"][i, t], ("accepted", t)
+        assert o.path_row == g["path_row"][i, t], ("path", t)
+        assert o.initial_slot == g["initial_slot"][i, t], ("slot", t)
+        assert o.number_slots == g["number_slots"][i, t], ("n", t)
+        if "core" in g:
+            assert o.core == g["core"][i, t] and o.mod == g["mod"][i, t], ("core/mod", t)
+        assert o.reward == g["reward"][i, t] and o.done == g["done"][i, t], ("reward/done", t)
+        c = e.counters()
+        assert np.array_equal(c, g["counters"][i, t]), ("counters", t, c, g["counters"][i, t])
+        # the four blocking-rate infos are pure functions of the counters (rmsa_env.py:234-248)
+        ic = [int(x) for x in o.info_counters]
+        assert (ic[0] - ic[1]) / ic[0] == g["info_service_blocking_rate"][i, t]
+        assert (ic[2] - ic[3]) / ic[2] == g["info_episode_service_blocking_rate"][i, t]
+        if "info_bit_rate_blocking_rate" in g:
+            assert (ic[4] - ic[5]) / ic[4] == g["info_bit_rate_blocking_rate"][i, t]
+            assert (ic[6] - ic[7]) / ic[6] == g["info_episode_bit_rate_blocking_rate"][i, t]
+        if i < g["avail_bits"].shape[0] and (t % 7 == 0 or t == T - 1):
+            avail = e.state()[0].reshape(Cc * E, S).astype(np.uint8)
+            assert np.array_equal(np.packbits(avail, axis=1, bitorder="little"), g["avail_bits"][i, t]), ("masks", t)
+        if o.done:
+            e.reset(full=False)
+    avail, alloc, now, nheap = e.state()
+    assert np.array_equal(avail, g["final_avail"][i])
+    assert np.array_equal(alloc, g["final_alloc"][i])
+    assert now == g["final_now"][i] and nheap == g["final_nheap"][i]
+    if "obs" in g:
+        assert np.array_equal(e.observation(), g["obs"][i, T])
+    assert e.error() == 0
+
+
+@pytest.mark.parametrize("name", helpers.golden_names())
+def test_oracle_replays_reference_trace(name):
+    g = helpers.load_golden(name)
+    for i in range(g["meta"]["n_envs"]):
+        replay(g, i)
+
+
+@pytest.mark.parametrize("name", [n for n in helpers.golden_names()
+                                  if helpers.load_golden(n)["meta"]["policy"] in helpers.HEURISTIC_ID])
+def test_oracle_heuristics_match_reference(name):
+    g = helpers.load_golden(name)
+    replay(g, 0, use_heuristic=True)
+
+
+def test_known_answer_values_from_reference_scripts():
+    """first two DeepRMSA requests for seed 10 are in the golden (env 0, seed0=10)."""
+    g = helpers.load_golden("deeprmsa_default_random")
+    assert g["req_arrival"][0, 0] == 0.08472372498338585 and g["req_holding"][0, 0] == 14.004294703908837
+    assert (g["req_src"][0, 0], g["req_dst"][0, 0], g["req_bit_rate"][0, 0]) == (8, 2, 87)
+    assert g["req_arrival"][0, 1] == 0.258217530635666 and g["req_bit_rate"][0, 1] == 66
