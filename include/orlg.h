@@ -1,0 +1,165 @@
+/*
+ * orlg.h -- C ABI of the B200-native batched Optical RL-Gym step path (liborlg.so).
+ *
+ * The reference (carlosnatalino/optical-rl-gym) has no FFI: its "operator API" for this
+ * path is the gym.Env method set of RWAEnv / RMSAEnv / DeepRMSAEnv / RMCSAEnv.  Each entry
+ * point below names the reference method(s) it replaces for a whole batch of independent
+ * environments (file:line relative to the reference tree).  Plain pointers and sizes only;
+ * every *_dev pointer is caller-owned DEVICE memory (e.g. a torch tensor's data_ptr()),
+ * every call is stream-ordered on the cudaStream_t passed as `stream` (0 = legacy default
+ * stream) and never synchronises.  Return value: 0 on success, <0 = ORLG_E_* (see
+ * orlg_last_error()).  One host thread per handle.
+ */
+#ifndef ORLG_H
+#define ORLG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORLG_VERSION 1
+
+/* environment kinds = the reference's gym ids (optical_rl_gym/__init__.py:3-26) */
+enum { ORLG_RWA = 0, ORLG_RMSA = 1, ORLG_DEEPRMSA = 2, ORLG_RMCSA = 3 };
+/* request sources */
+enum { ORLG_TRAFFIC_TRACE = 0, ORLG_TRAFFIC_PHILOX = 1 };
+/* observation element type (DeepRMSA): f64 reproduces deeprmsa_env.py:60-121 bit-for-bit */
+enum { ORLG_OBS_F32 = 0, ORLG_OBS_F64 = 1 };
+/* heuristic action sources (rmsa_env.py:747-803, rwa_env.py:425-502, deeprmsa_env.py:135-155,
+ * rmcsa_env.py:882-911) */
+enum { ORLG_HEUR_SP_FF = 0, ORLG_HEUR_SAP_FF = 1, ORLG_HEUR_LLP_FF = 2, ORLG_HEUR_SAP_LF = 3 };
+/* error codes */
+enum { ORLG_OK = 0, ORLG_E_INVALID = -1, ORLG_E_UNSUPPORTED = -2, ORLG_E_CUDA = -3, ORLG_E_NOMEM = -4 };
+/* per-environment soft error bits (orlg_error_flags) */
+enum {
+    ORLG_ERR_TRACE_EXHAUSTED = 1,  /* the recorded trace has no request left */
+    ORLG_ERR_HEAP_OVERFLOW = 2,    /* more live services than heap_capacity: the request was blocked */
+    ORLG_ERR_NO_SUCH_PATH = 4      /* action chose path >= number of candidate paths (reference: IndexError) */
+};
+
+typedef struct orlg_env orlg_env;     /* opaque handle: owns all per-environment state in HBM */
+typedef void *orlg_stream;            /* cudaStream_t */
+
+/* Constructor keyword arguments of the reference envs (optical_network_env.py:14-25,
+ * rmsa_env.py:29-46, deeprmsa_env.py:10-21, rwa_env.py:19-31, rmcsa_env.py:29-49). */
+typedef struct orlg_config {
+    int32_t kind;              /* ORLG_RWA ... */
+    int32_t num_envs;          /* environments held by this handle (this GPU's shard) */
+    int64_t env_id_base;       /* global id of local env 0: Philox streams are keyed by global id */
+    int32_t num_slots;         /* num_spectrum_resources */
+    int32_t num_cores;         /* num_spatial_resources (RMCSA), else 1 */
+    int32_t j;                 /* DeepRMSA: candidate blocks per path */
+    int32_t episode_length;
+    int32_t allow_rejection;
+    int32_t bit_rate_lo, bit_rate_hi;   /* continuous bit-rate selection: randint bounds */
+    int32_t traffic;           /* ORLG_TRAFFIC_* */
+    int32_t obs_dtype;         /* ORLG_OBS_* */
+    int32_t auto_reset;        /* VecEnv semantics: reset(only_episode_counters=True) right after done */
+    int32_t heap_capacity;     /* max live services per env; 0 = derive from the load */
+    uint64_t seed;             /* Philox key */
+    double channel_width;      /* GHz per slot */
+    double mean_holding;       /* mean_service_holding_time */
+    double mean_iat;           /* mean_service_inter_arrival_time = holding / load */
+    double worst_xt;           /* RMCSA worst aggregate inter-core crosstalk (dB), before the +4 dB margin */
+} orlg_config;
+
+/* Host-side topology tables (what topology.graph["ksp"/"modulations"] holds after
+ * examples/create_topology.py:96-147).  HOST pointers, copied by orlg_create. */
+typedef struct orlg_tables {
+    int32_t num_nodes, num_links, k_paths, num_paths, num_mods, num_bit_rates;
+    const int32_t *pair_first;     /* [N*N] first path row of (src,dst) */
+    const int32_t *pair_count;     /* [N*N] candidate paths of the pair (<= k_paths) */
+    const int32_t *path_hops;      /* [P] */
+    const int32_t *path_se;        /* [P] spectral efficiency of Path.best_modulation */
+    const int32_t *path_mod;       /* [P] index of best_modulation */
+    const int32_t *path_link_ptr;  /* [P+1] CSR */
+    const int32_t *path_links;     /* link index of every hop */
+    const double *path_length;     /* [P] km */
+    const int32_t *mod_se;         /* [M] */
+    const double *mod_osnr;        /* [M] minimum_osnr */
+    const double *mod_xt;          /* [M] inband_xt */
+    const double *node_prob;       /* [N] node_request_probabilities */
+    const int32_t *bit_rates;      /* [num_bit_rates] discrete bit-rate selection (0 = continuous) */
+    const double *bit_rate_prob;   /* [num_bit_rates] */
+} orlg_tables;
+
+/* One recorded request of a trace (ORLG_TRAFFIC_TRACE): what _next_service draws,
+ * rmsa_env.py:545-573.  arrival is absolute time. */
+typedef struct orlg_request {
+    double arrival;
+    double holding;
+    int32_t src, dst, bit_rate, reserved;
+} orlg_request;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* gym.make(id, **env_args) for num_envs environments on CUDA device `device`
+ * (optical_network_env.py:14-74 + the env constructors).  Does NOT reset: call orlg_reset(full=1). */
+int orlg_create(const orlg_config *cfg, const orlg_tables *tables, int device, orlg_env **out);
+int orlg_destroy(orlg_env *env);
+const char *orlg_last_error(void);
+int orlg_version(void);
+
+/* ---- shape queries -------------------------------------------------------------------- */
+int orlg_action_dim(const orlg_env *env);   /* 1 DeepRMSA (Discrete), 2 RMSA/RWA, 4 RMCSA (MultiDiscrete) */
+int orlg_obs_dim(const orlg_env *env);      /* 1 + 2N + (2j+3)k for DeepRMSA (deeprmsa_env.py:34-40), else 0 */
+int orlg_mask_words(const orlg_env *env);   /* 32-bit words per (core, link) in orlg_export_state */
+int orlg_heap_capacity(const orlg_env *env);
+int64_t orlg_state_bytes(const orlg_env *env);
+
+/* ---- traffic -------------------------------------------------------------------------- */
+/* Replay mode: trace_dev[e * trace_len + i] is the i-th request of env e since the last full
+ * reset.  The buffer must stay valid while the handle steps. */
+int orlg_set_trace(orlg_env *env, const orlg_request *trace_dev, int64_t trace_len);
+
+/* ---- the hot path --------------------------------------------------------------------- */
+/* env.reset(only_episode_counters = !full) for every env (rmsa_env.py:284-359,
+ * rwa_env.py:164-208, rmcsa_env.py:386-483).  obs_dev (may be NULL): [num_envs, obs_dim]. */
+int orlg_reset(orlg_env *env, int full, void *obs_dev, orlg_stream stream);
+
+/* obs, reward, done, info = env.step(action) for every env (rmsa_env.py:163-282,
+ * deeprmsa_env.py:48-58, rwa_env.py:101-162, rmcsa_env.py:209-339), including _next_service and
+ * the release loop (rmsa_env.py:545-597).
+ *   actions_dev   int32 [num_envs, action_dim]
+ *   obs_dev       f32/f64 [num_envs, obs_dim]           (NULL: skip; ignored for obs_dim == 0)
+ *   reward_dev    f32 [num_envs]                         (NULL: skip)
+ *   done_dev      u8  [num_envs]                         (NULL: skip)
+ *   decision_dev  int32 [num_envs, 6] = accepted, path row, initial slot, slots, core, modulation
+ *                 (-1 where not applicable)              (NULL: skip)
+ *   info_dev      int64 [num_envs, 8] = the counters at the moment the reference builds `info`:
+ *                 processed, accepted, episode processed, episode accepted, bit_rate requested,
+ *                 provisioned, episode requested, episode provisioned (NULL: skip)            */
+int orlg_step(orlg_env *env, const int32_t *actions_dev, void *obs_dev, float *reward_dev, uint8_t *done_dev,
+              int32_t *decision_dev, int64_t *info_dev, orlg_stream stream);
+
+/* env.observation() of the pending request (deeprmsa_env.py:60-121) */
+int orlg_observation(orlg_env *env, void *obs_dev, orlg_stream stream);
+/* integer pre-image of the observation: int32 [num_envs, k, 2j+3] = (start_b, len_b)*j, n_slots,
+ * total free slots, number of free runs; -1 = absent */
+int orlg_observation_int(orlg_env *env, int32_t *out_dev, orlg_stream stream);
+
+/* heuristic(env) -> action for every env; `which` = ORLG_HEUR_* */
+int orlg_heuristic(orlg_env *env, int which, int32_t *actions_dev, orlg_stream stream);
+/* uniform random policy (action_space.sample() equivalent, Philox stream 2) */
+int orlg_random_actions(orlg_env *env, int32_t *actions_dev, orlg_stream stream);
+
+/* ---- introspection (what heuristics / tests read from the reference env object) -------- */
+/* counters after the last step: int64 [num_envs, 8], same order as info_dev */
+int orlg_get_counters(orlg_env *env, int64_t *counters_dev, orlg_stream stream);
+/* env.current_service: requests_dev [num_envs], service_id_dev int32 [num_envs] (either may be NULL) */
+int orlg_get_requests(orlg_env *env, orlg_request *requests_dev, int32_t *service_id_dev, orlg_stream stream);
+/* topology.graph["available_slots"] bit-packed: uint32 [num_envs, cores*links, mask_words] (bit s of
+ * word s/32 = slot s free); spectrum_slots_allocation: int32 [num_envs, cores, links, slots];
+ * current_time f64 [num_envs]; len(_events) int32 [num_envs].  Any pointer may be NULL. */
+int orlg_export_state(orlg_env *env, uint32_t *masks_dev, int32_t *alloc_dev, double *now_dev, int32_t *nheap_dev,
+                      orlg_stream stream);
+int orlg_error_flags(orlg_env *env, uint32_t *flags_dev, orlg_stream stream);
+/* per-device sums over envs of the 8 counters + number of envs with error flags: int64 [9]
+ * (input of the cross-GPU all-reduce of episode statistics) */
+int orlg_reduce_counters(orlg_env *env, int64_t *sums_dev, orlg_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORLG_H */

@@ -1,0 +1,380 @@
+// orlg_api.cu -- the C ABI (include/orlg.h) on top of the step kernels.  Links cudart only.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "orlg_kernels.cuh"
+
+using namespace orlg;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_OK(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail(ORLG_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+struct orlg_env {
+    Params p;
+    orlg_config cfg;
+    int device;
+    int km;                       // KM template instance (5 or 8)
+    size_t obs_smem;
+    int64_t state_bytes;
+    std::vector<void *> allocs;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(orlg_env *env, T **out, size_t count, bool zero = true) {
+    void *ptr = nullptr;
+    size_t bytes = sizeof(T) * (count ? count : 1);
+    if (cudaMalloc(&ptr, bytes) != cudaSuccess) return fail(ORLG_E_NOMEM, "cudaMalloc failed for " + std::to_string(bytes) + " bytes");
+    if (zero && cudaMemset(ptr, 0, bytes) != cudaSuccess) return fail(ORLG_E_CUDA, "cudaMemset failed");
+    env->allocs.push_back(ptr);
+    env->state_bytes += (int64_t)bytes;
+    *out = reinterpret_cast<T *>(ptr);
+    return ORLG_OK;
+}
+
+template <typename T>
+int dev_upload(orlg_env *env, const T **out, const std::vector<T> &host) {
+    T *ptr = nullptr;
+    int rc = dev_alloc(env, &ptr, host.size(), false);
+    if (rc) return rc;
+    if (!host.empty() && cudaMemcpy(ptr, host.data(), sizeof(T) * host.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(ORLG_E_CUDA, "cudaMemcpy (table upload) failed");
+    *out = ptr;
+    return ORLG_OK;
+}
+
+// integer CDF thresholds of the Philox node / bit-rate draws (DESIGN.md "Traffic")
+std::vector<unsigned> thresholds(const double *prob, int n) {
+    std::vector<unsigned> thr(n);
+    double tot = 0.0, acc = 0.0;
+    for (int i = 0; i < n; i++) tot += prob[i];
+    for (int i = 0; i < n; i++) {
+        acc += prob[i];
+        double v = std::floor(acc / tot * 4294967296.0 + 0.5);
+        if (v > 4294967295.0) v = 4294967295.0;
+        thr[i] = (unsigned)v;
+    }
+    thr[n - 1] = 4294967295u;
+    return thr;
+}
+
+// rmcsa_env.py:341-384: longest reach (km) of a modulation at a bit rate = min(lmax_snr, lmax_xt)
+double reach_km(double osnr, double inband_xt_raw, int se, int bit_rate, double worst_xt_raw) {
+    double average_power = 1, nf_db = 5.5;
+    double nf = std::pow(10.0, nf_db / 10.0);
+    double amp_spam = 100, amp_gain_db = 20;
+    double amp_gain = std::pow(10.0, amp_gain_db / 10.0);
+    double lambda_ = 1550, h = 6.626068e-34;
+    double f_hz = 2.99e8 / (lambda_ * 1e-9);
+    double inband_xt = inband_xt_raw + 4;        // rmcsa_env.py:127-129 (+4 dB margins)
+    double worst_xt = worst_xt_raw + 4;
+    double snr_min = std::pow(10.0, (osnr + 2) / 10);
+    double lmax_snr = (average_power * amp_spam) /
+                      (snr_min * h * f_hz * amp_gain * nf * ((double)bit_rate / (double)se) * 1e9);
+    lmax_snr = lmax_snr / 1000;
+    double lmax_xt = std::pow(10.0, (inband_xt - worst_xt - 4) / 10);
+    return lmax_snr < lmax_xt ? lmax_snr : lmax_xt;
+}
+
+template <int KIND>
+void launch_step_kind(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s) {
+    const int blocks = (env->p.n + STEP_THREADS - 1) / STEP_THREADS;
+    const size_t smem = (KIND == ORLG_DEEPRMSA && io.obs) ? env->obs_smem : 0;
+    if (env->km == 5) step_kernel<KIND, 5><<<blocks, STEP_THREADS, smem, s>>>(env->p, io, mode);
+    else step_kernel<KIND, KMAX><<<blocks, STEP_THREADS, smem, s>>>(env->p, io, mode);
+}
+
+int launch_step(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s) {
+    switch (env->p.kind) {
+    case ORLG_RWA: launch_step_kind<ORLG_RWA>(env, io, mode, s); break;
+    case ORLG_RMSA: launch_step_kind<ORLG_RMSA>(env, io, mode, s); break;
+    case ORLG_DEEPRMSA: launch_step_kind<ORLG_DEEPRMSA>(env, io, mode, s); break;
+    case ORLG_RMCSA: launch_step_kind<ORLG_RMCSA>(env, io, mode, s); break;
+    default: return fail(ORLG_E_INVALID, "unknown env kind");
+    }
+    CUDA_OK(cudaGetLastError());
+    return ORLG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *orlg_last_error(void) { return g_err.c_str(); }
+int orlg_version(void) { return ORLG_VERSION; }
+
+int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_env **out) {
+    if (!cfg || !t || !out) return fail(ORLG_E_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->kind < ORLG_RWA || cfg->kind > ORLG_RMCSA) return fail(ORLG_E_INVALID, "unknown env kind");
+    if (cfg->num_envs <= 0) return fail(ORLG_E_INVALID, "num_envs must be positive");
+    if (t->num_links > 32 || cfg->num_slots > MAX_SLOTS || cfg->num_slots <= 0)
+        return fail(ORLG_E_UNSUPPORTED, "this build handles <= 32 links and <= 128 slots per link (NSFNET class)");
+    if (t->num_nodes > 255 || t->num_nodes < 2) return fail(ORLG_E_UNSUPPORTED, "2..255 nodes");
+    if (t->k_paths > KMAX || t->k_paths < 1) return fail(ORLG_E_UNSUPPORTED, "k_paths must be 1..8");
+    if (t->num_paths >= (1 << 20)) return fail(ORLG_E_UNSUPPORTED, "too many paths");
+    const int C = cfg->kind == ORLG_RMCSA ? cfg->num_cores : 1;
+    if (C < 1 || C > 31) return fail(ORLG_E_UNSUPPORTED, "1..31 cores");
+    const int J = cfg->kind == ORLG_DEEPRMSA ? cfg->j : 1;
+    if (J < 1 || J > 16) return fail(ORLG_E_INVALID, "j must be 1..16");
+    if (cfg->episode_length < 1 || cfg->episode_length >= (1 << 22)) return fail(ORLG_E_UNSUPPORTED, "episode_length must be < 2^22");
+    if (!(cfg->mean_holding > 0) || !(cfg->mean_iat > 0)) return fail(ORLG_E_INVALID, "holding / inter-arrival times must be positive");
+    if (cfg->kind != ORLG_RWA && t->num_bit_rates == 0 && cfg->bit_rate_hi < cfg->bit_rate_lo)
+        return fail(ORLG_E_INVALID, "bit_rate_higher_bound < bit_rate_lower_bound");
+    if (cfg->kind == ORLG_RMCSA && t->num_mods < 1) return fail(ORLG_E_INVALID, "RMCSA needs a modulation table");
+
+    CUDA_OK(cudaSetDevice(device));
+    orlg_env *env = new orlg_env();
+    env->cfg = *cfg;
+    env->device = device;
+    env->state_bytes = 0;
+    Params &p = env->p;
+    std::memset(&p, 0, sizeof(p));
+    p.kind = cfg->kind; p.n = cfg->num_envs; p.N = t->num_nodes; p.E = t->num_links; p.C = C; p.S = cfg->num_slots;
+    p.k = t->k_paths; p.J = J; p.M = t->num_mods;
+    p.episode_length = cfg->episode_length; p.allow_rejection = cfg->allow_rejection ? 1 : 0;
+    p.auto_reset = cfg->auto_reset ? 1 : 0; p.traffic = cfg->traffic; p.obs_f64 = cfg->obs_dtype == ORLG_OBS_F64;
+    p.n_bit_rates = t->num_bit_rates;
+    p.br_lo = cfg->bit_rate_lo; p.br_span = cfg->bit_rate_hi - cfg->bit_rate_lo + 1;
+    int br_max = cfg->kind == ORLG_RWA ? 0 : cfg->bit_rate_hi;
+    for (int i = 0; i < t->num_bit_rates; i++) br_max = t->bit_rates[i] > br_max ? t->bit_rates[i] : br_max;
+    if (br_max < 0 || br_max > 65535) { delete env; return fail(ORLG_E_UNSUPPORTED, "bit rates must be 0..65535"); }
+    p.br_max = br_max;
+    p.seed = cfg->seed; p.env_id_base = cfg->env_id_base;
+    p.mean_holding = cfg->mean_holding; p.mean_iat = cfg->mean_iat;
+    p.obs_dim = cfg->kind == ORLG_DEEPRMSA ? 1 + 2 * p.N + (2 * J + 3) * p.k : 0;
+    p.cand_stride = ((p.k * J + 3) / 4) * 4;
+    env->km = p.k <= 5 ? 5 : KMAX;
+    env->obs_smem = (size_t)STEP_THREADS * p.obs_dim * (p.obs_f64 ? 8 : 4);
+    if (env->obs_smem > 200 * 1024) { delete env; return fail(ORLG_E_UNSUPPORTED, "observation too large for the staging tile"); }
+
+    // heap capacity: live services ~ Poisson(load) at most (M/M/inf bound); hard bound E*S*C/2 slots pairs
+    int cap = cfg->heap_capacity;
+    if (cap <= 0) {
+        double load = cfg->mean_holding / cfg->mean_iat;
+        double want = load + 8.0 * std::sqrt(load) + 16.0;
+        double hard = cfg->kind == ORLG_RWA ? (double)p.E * p.S * C : (double)p.E * p.S * C / 2.0;
+        cap = (int)std::ceil(want < hard ? want : hard) + (int)HEAP_ROOT + 1;
+    }
+    cap = ((cap + 3) / 4) * 4;
+    if (cap < 8) cap = 8;
+    p.heap_cap = cap;
+
+    // ---- tables
+    int rc = ORLG_OK;
+    const int NN = p.N * p.N, P = t->num_paths;
+    std::vector<int> pair_first(t->pair_first, t->pair_first + NN);
+    std::vector<unsigned char> pair_count(NN);
+    for (int i = 0; i < NN; i++) pair_count[i] = (unsigned char)(t->pair_count[i] < 0 ? 0 : (t->pair_count[i] > p.k ? p.k : t->pair_count[i]));
+    std::vector<unsigned> linkmask(P), meta(P);
+    int se_max = 1;
+    for (int r = 0; r < P; r++) {
+        unsigned lm = 0;
+        for (int h = t->path_link_ptr[r]; h < t->path_link_ptr[r + 1]; h++) lm |= 1u << t->path_links[h];
+        linkmask[r] = lm;
+        int se = t->path_se[r] < 1 ? 1 : t->path_se[r];
+        meta[r] = (unsigned)(t->path_hops[r] & 0xff) | ((unsigned)(se & 0xff) << 8) | ((unsigned)(t->path_mod[r] & 0xff) << 16);
+        se_max = se > se_max ? se : se_max;
+    }
+    std::vector<unsigned char> mod_se(t->num_mods > 0 ? t->num_mods : 1, 1);
+    for (int m = 0; m < t->num_mods; m++) { mod_se[m] = (unsigned char)t->mod_se[m]; se_max = t->mod_se[m] > se_max ? t->mod_se[m] : se_max; }
+    // get_number_slots (rmsa_env.py:610-621): ceil(bit_rate / (SE * channel_width)) + 1, same float expression
+    std::vector<unsigned char> nslots((size_t)(se_max + 1) * (br_max + 1), 1);
+    for (int se = 1; se <= se_max; se++)
+        for (int b = 0; b <= br_max; b++) {
+            int n = (int)std::ceil((double)b / ((double)se * cfg->channel_width)) + 1;
+            if (n > 200) n = 200;      // > S anyway: can never fit
+            nslots[(size_t)se * (br_max + 1) + b] = (unsigned char)n;
+        }
+    std::vector<double> reach((size_t)(t->num_mods > 0 ? t->num_mods : 1) * (br_max + 1), 0.0);
+    if (cfg->kind == ORLG_RMCSA)
+        for (int m = 0; m < t->num_mods; m++)
+            for (int b = 0; b <= br_max; b++)
+                reach[(size_t)m * (br_max + 1) + b] = b == 0 ? 1e300 : reach_km(t->mod_osnr[m], t->mod_xt[m], t->mod_se[m], b, cfg->worst_xt);
+    std::vector<double> plen(t->path_length, t->path_length + P);
+    std::vector<unsigned> node_thr = thresholds(t->node_prob, p.N);
+    std::vector<unsigned> br_thr = t->num_bit_rates > 0 ? thresholds(t->bit_rate_prob, t->num_bit_rates) : std::vector<unsigned>(1, 0u);
+    std::vector<int> bit_rates(t->num_bit_rates > 0 ? t->num_bit_rates : 1, 0);
+    for (int i = 0; i < t->num_bit_rates; i++) bit_rates[i] = t->bit_rates[i];
+
+    if (!rc) rc = dev_upload(env, &p.pair_first, pair_first);
+    if (!rc) rc = dev_upload(env, &p.pair_count, pair_count);
+    if (!rc) rc = dev_upload(env, &p.path_linkmask, linkmask);
+    if (!rc) rc = dev_upload(env, &p.path_meta, meta);
+    if (!rc) rc = dev_upload(env, &p.path_length, plen);
+    if (!rc) rc = dev_upload(env, &p.nslots, nslots);
+    if (!rc) rc = dev_upload(env, &p.mod_se, mod_se);
+    if (!rc) rc = dev_upload(env, &p.reach, reach);
+    if (!rc) rc = dev_upload(env, &p.node_thr, node_thr);
+    if (!rc) rc = dev_upload(env, &p.br_thr, br_thr);
+    if (!rc) rc = dev_upload(env, &p.bit_rates, bit_rates);
+    // ---- state
+    const size_t n = (size_t)p.n;
+    if (!rc) rc = dev_alloc(env, &p.masks, (size_t)C * p.E * n);
+    if (!rc) rc = dev_alloc(env, &p.now, n);
+    if (!rc) rc = dev_alloc(env, &p.cur_hold, n);
+    if (!rc) rc = dev_alloc(env, &p.cur_req, n);
+    if (!rc) rc = dev_alloc(env, &p.counters, 8 * n);
+    if (!rc) rc = dev_alloc(env, &p.req_index, n);
+    if (!rc) rc = dev_alloc(env, &p.nheap, n);
+    if (!rc) rc = dev_alloc(env, &p.heap_min, n);
+    if (!rc) rc = dev_alloc(env, &p.heap, n * (size_t)p.heap_cap, false);
+    if (!rc) rc = dev_alloc(env, &p.cand, n * (size_t)p.cand_stride);
+    if (!rc) rc = dev_alloc(env, &p.errors, n);
+    if (rc) { orlg_destroy(env); return rc; }
+
+    if (env->obs_smem > 48 * 1024) {
+        cudaError_t e1 = cudaFuncSetAttribute(step_kernel<ORLG_DEEPRMSA, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->obs_smem);
+        cudaError_t e2 = cudaFuncSetAttribute(step_kernel<ORLG_DEEPRMSA, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->obs_smem);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) { orlg_destroy(env); return fail(ORLG_E_CUDA, "cudaFuncSetAttribute(shared memory) failed"); }
+    }
+    *out = env;
+    return ORLG_OK;
+}
+
+int orlg_destroy(orlg_env *env) {
+    if (!env) return ORLG_OK;
+    cudaSetDevice(env->device);
+    for (void *ptr : env->allocs) cudaFree(ptr);
+    delete env;
+    return ORLG_OK;
+}
+
+int orlg_action_dim(const orlg_env *env) { return env->p.kind == ORLG_DEEPRMSA ? 1 : (env->p.kind == ORLG_RMCSA ? 4 : 2); }
+int orlg_obs_dim(const orlg_env *env) { return env->p.obs_dim; }
+int orlg_mask_words(const orlg_env *env) { (void)env; return NW; }
+int orlg_heap_capacity(const orlg_env *env) { return env->p.heap_cap - (int)HEAP_ROOT; }
+int64_t orlg_state_bytes(const orlg_env *env) { return env->state_bytes; }
+
+int orlg_set_trace(orlg_env *env, const orlg_request *trace_dev, int64_t trace_len) {
+    if (!env || (trace_len > 0 && !trace_dev)) return fail(ORLG_E_INVALID, "null trace");
+    if (trace_len >= (1LL << 32)) return fail(ORLG_E_UNSUPPORTED, "trace too long");
+    env->p.trace = trace_dev;
+    env->p.trace_len = trace_len;
+    env->p.traffic = ORLG_TRAFFIC_TRACE;
+    return ORLG_OK;
+}
+
+int orlg_reset(orlg_env *env, int full, void *obs_dev, orlg_stream stream) {
+    if (!env) return fail(ORLG_E_INVALID, "null handle");
+    if (env->p.traffic == ORLG_TRAFFIC_TRACE && env->p.trace == nullptr) return fail(ORLG_E_INVALID, "trace traffic selected but orlg_set_trace was not called");
+    StepIO io;
+    std::memset(&io, 0, sizeof(io));
+    io.obs = env->p.obs_dim ? obs_dev : nullptr;
+    return launch_step(env, io, full ? MODE_FULL_RESET : MODE_EPISODE_RESET, (cudaStream_t)stream);
+}
+
+int orlg_step(orlg_env *env, const int32_t *actions_dev, void *obs_dev, float *reward_dev, uint8_t *done_dev,
+              int32_t *decision_dev, int64_t *info_dev, orlg_stream stream) {
+    if (!env || !actions_dev) return fail(ORLG_E_INVALID, "null handle or actions");
+    StepIO io;
+    io.actions = actions_dev;
+    io.obs = env->p.obs_dim ? obs_dev : nullptr;
+    io.reward = reward_dev;
+    io.done = done_dev;
+    io.decision = decision_dev;
+    io.info = reinterpret_cast<long long *>(info_dev);
+    io.obs_int = nullptr;
+    return launch_step(env, io, MODE_STEP, (cudaStream_t)stream);
+}
+
+int orlg_observation(orlg_env *env, void *obs_dev, orlg_stream stream) {
+    if (!env || !obs_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
+    if (!env->p.obs_dim) return fail(ORLG_E_UNSUPPORTED, "this env kind has a dict observation (no tensor)");
+    StepIO io;
+    std::memset(&io, 0, sizeof(io));
+    io.obs = obs_dev;
+    return launch_step(env, io, MODE_OBSERVE, (cudaStream_t)stream);
+}
+
+int orlg_observation_int(orlg_env *env, int32_t *out_dev, orlg_stream stream) {
+    if (!env || !out_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
+    if (!env->p.obs_dim) return fail(ORLG_E_UNSUPPORTED, "this env kind has a dict observation (no tensor)");
+    StepIO io;
+    std::memset(&io, 0, sizeof(io));
+    io.obs_int = out_dev;
+    return launch_step(env, io, MODE_OBSERVE, (cudaStream_t)stream);
+}
+
+int orlg_heuristic(orlg_env *env, int which, int32_t *actions_dev, orlg_stream stream) {
+    if (!env || !actions_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
+    if (which < 0 || which > ORLG_HEUR_SAP_LF) return fail(ORLG_E_INVALID, "unknown heuristic");
+    const int threads = 128, blocks = (env->p.n + threads - 1) / threads;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (env->p.kind) {
+    case ORLG_RWA: heuristic_kernel<ORLG_RWA><<<blocks, threads, 0, s>>>(env->p, which, actions_dev); break;
+    case ORLG_RMSA:
+        if (which == ORLG_HEUR_SAP_LF) return fail(ORLG_E_UNSUPPORTED, "last-fit exists for RWA only");
+        heuristic_kernel<ORLG_RMSA><<<blocks, threads, 0, s>>>(env->p, which, actions_dev); break;
+    case ORLG_DEEPRMSA:
+        if (which > ORLG_HEUR_SAP_FF) return fail(ORLG_E_UNSUPPORTED, "DeepRMSA has SP-FF and SAP-FF only");
+        heuristic_kernel<ORLG_DEEPRMSA><<<blocks, threads, 0, s>>>(env->p, which, actions_dev); break;
+    case ORLG_RMCSA: heuristic_kernel<ORLG_RMCSA><<<blocks, threads, 0, s>>>(env->p, which, actions_dev); break;
+    }
+    CUDA_OK(cudaGetLastError());
+    return ORLG_OK;
+}
+
+int orlg_random_actions(orlg_env *env, int32_t *actions_dev, orlg_stream stream) {
+    if (!env || !actions_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
+    const int threads = 256, blocks = (env->p.n + threads - 1) / threads;
+    random_action_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->p, actions_dev);
+    CUDA_OK(cudaGetLastError());
+    return ORLG_OK;
+}
+
+static int run_export(orlg_env *env, uint32_t *masks, int32_t *alloc, double *now, int32_t *nheap, int64_t *counters,
+                      orlg_request *req, int32_t *sid, uint32_t *err, orlg_stream stream) {
+    if (!env) return fail(ORLG_E_INVALID, "null handle");
+    const int threads = 128, blocks = (env->p.n + threads - 1) / threads;
+    export_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->p, masks, alloc, now, nheap,
+                                                                reinterpret_cast<long long *>(counters), req, sid, err);
+    CUDA_OK(cudaGetLastError());
+    return ORLG_OK;
+}
+
+int orlg_get_counters(orlg_env *env, int64_t *counters_dev, orlg_stream stream) {
+    return run_export(env, nullptr, nullptr, nullptr, nullptr, counters_dev, nullptr, nullptr, nullptr, stream);
+}
+
+int orlg_get_requests(orlg_env *env, orlg_request *requests_dev, int32_t *service_id_dev, orlg_stream stream) {
+    return run_export(env, nullptr, nullptr, nullptr, nullptr, nullptr, requests_dev, service_id_dev, nullptr, stream);
+}
+
+int orlg_export_state(orlg_env *env, uint32_t *masks_dev, int32_t *alloc_dev, double *now_dev, int32_t *nheap_dev,
+                      orlg_stream stream) {
+    return run_export(env, masks_dev, alloc_dev, now_dev, nheap_dev, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+int orlg_error_flags(orlg_env *env, uint32_t *flags_dev, orlg_stream stream) {
+    return run_export(env, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, flags_dev, stream);
+}
+
+int orlg_reduce_counters(orlg_env *env, int64_t *sums_dev, orlg_stream stream) {
+    if (!env || !sums_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_OK(cudaMemsetAsync(sums_dev, 0, 9 * sizeof(int64_t), s));
+    int blocks = (env->p.n + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    reduce_counters_kernel<<<blocks, 256, 0, s>>>(env->p, reinterpret_cast<unsigned long long *>(sums_dev));
+    CUDA_OK(cudaGetLastError());
+    return ORLG_OK;
+}
+
+}  // extern "C"

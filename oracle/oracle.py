@@ -73,6 +73,13 @@ def lib():
         L.oracle_rollout_mt.restype = C.c_long
         L.oracle_rollout_mt.argtypes = [C.POINTER(Cfg), C.POINTER(Tab), C.c_uint64, C.c_uint32, C.c_int, C.c_long,
                                         C.c_int, C.c_int, C.c_int]
+        L.oracle_vec_create.restype = C.c_void_p
+        L.oracle_vec_create.argtypes = [C.POINTER(Cfg), C.POINTER(Tab), C.c_uint64, C.c_uint32, C.c_int]
+        L.oracle_vec_destroy.argtypes = [C.c_void_p]
+        L.oracle_vec_run.restype = C.c_long
+        L.oracle_vec_run.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int]
+        L.oracle_vec_env.restype = C.c_void_p
+        L.oracle_vec_env.argtypes = [C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -213,3 +220,31 @@ def rollout_mt(env_id, tables, *, seed, env0, n_envs, steps, policy=1, with_obs=
     threads = threads or os.cpu_count() or 1
     return lib().oracle_rollout_mt(C.byref(cfg), C.byref(tab), int(seed), int(env0), int(n_envs), int(steps),
                                    int(policy), int(with_obs), int(threads))
+
+
+class OracleVec:
+    """Persistent batch of oracle envs stepped by all host threads: the CPU arm of bench.py
+    (the reference's one-env-per-worker SubprocVecEnv pattern, restated in C)."""
+
+    def __init__(self, env_id, tables, n_envs, *, seed, env0=0, threads=None, **kw):
+        self.L = lib()
+        self.cfg, self.tab, self._keep = make_cfg_tab(env_id, tables, **kw)
+        self.n_envs = int(n_envs)
+        self.threads = int(threads or os.cpu_count() or 1)
+        self.h = self.L.oracle_vec_create(C.byref(self.cfg), C.byref(self.tab), int(seed), int(env0), self.n_envs)
+
+    def run(self, steps, policy=1, with_obs=True):
+        """Advance every env by `steps` steps; returns the number of accepted requests."""
+        return self.L.oracle_vec_run(self.h, int(steps), int(policy), int(with_obs), self.threads)
+
+    def counters(self, i):
+        c = np.zeros(8, np.int64)
+        self.L.oracle_get_counters(self.L.oracle_vec_env(self.h, int(i)), _ptr(c))
+        return c
+
+    def close(self):
+        if self.h:
+            self.L.oracle_vec_destroy(self.h)
+            self.h = None
+
+    __del__ = close

@@ -396,6 +396,20 @@ void *oracle_create(const ocfg_t *cfg, const otab_t *tab) {
     return e;
 }
 
+/* same, but borrows the caller's tables (they must outlive the env): used by the batched baseline */
+void *oracle_create_shared(const ocfg_t *cfg, const otab_t *tab) {
+    oenv_t *e = (oenv_t *)calloc(1, sizeof(oenv_t));
+    e->c = *cfg;
+    e->t = *tab;
+    size_t cells = (size_t)cfg->num_cores * cfg->num_links * cfg->num_slots;
+    e->avail = (int8_t *)malloc(cells);
+    e->alloc = (int32_t *)malloc(cells * sizeof(int32_t));
+    build_thresholds(e->t.node_prob, cfg->num_nodes, e->src_thr);
+    if (cfg->num_bit_rates > 0) build_thresholds(e->t.bit_rate_prob, cfg->num_bit_rates, e->br_thr);
+    e->traffic = 1;
+    return e;
+}
+
 void oracle_destroy(void *p) {
     oenv_t *e = (oenv_t *)p;
     for (int i = 0; i < e->nown; i++) free(e->own[i]);
@@ -793,3 +807,65 @@ long oracle_rollout_mt(const ocfg_t *cfg, const otab_t *tab, uint64_t seed, uint
     for (int i = 0; i < n_threads; i++) { pthread_join(th[i], NULL); acc += args[i].acc; }
     return acc;
 }
+
+/* ------------------------------------------------------------------ persistent batch ("SubprocVecEnv"-shaped CPU baseline)
+ * n independent envs kept alive across calls; oracle_vec_run advances every env by `steps` steps using
+ * n_threads host threads (static partition, no per-step barrier: the envs never interact). */
+typedef struct { int n; void **envs; ocfg_t cfg; otab_t tab; oenv_t *tabs_owner; } ovec_t;
+typedef struct { ovec_t *v; int tid, stride; long steps; int policy, with_obs; long acc; } vec_arg_t;
+
+void *oracle_vec_create(const ocfg_t *cfg, const otab_t *tab, uint64_t seed, uint32_t id0, int n) {
+    ovec_t *v = (ovec_t *)calloc(1, sizeof(ovec_t));
+    v->n = n; v->cfg = *cfg;
+    v->tabs_owner = (oenv_t *)oracle_create(cfg, tab);     /* owns one copy of the tables */
+    v->tab = v->tabs_owner->t;
+    v->envs = (void **)calloc((size_t)n, sizeof(void *));
+    for (int i = 0; i < n; i++) {
+        v->envs[i] = oracle_create_shared(&v->cfg, &v->tab);
+        oracle_set_philox(v->envs[i], seed, id0 + (uint32_t)i);
+        oracle_reset(v->envs[i], 1);
+    }
+    return v;
+}
+
+void oracle_vec_destroy(void *p) {
+    ovec_t *v = (ovec_t *)p;
+    for (int i = 0; i < v->n; i++) oracle_destroy(v->envs[i]);
+    oracle_destroy(v->tabs_owner);
+    free(v->envs); free(v);
+}
+
+static void *vec_worker(void *vp) {
+    vec_arg_t *a = (vec_arg_t *)vp;
+    double obs[4096];
+    for (int i = a->tid; i < a->v->n; i += a->stride) {
+        void *e = a->v->envs[i];
+        for (long t = 0; t < a->steps; t++) {
+            int32_t act[4];
+            if (a->policy == 1) oracle_random_action(e, act); else oracle_heuristic(e, a->policy - 10, act);
+            ostep_t o;
+            oracle_step(e, act, &o);
+            a->acc += o.accepted;
+            if (a->with_obs && a->v->cfg.kind == KIND_DEEPRMSA) oracle_observation(e, obs);
+            if (o.done) oracle_reset(e, 0);
+        }
+    }
+    return NULL;
+}
+
+long oracle_vec_run(void *p, long steps, int policy, int with_obs, int n_threads) {
+    ovec_t *v = (ovec_t *)p;
+    pthread_t th[512]; vec_arg_t args[512];
+    if (n_threads > 512) n_threads = 512;
+    if (n_threads < 1) n_threads = 1;
+    for (int i = 0; i < n_threads; i++) {
+        vec_arg_t a = { v, i, n_threads, steps, policy, with_obs, 0 };
+        args[i] = a;
+        pthread_create(&th[i], NULL, vec_worker, &args[i]);
+    }
+    long acc = 0;
+    for (int i = 0; i < n_threads; i++) { pthread_join(th[i], NULL); acc += args[i].acc; }
+    return acc;
+}
+
+void *oracle_vec_env(void *p, int i) { return ((ovec_t *)p)->envs[i]; }

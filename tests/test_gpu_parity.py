@@ -1,0 +1,242 @@
+"""GPU parity tests: the CUDA step path (through the C ABI / VecEnv) against
+(a) golden vectors recorded from the live reference and (b) the CPU oracle on Philox traffic.
+
+Bars (BASELINE.json north_star): bit-exact accept/block decisions, slot allocations, link
+states, counters and integer observation fields; float64 observations bit-exact (same
+operation order); float32 observations within 1e-6 relative of the reference's float64.
+"""
+import numpy as np
+import pytest
+
+import helpers
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+OBS_RTOL = 1e-6      # north_star: "Within 1e-6 relative: normalised float observations and rewards"
+
+
+def make_env(meta, n_envs, **over):
+    from optical_rl_gym_b200 import OpticalVecEnv
+
+    args = dict(meta["env_args"])
+    kw = dict(traffic="trace", record_decisions=True, collect_info=True, auto_reset=True)
+    kw.update(over)
+    return OpticalVecEnv(meta["kind"], n_envs, helpers.golden_tables(), **kw, **args)
+
+
+def unpack_masks(m, S):
+    """int32 [N, CE, words] -> uint8 bits [N, CE, ceil(S/8)] in np.packbits(little) layout."""
+    b = m.cpu().numpy().view(np.uint8)          # little-endian words -> little bit order bytes
+    return b.reshape(m.shape[0], m.shape[1], -1)[:, :, :(S + 7) // 8]
+
+
+def replay_golden(g, obs_dtype, use_heuristic=False):
+    meta = g["meta"]
+    n, T, kind = meta["n_envs"], meta["T"], meta["kind"]
+    env = make_env(meta, n, obs_dtype=obs_dtype)
+    env.set_trace(g["req_arrival"], g["req_holding"], g["req_src"], g["req_dst"], g["req_bit_rate"])
+    obs = env.reset(full=True)
+    S = env.num_spectrum_resources
+    hid = meta["policy"] if use_heuristic else None
+    nm = g["avail_bits"].shape[0]
+
+    def check_obs(o, t):
+        if kind != "DeepRMSA-v0":
+            assert o is None
+            return
+        got = o.cpu().numpy()
+        if obs_dtype == torch.float64:
+            assert np.array_equal(got, g["obs"][:, t]), ("obs f64", t)
+        else:
+            np.testing.assert_allclose(got, g["obs"][:, t], rtol=OBS_RTOL, atol=0, err_msg="obs f32 step %d" % t)
+
+    check_obs(obs, 0)
+    for t in range(T):
+        req, sid = env.current_requests()
+        assert np.array_equal(req["arrival"], g["req_arrival"][:, t]) and np.array_equal(sid, g["req_id"][:, t]), t
+        if hid is not None:
+            a = env.heuristic(hid)
+            assert np.array_equal(a.cpu().numpy(), g["actions"][:, t]), ("heuristic", t, a.cpu().numpy(), g["actions"][:, t])
+        else:
+            a = torch.as_tensor(g["actions"][:, t], device="cuda")
+        obs, reward, done, info = env.step(a)
+        d = env.decisions.cpu().numpy()
+        assert np.array_equal(d[:, 0], g["accepted"][:, t]), ("accepted", t)
+        assert np.array_equal(d[:, 1], g["path_row"][:, t]), ("path", t)
+        assert np.array_equal(d[:, 2], g["initial_slot"][:, t]), ("slot", t)
+        assert np.array_equal(d[:, 3], g["number_slots"][:, t]), ("n", t)
+        if "core" in g:
+            assert np.array_equal(d[:, 4], g["core"][:, t]) and np.array_equal(d[:, 5], g["mod"][:, t]), ("core/mod", t)
+        assert np.array_equal(reward.cpu().numpy().astype(np.float64), g["reward"][:, t]), ("reward", t)
+        assert np.array_equal(done.cpu().numpy(), g["done"][:, t]), ("done", t)
+        for key in info.keys():
+            assert np.array_equal(info[key].cpu().numpy(), g["info_" + key][:, t]), (key, t)
+        assert np.array_equal(env.counters().cpu().numpy(), g["counters"][:, t]), ("counters", t)
+        check_obs(obs, t + 1)
+        if t % 5 == 0 or t == T - 1:
+            m = unpack_masks(env.export_state()[0], S)
+            assert np.array_equal(m[:nm], g["avail_bits"][:, t]), ("masks", t)
+    m, alloc, now, nheap = env.export_state(allocation=True)
+    avail = env.available_slots().cpu().numpy().reshape(g["final_avail"].shape)
+    assert np.array_equal(avail, g["final_avail"])
+    assert np.array_equal(alloc.cpu().numpy(), g["final_alloc"])
+    assert np.array_equal(now.cpu().numpy(), g["final_now"]) and np.array_equal(nheap.cpu().numpy(), g["final_nheap"])
+    assert int(env.error_flags().abs().sum()) == 0
+    env.close()
+
+
+@pytest.mark.parametrize("name", helpers.golden_names())
+def test_cuda_replays_reference_trace_bit_exact(name):
+    replay_golden(helpers.load_golden(name), torch.float64)
+
+
+@pytest.mark.parametrize("name", [n for n in helpers.golden_names() if n.startswith("deeprmsa")])
+def test_cuda_float32_observations_within_tolerance(name):
+    replay_golden(helpers.load_golden(name), torch.float32)
+
+
+@pytest.mark.parametrize("name", [n for n in helpers.golden_names()
+                                  if helpers.load_golden(n)["meta"]["policy"] in helpers.HEURISTIC_ID])
+def test_cuda_heuristics_match_reference(name):
+    replay_golden(helpers.load_golden(name), torch.float64, use_heuristic=True)
+
+
+# ------------------------------------------------------------------ Philox traffic: CUDA vs oracle
+PHILOX_CASES = [
+    ("DeepRMSA-v0", dict(episode_length=37), "random", 96, 400),
+    ("DeepRMSA-v0", dict(episode_length=50, j=3, allow_rejection=True, mean_service_holding_time=10.0,
+                         node_request_probabilities=None), "sap", 64, 300),
+    ("RMSA-v0", dict(episode_length=50, load=250, mean_service_holding_time=25, allow_rejection=True), "random", 64, 300),
+    ("RMSA-v0", dict(episode_length=50, load=300, mean_service_holding_time=25, allow_rejection=True), "sap_ff", 64, 400),
+    ("RMSA-v0", dict(episode_length=50, load=100, mean_service_holding_time=25, allow_rejection=True,
+                     bit_rate_selection="discrete", num_spectrum_resources=64), "llp_ff", 48, 300),
+    ("RWA-v0", dict(episode_length=64, load=450, mean_service_holding_time=25), "sap_ff", 64, 600),
+    ("RWA-v0", dict(episode_length=64, load=450, mean_service_holding_time=25), "random", 64, 300),
+    ("RMCSA-v0", dict(episode_length=50, load=1200, mean_service_holding_time=25, num_spectrum_resources=64,
+                      num_spatial_resources=7, worst_xt=-84.7, allow_rejection=True), "heuristic", 48, 400),
+    ("RMCSA-v0", dict(episode_length=50, load=400, mean_service_holding_time=25, num_spectrum_resources=100,
+                      num_spatial_resources=3, worst_xt=-84.7, allow_rejection=True), "random", 48, 300),
+]
+
+
+@pytest.mark.parametrize("kind,env_args,policy,n_envs,T", PHILOX_CASES)
+def test_cuda_matches_oracle_on_philox_traffic(kind, env_args, policy, n_envs, T):
+    from optical_rl_gym_b200 import OpticalVecEnv
+    from oracle import oracle
+
+    tables = helpers.golden_tables()
+    seed, base = 77, 1000
+    meta = dict(kind=kind, env_args=env_args)
+    env = OpticalVecEnv(kind, n_envs, tables, traffic="philox", record_decisions=True, obs_dtype=torch.float64,
+                        env_id_base=base, seed=seed, **env_args)
+    okw = helpers.sim_kwargs(meta)
+    if env_args.get("bit_rate_selection") == "discrete":
+        okw["bit_rates"] = [10, 40, 100]
+    oracles = []
+    for i in range(n_envs):
+        o = oracle.OracleEnv(kind, tables, **okw)
+        o.set_philox(seed, base + i)
+        o.reset(full=True)
+        oracles.append(o)
+    pol = {"random": 1}.get(policy)
+    hid = helpers.HEURISTIC_ID.get(policy)
+    ref = [o.rollout(T, policy=pol if pol is not None else 10 + hid, want_obs=(kind == "DeepRMSA-v0")) for o in oracles]
+    for t in range(T):
+        a = env.sample_actions() if pol is not None else env.heuristic(hid)
+        want_a = np.stack([r["actions"][t] for r in ref])
+        assert np.array_equal(a.cpu().numpy(), want_a), ("actions", t)
+        obs, reward, done, info = env.step(a)
+        d = env.decisions.cpu().numpy()
+        want_d = np.stack([r["decisions"][t] for r in ref])
+        assert np.array_equal(d[:, :4], want_d), ("decision", t, d[:4], want_d[:4])
+        assert np.array_equal(reward.cpu().numpy().astype(np.float64), np.array([r["rewards"][t] for r in ref])), t
+        assert np.array_equal(done.cpu().numpy(), np.array([r["dones"][t] for r in ref])), ("done", t)
+        if kind == "DeepRMSA-v0":
+            assert np.array_equal(obs.cpu().numpy(), np.stack([r["obs"][t] for r in ref])), ("obs", t)
+    # final state
+    m, alloc, now, nheap = env.export_state(allocation=True)
+    avail = env.available_slots().cpu().numpy()
+    cnt = env.counters().cpu().numpy()
+    req, sid = env.current_requests()
+    for i, o in enumerate(oracles):
+        oa, oal, onow, onh = o.state()
+        assert np.array_equal(avail[i].reshape(oa.shape), oa), ("avail", i)
+        assert np.array_equal(alloc[i].cpu().numpy(), oal), ("alloc", i)
+        assert now[i].item() == onow and nheap[i].item() == onh
+        assert np.array_equal(cnt[i], o.counters())
+        r = o.request()
+        assert (req["arrival"][i], req["holding"][i], req["src"][i], req["dst"][i], req["bit_rate"][i], sid[i]) == \
+               (r["arrival"], r["holding"], r["src"], r["dst"], r["bit_rate"], r["service_id"])
+    assert int(env.error_flags().abs().sum()) == 0
+    env.close()
+
+
+def test_results_do_not_depend_on_sharding():
+    """Envs are keyed by global id: one batch of 128 == two shards of 64."""
+    from optical_rl_gym_b200 import OpticalVecEnv
+
+    tables = helpers.golden_tables()
+    kw = dict(traffic="philox", seed=5, episode_length=40, record_decisions=True)
+    whole = OpticalVecEnv("DeepRMSA-v0", 128, tables, env_id_base=0, **kw)
+    parts = [OpticalVecEnv("DeepRMSA-v0", 64, tables, env_id_base=b, **kw) for b in (0, 64)]
+    for t in range(200):
+        ow, rw, dw, _ = whole.step(whole.sample_actions())
+        outs = [p.step(p.sample_actions()) for p in parts]
+        assert torch.equal(ow, torch.cat([o[0] for o in outs])) and torch.equal(rw, torch.cat([o[1] for o in outs]))
+        assert torch.equal(dw, torch.cat([o[2] for o in outs]))
+    assert torch.equal(whole.reduce_counters(), parts[0].reduce_counters() + parts[1].reduce_counters())
+    assert torch.equal(whole.reduce_counters()[:8], whole.counters().sum(0))
+
+
+def test_full_size_invariants_65536_envs():
+    """BASELINE.json config[2] size: properties that hold at any scale + a sampled oracle cross-check."""
+    from optical_rl_gym_b200 import OpticalVecEnv
+    from oracle import oracle
+
+    tables = helpers.golden_tables()
+    N, T, seed = 65536, 300, 3
+    env = OpticalVecEnv("DeepRMSA-v0", N, tables, traffic="philox", seed=seed, record_decisions=True)
+    acc = torch.zeros(N, dtype=torch.int64, device="cuda")
+    ndone = torch.zeros(N, dtype=torch.int64, device="cuda")
+    for t in range(T):
+        obs, reward, done, info = env.step(env.sample_actions())
+        acc += (reward > 0)
+        ndone += done
+    cnt = env.counters()
+    assert int(env.error_flags().abs().sum()) == 0
+    assert torch.all(cnt[:, 0] == T + 1) and torch.all(cnt[:, 1] == acc)          # processed / accepted
+    assert torch.all(ndone == T // 999) or env.episode_length != 1000
+    m, alloc, now, nheap = env.export_state(allocation=True)
+    # every busy slot belongs to exactly one live service: popcount(busy) == #cells with an id
+    avail = env.available_slots()
+    assert torch.equal((avail == 0), (alloc.reshape(avail.shape) >= 0))
+    assert torch.all(nheap >= 0) and torch.all(nheap <= acc)
+    assert torch.isfinite(obs).all() and obs.min() >= -1.0001 and obs.max() <= 1.0001 + 12
+    rate = float(acc.sum()) / (N * T)
+    assert 0.25 < rate < 0.6, rate                # random policy at 250 Erlang: ~0.34 in steady state, higher while filling
+    # sampled envs against the oracle (same Philox streams)
+    for i in (0, 1, 4097, 65535):
+        o = oracle.OracleEnv("DeepRMSA-v0", tables, num_slots=100)
+        o.set_philox(seed, i)
+        o.reset(full=True)
+        o.rollout(T, policy=1)
+        oa = o.state()[0]
+        assert np.array_equal(avail[i].cpu().numpy().reshape(oa.shape), oa), i
+        assert np.array_equal(cnt[i].cpu().numpy(), o.counters()), i
+        assert np.array_equal(obs[i].cpu().numpy(), o.observation().astype(np.float32)) or \
+            np.allclose(obs[i].cpu().numpy(), o.observation(), rtol=OBS_RTOL, atol=0), i
+    env.close()
+
+
+def test_rejects_unsupported_and_missing_trace():
+    from optical_rl_gym_b200 import OpticalVecEnv, _native
+
+    tables = helpers.golden_tables()
+    with pytest.raises(_native.NativeError):
+        OpticalVecEnv("RMSA-v0", 4, tables, num_spectrum_resources=320)        # > 128 slots: next-row config
+    env = OpticalVecEnv("RMSA-v0", 4, tables, traffic="trace")
+    with pytest.raises(_native.NativeError):
+        env.reset(full=True)                                                    # no trace set
+    with pytest.raises(TypeError):
+        OpticalVecEnv("RWA-v0", 4, tables, j=3)
