@@ -152,7 +152,7 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     p.auto_reset = cfg->auto_reset ? 1 : 0; p.traffic = cfg->traffic; p.obs_f64 = cfg->obs_dtype == ORLG_OBS_F64;
     p.n_bit_rates = t->num_bit_rates;
     p.br_lo = cfg->bit_rate_lo; p.br_span = cfg->bit_rate_hi - cfg->bit_rate_lo + 1;
-    int br_max = cfg->kind == ORLG_RWA ? 0 : cfg->bit_rate_hi;
+    int br_max = cfg->kind == ORLG_RWA ? 0 : (cfg->bit_rate_hi > 1023 ? cfg->bit_rate_hi : 1023);   // traces may carry any rate <= 1023
     for (int i = 0; i < t->num_bit_rates; i++) br_max = t->bit_rates[i] > br_max ? t->bit_rates[i] : br_max;
     if (br_max < 0 || br_max > 65535) { delete env; return fail(ORLG_E_UNSUPPORTED, "bit rates must be 0..65535"); }
     p.br_max = br_max;

@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
         } else {
             if ((long long)ridx < p.trace_len) {
                 const orlg_request r = p.trace[(size_t)e * p.trace_len + ridx];
-                arrival = r.arrival; holding = r.holding; nsrc = r.src; ndst = r.dst; nbr = r.bit_rate;
+                arrival = r.arrival; holding = r.holding; nsrc = r.src; ndst = r.dst;
+                nbr = min(max(r.bit_rate, 0), p.br_max);
             } else {
                 err |= ORLG_ERR_TRACE_EXHAUSTED;
                 arrival = now; holding = 0.0; nsrc = 0; ndst = 1; nbr = p.br_lo;

@@ -16,6 +16,7 @@ HEURISTICS = {"shortest_path_first_fit": 0, "sp_ff": 0, "sp": 0,
               "least_loaded_path_first_fit": 2, "llp_ff": 2,
               "shortest_available_path_last_fit": 3, "sap_lf": 3}
 ERR_TRACE_EXHAUSTED, ERR_HEAP_OVERFLOW, ERR_NO_SUCH_PATH = 1, 2, 4
+MAX_BIT_RATE = 1023       # bit rates (Gb/s) are tabulated up to here (orlg_api.cu)
 
 
 class Config(C.Structure):

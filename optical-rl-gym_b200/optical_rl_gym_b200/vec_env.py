@@ -167,7 +167,8 @@ class OpticalVecEnv:
         cfg = nat.Config(kind=self.kind, num_envs=self.num_envs, env_id_base=int(env_id_base),
                          num_slots=self.num_spectrum_resources, num_cores=self.num_spatial_resources, j=self.j,
                          episode_length=self.episode_length, allow_rejection=int(self.allow_rejection),
-                         bit_rate_lo=int(a.get("bit_rate_lower_bound", 0)), bit_rate_hi=int(a.get("bit_rate_higher_bound", 0)),
+                         # DeepRMSAEnv cannot change the bounds: it always runs RMSAEnv's defaults
+                         bit_rate_lo=int(a.get("bit_rate_lower_bound", 25.0)), bit_rate_hi=int(a.get("bit_rate_higher_bound", 100.0)),
                          traffic=nat.TRAFFIC_PHILOX if traffic == "philox" else nat.TRAFFIC_TRACE,
                          obs_dtype=nat.OBS_F64 if obs_dtype == torch.float64 else nat.OBS_F32,
                          auto_reset=int(auto_reset), heap_capacity=int(heap_capacity), seed=self.rand_seed,
@@ -262,6 +263,10 @@ class OpticalVecEnv:
         rec["arrival"], rec["holding"] = arrival, np.asarray(holding, np.float64)
         rec["src"], rec["dst"] = np.asarray(src, np.int32), np.asarray(dst, np.int32)
         rec["bit_rate"] = 0 if bit_rate is None else np.asarray(bit_rate, np.int32)
+        if rec["bit_rate"].min() < 0 or rec["bit_rate"].max() > nat.MAX_BIT_RATE:
+            raise ValueError("trace bit rates must lie in 0..%d" % nat.MAX_BIT_RATE)
+        if rec["src"].min() < 0 or max(rec["src"].max(), rec["dst"].max()) >= self.tables.num_nodes or (rec["src"] == rec["dst"]).any():
+            raise ValueError("trace node ids out of range (or src == dst)")
         self._trace = torch.from_numpy(rec.view(np.uint8).reshape(n, T * nat.REQUEST_DTYPE.itemsize)).to(self.device)
         nat.check(self._lib.orlg_set_trace(self._h, _ptr(self._trace), T))
         self.traffic = "trace"
