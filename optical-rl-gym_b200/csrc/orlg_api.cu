@@ -6,7 +6,7 @@
 #include <string>
 #include <vector>
 
-#include "orlg_kernels.cuh"
+#include "orlg_deeprmsa_fast.cuh"
 
 using namespace orlg;
 
@@ -29,6 +29,8 @@ struct orlg_env {
     orlg_config cfg;
     int device;
     int km;                       // KM template instance (5 or 8)
+    bool fast;                    // DeepRMSA fast kernel applicable (NSFNET-class: 22 links, k <= 5)
+    size_t fast_smem;
     size_t obs_smem;
     int64_t state_bytes;
     std::vector<void *> allocs;
@@ -100,7 +102,19 @@ void launch_step_kind(const orlg_env *env, const StepIO &io, int mode, cudaStrea
     else step_kernel<KIND, KMAX><<<blocks, STEP_THREADS, smem, s>>>(env->p, io, mode);
 }
 
+template <int JT, bool OBS64>
+void launch_fast(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s) {
+    const int blocks = (env->p.n + FAST_THREADS - 1) / FAST_THREADS;
+    deeprmsa_fast_kernel<22, 5, JT, OBS64><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode);
+}
+
 int launch_step(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s) {
+    if (env->fast) {
+        if (env->p.J == 1) { if (env->p.obs_f64) launch_fast<1, true>(env, io, mode, s); else launch_fast<1, false>(env, io, mode, s); }
+        else { if (env->p.obs_f64) launch_fast<0, true>(env, io, mode, s); else launch_fast<0, false>(env, io, mode, s); }
+        CUDA_OK(cudaGetLastError());
+        return ORLG_OK;
+    }
     switch (env->p.kind) {
     case ORLG_RWA: launch_step_kind<ORLG_RWA>(env, io, mode, s); break;
     case ORLG_RMSA: launch_step_kind<ORLG_RMSA>(env, io, mode, s); break;
@@ -159,7 +173,7 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     p.seed = cfg->seed; p.env_id_base = cfg->env_id_base;
     p.mean_holding = cfg->mean_holding; p.mean_iat = cfg->mean_iat;
     p.obs_dim = cfg->kind == ORLG_DEEPRMSA ? 1 + 2 * p.N + (2 * J + 3) * p.k : 0;
-    p.cand_stride = ((p.k * J + 3) / 4) * 4;
+    p.cand_stride = ((p.k * J + 7) / 8) * 8;
     env->km = p.k <= 5 ? 5 : KMAX;
     env->obs_smem = (size_t)STEP_THREADS * p.obs_dim * (p.obs_f64 ? 8 : 4);
     if (env->obs_smem > 200 * 1024) { delete env; return fail(ORLG_E_UNSUPPORTED, "observation too large for the staging tile"); }
@@ -172,8 +186,8 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
         double hard = cfg->kind == ORLG_RWA ? (double)p.E * p.S * C : (double)p.E * p.S * C / 2.0;
         cap = (int)std::ceil(want < hard ? want : hard) + (int)HEAP_ROOT + 1;
     }
-    cap = ((cap + 3) / 4) * 4;
-    if (cap < 8) cap = 8;
+    cap = ((cap + (int)HD - 1) / (int)HD) * (int)HD;
+    if (cap < 2 * (int)HD) cap = 2 * (int)HD;
     p.heap_cap = cap;
 
     // ---- tables
@@ -234,10 +248,59 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     if (!rc) rc = dev_alloc(env, &p.req_index, n);
     if (!rc) rc = dev_alloc(env, &p.nheap, n);
     if (!rc) rc = dev_alloc(env, &p.heap_min, n);
-    if (!rc) rc = dev_alloc(env, &p.heap, n * (size_t)p.heap_cap, false);
+    if (!rc) rc = dev_alloc(env, &p.heap_time, n * (size_t)p.heap_cap, false);
+    if (!rc) rc = dev_alloc(env, &p.heap_pay, n * (size_t)p.heap_cap, false);
     if (!rc) rc = dev_alloc(env, &p.cand, n * (size_t)p.cand_stride);
     if (!rc) rc = dev_alloc(env, &p.errors, n);
     if (rc) { orlg_destroy(env); return rc; }
+
+    // ---- fast DeepRMSA kernel: small tables packed for shared-memory staging
+    env->fast = false;
+    if (cfg->kind == ORLG_DEEPRMSA && p.E == 22 && p.k <= 5 && P <= 65535 && se_max <= 15 && !std::getenv("ORLG_FORCE_GENERIC")) {
+        std::vector<unsigned char> blob;
+        auto put = [&blob](const void *src, size_t bytes) {
+            size_t off = (blob.size() + 15) / 16 * 16;
+            blob.resize(off + bytes);
+            std::memcpy(blob.data() + off, src, bytes);
+            return (int)off;
+        };
+        std::vector<unsigned short> pf16(NN);
+        for (int i = 0; i < NN; i++) pf16[i] = (unsigned short)(pair_first[i] < 0 ? 0 : pair_first[i]);
+        std::vector<unsigned char> pse(P);
+        for (int r = 0; r < P; r++) pse[r] = (unsigned char)((meta[r] >> 8) & 0xff);
+        std::vector<unsigned char> ns128((size_t)(se_max + 1) * 128, 1);
+        for (int se = 1; se <= se_max; se++)
+            for (int b = 0; b < 128 && b <= br_max; b++) ns128[(size_t)se * 128 + b] = nslots[(size_t)se * (br_max + 1) + b];
+        std::vector<float> pos(p.S + 1), nsl(32);
+        for (int v = 0; v <= p.S; v++) pos[v] = (float)(2 * v - p.S) / (float)p.S;      // IEEE f32 division == __fdiv_rn
+        for (int v = 0; v < 32; v++) nsl[v] = (float)(2 * v - 11) / 7.0f;
+        p.off_pair_first = put(pf16.data(), pf16.size() * 2);
+        p.off_pair_count = put(pair_count.data(), pair_count.size());
+        p.off_path_lm = put(linkmask.data(), linkmask.size() * 4);
+        p.off_path_se = put(pse.data(), pse.size());
+        p.off_nslots = put(ns128.data(), ns128.size());
+        p.off_node_thr = put(node_thr.data(), node_thr.size() * 4);
+        p.off_pos = put(pos.data(), pos.size() * 4);
+        p.off_nsl = put(nsl.data(), nsl.size() * 4);
+        blob.resize((blob.size() + 15) / 16 * 16);
+        if (blob.size() <= 24 * 1024) {
+            std::vector<uint4> blob4(blob.size() / 16);
+            std::memcpy(blob4.data(), blob.data(), blob.size());
+            rc = dev_upload(env, &p.tab_blob, blob4);
+            if (rc) { orlg_destroy(env); return rc; }
+            p.tab_vec = (int)blob4.size();
+            env->fast = true;
+            env->fast_smem = blob.size() + (size_t)FAST_THREADS * p.obs_dim * (p.obs_f64 ? 8 : 4);
+            cudaError_t ea = cudaSuccess;
+            if (env->fast_smem > 48 * 1024) {
+                ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<22, 5, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
+                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<22, 5, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
+                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<22, 5, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
+                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<22, 5, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
+            }
+            if (ea != cudaSuccess) env->fast = false;
+        }
+    }
 
     if (env->obs_smem > 48 * 1024) {
         cudaError_t e1 = cudaFuncSetAttribute(step_kernel<ORLG_DEEPRMSA, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->obs_smem);

@@ -175,72 +175,76 @@ __device__ __forceinline__ double neg_log_u32(uint32_t r) {
     return __dadd_rn(22.180709777918249, -lnx);
 }
 
-// ---------------------------------------------------------------- per-env release-time heap (4-ary, HBM)
-// Entry = 16 B {f64 release time, u64 payload}.  Slots 0..2 of an env's heap region are unused so that
-// the 4 children of slot s (4s-8 .. 4s-5) are one 64-byte aligned group: one fetch per level.
+// ---------------------------------------------------------------- per-env release-time heap (8-ary, HBM)
+// Two parallel arrays per env: release times (f64) and payloads (u64).  Slots 0..HD-2 are unused so
+// that the HD children of slot s (HD*(s-HD+2) ...) are one 64-byte aligned group of times: a level
+// of a sift-down is one independent 64-byte fetch, and ~86 live services need only 2-3 levels.
 // Replaces heapq in optical_network_env.py:143-154 / rmsa_env.py:591-597 (pop order by time is
 // identical for any heap arity because release times are distinct).
-constexpr unsigned HEAP_ROOT = 3;
+constexpr unsigned HD = 8;
+constexpr unsigned HEAP_ROOT = HD - 1;
+#define ORLG_INF __longlong_as_double(0x7ff0000000000000LL)
 
-__device__ __forceinline__ double ent_time(const uint4 &e) {
-    return __longlong_as_double(((long long)e.y << 32) | (long long)e.x);
-}
-__device__ __forceinline__ unsigned long long ent_payload(const uint4 &e) {
-    return ((unsigned long long)e.w << 32) | (unsigned long long)e.z;
-}
-__device__ __forceinline__ uint4 make_ent(double t, unsigned long long payload) {
-    long long b = __double_as_longlong(t);
-    return make_uint4((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)payload, (uint32_t)(payload >> 32));
-}
+__device__ __forceinline__ unsigned heap_first_child(unsigned s) { return HD * (s - HD + 2); }
+__device__ __forceinline__ unsigned heap_parent(unsigned c) { return c / HD + HD - 2; }
 
-__device__ __forceinline__ void heap_push(uint4 *h, unsigned &n, double t, unsigned long long payload) {
+__device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
+__device__ __forceinline__ void heap_push(double *ht, unsigned long long *hp, unsigned &n, double t,
+                                          unsigned long long payload) {
     unsigned i = n + HEAP_ROOT;
     n++;
     while (i > HEAP_ROOT) {
-        unsigned p = (i >> 2) + 2;
-        uint4 pe = h[p];
-        if (ent_time(pe) <= t) break;
-        h[i] = pe;
+        unsigned p = heap_parent(i);
+        double pt = ht[p];
+        if (pt <= t) break;
+        ht[i] = pt;
+        hp[i] = hp[p];
         i = p;
     }
-    h[i] = make_ent(t, payload);
+    ht[i] = t;
+    hp[i] = payload;
 }
 
 // pops the root; returns its payload and the new minimum time (+inf when empty)
-__device__ __forceinline__ unsigned long long heap_pop(uint4 *h, unsigned &n, double &new_min) {
-    uint4 top = h[HEAP_ROOT];
+__device__ __forceinline__ unsigned long long heap_pop(double *ht, unsigned long long *hp, unsigned &n, double &new_min) {
+    const unsigned long long top = hp[HEAP_ROOT];
     n--;
     if (n == 0) {
-        new_min = __longlong_as_double(0x7ff0000000000000LL);
-        return ent_payload(top);
+        new_min = ORLG_INF;
+        return top;
     }
-    unsigned end = n + HEAP_ROOT;     // valid slots [HEAP_ROOT, end); the old last element sits at `end`
-    uint4 last = h[end];
-    double lt = ent_time(last);
+    const unsigned end = n + HEAP_ROOT;      // valid slots [HEAP_ROOT, end); the old last element sits at `end`
+    const double lt = ht[end];
+    const unsigned long long lp = hp[end];
     unsigned i = HEAP_ROOT;
     bool first = true;
     new_min = lt;
     for (;;) {
-        unsigned c0 = 4 * i - 8;
+        const unsigned c0 = heap_first_child(i);
         if (c0 >= end) break;
-        uint4 best = h[c0];
-        unsigned bi = c0;
-        double bt = ent_time(best);
+        const double2 *g = reinterpret_cast<const double2 *>(ht + c0);
+        double tv[HD];
 #pragma unroll
-        for (unsigned q = 1; q < 4; q++) {
-            if (c0 + q < end) {
-                uint4 ce = h[c0 + q];
-                double ct = ent_time(ce);
-                if (ct < bt) { bt = ct; best = ce; bi = c0 + q; }
-            }
+        for (unsigned q = 0; q < HD / 2; q++) {
+            double2 v = g[q];
+            tv[2 * q] = v.x; tv[2 * q + 1] = v.y;
+        }
+        double bt = tv[0];
+        unsigned bi = c0;
+#pragma unroll
+        for (unsigned q = 1; q < HD; q++) {
+            if (c0 + q < end && tv[q] < bt) { bt = tv[q]; bi = c0 + q; }
         }
         if (lt <= bt) break;
-        h[i] = best;
+        ht[i] = bt;
+        hp[i] = hp[bi];
         if (first) { new_min = bt; first = false; }
         i = bi;
     }
-    h[i] = last;
-    return ent_payload(top);
+    ht[i] = lt;
+    hp[i] = lp;
+    return top;
 }
 
 // payload: path row (20 bits) | start (9) | slots (8) | core (5) | service id (22)

@@ -39,6 +39,10 @@ struct Params {
     const int *bit_rates;              // [n_bit_rates]
     const orlg_request *trace;         // [n * trace_len]
     long long trace_len;
+    // packed copy of the small tables, staged in shared memory by the fast kernel (byte offsets)
+    const uint4 *tab_blob;
+    int tab_vec;                       // size in 16-byte units
+    int off_pair_first, off_pair_count, off_path_lm, off_path_se, off_nslots, off_node_thr, off_pos, off_nsl;
     // ---- per-env state (struct of arrays)
     uint4 *masks;                      // [C*E][n]
     double *now;                       // [n] current_time
@@ -48,7 +52,8 @@ struct Params {
     unsigned *req_index;               // [n] requests generated since the last full reset
     unsigned *nheap;                   // [n]
     double *heap_min;                  // [n] earliest release time (+inf if none)
-    uint4 *heap;                       // [n][heap_cap]
+    double *heap_time;                 // [n][heap_cap] release times (8-ary heap, see orlg_device.cuh)
+    unsigned long long *heap_pay;      // [n][heap_cap] packed services
     unsigned char *cand;               // [n][cand_stride] first-fit block starts of the pending request
     unsigned *errors;                  // [n]
 };
@@ -98,7 +103,7 @@ __device__ __forceinline__ int pick_thr(const unsigned *thr, int n, unsigned r) 
 }
 
 // _next_service's draws (rmsa_env.py:548-561) from the counter-based generator
-__device__ __forceinline__ void philox_request(const Params &p, int env, unsigned ridx, double now,
+__device__ __forceinline__ void philox_request(const Params &p, const unsigned *node_thr, int env, unsigned ridx, double now,
                                                double &arrival, double &holding, int &src, int &dst, int &br) {
     unsigned long long gid = (unsigned long long)(p.env_id_base + env);
     uint32_t c[4] = {ridx, 0u, (uint32_t)gid, 0u};
@@ -106,15 +111,15 @@ __device__ __forceinline__ void philox_request(const Params &p, int env, unsigne
     arrival = __dadd_rn(now, __dmul_rn(neg_log_u32(c[0]), p.mean_iat));
     holding = __dmul_rn(neg_log_u32(c[1]), p.mean_holding);
     int n = p.N;
-    src = pick_thr(p.node_thr, n, c[2]);
-    unsigned long long lo = src ? p.node_thr[src - 1] : 0u;
-    unsigned long long hi = (src == n - 1) ? 4294967296ULL : (unsigned long long)p.node_thr[src];
+    src = pick_thr(node_thr, n, c[2]);
+    unsigned long long lo = src ? node_thr[src - 1] : 0u;
+    unsigned long long hi = (src == n - 1) ? 4294967296ULL : (unsigned long long)node_thr[src];
     unsigned long long mass = hi - lo;
     unsigned long long tt = ((unsigned long long)c[3] * (4294967296ULL - mass)) >> 32;
     if (tt >= lo) tt += mass;
     dst = n - 1;
     for (int i = 0; i < n - 1; i++)
-        if (tt < (unsigned long long)p.node_thr[i]) { dst = i; break; }
+        if (tt < (unsigned long long)node_thr[i]) { dst = i; break; }
     if (dst == src) dst = (src + 1) % n;
     br = 0;
     if (p.kind != ORLG_RWA) {
@@ -156,7 +161,8 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
     unsigned nheap = p.nheap[e];
     double hmin = p.heap_min[e];
     unsigned err = p.errors[e];
-    uint4 *heap = p.heap + (size_t)e * p.heap_cap;
+    double *ht = p.heap_time + (size_t)e * p.heap_cap;
+    unsigned long long *hp = p.heap_pay + (size_t)e * p.heap_cap;
 
     bool accepted = false;
     int d_row = -1, d_start = -1, d_n = -1, d_core = -1, d_mod = -1;
@@ -168,7 +174,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
         Bits full = bits_range(0, p.S);
         if (live)
             for (int l = 0; l < p.C * p.E; l++) p.masks[(size_t)l * p.n + env] = bits_to(full);
-        now = 0.0; nheap = 0; hmin = __longlong_as_double(0x7ff0000000000000LL); ridx = 0; err = 0;
+        now = 0.0; nheap = 0; hmin = ORLG_INF; ridx = 0; err = 0;
 #pragma unroll
         for (int q = 0; q < 8; q++) cnt[q] = 0;
     }
@@ -245,7 +251,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
             if (live) {
                 path_update(p, env, lm, core, bits_range(start, start + n), false);
                 double rel = __dadd_rn(now, hold);          // arrival_time + holding_time (now == arrival)
-                heap_push(heap, nheap, rel, pack_service(row, start, n, core, sid));
+                heap_push(ht, hp, nheap, rel, pack_service(row, start, n, core, sid));
                 hmin = fmin(hmin, rel);
             }
             cnt[1] += 1; cnt[3] += 1;                        // services_accepted (+episode)
@@ -276,7 +282,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
         double arrival, holding;
         int nsrc, ndst, nbr;
         if (p.traffic == ORLG_TRAFFIC_PHILOX) {
-            philox_request(p, e, ridx, now, arrival, holding, nsrc, ndst, nbr);
+            philox_request(p, p.node_thr, e, ridx, now, arrival, holding, nsrc, ndst, nbr);
         } else {
             if ((long long)ridx < p.trace_len) {
                 const orlg_request r = p.trace[(size_t)e * p.trace_len + ridx];
@@ -297,7 +303,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
         }
         // release every service whose time has come (rmsa_env.py:591-597)
         while (nheap > 0 && hmin <= now) {
-            unsigned long long pl = heap_pop(heap, nheap, hmin);
+            unsigned long long pl = heap_pop(ht, hp, nheap, hmin);
             int rs = svc_start(pl);
             if (live) path_update(p, env, p.path_linkmask[svc_row(pl)], svc_core(pl), bits_range(rs, rs + svc_slots(pl)), true);
         }
@@ -575,10 +581,10 @@ __global__ void export_kernel(const Params p, unsigned *masks_out, int *alloc_ou
         // spectrum_slots_allocation rebuilt from the live services (rmsa_env.py:386-389)
         int *o = alloc_out + (size_t)env * CE * p.S;
         for (int q = 0; q < CE * p.S; q++) o[q] = -1;
-        const uint4 *h = p.heap + (size_t)env * p.heap_cap;
+        const unsigned long long *h = p.heap_pay + (size_t)env * p.heap_cap;
         const unsigned nh = p.nheap[env];
         for (unsigned s = 0; s < nh; s++) {
-            unsigned long long pl = ent_payload(h[HEAP_ROOT + s]);
+            unsigned long long pl = h[HEAP_ROOT + s];
             unsigned lm = p.path_linkmask[svc_row(pl)];
             while (lm) {
                 int l = __ffs(lm) - 1;
