@@ -105,7 +105,7 @@ void launch_step_kind(const orlg_env *env, const StepIO &io, int mode, cudaStrea
 template <int JT, bool OBS64>
 void launch_fast(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s) {
     const int blocks = (env->p.n + FAST_THREADS - 1) / FAST_THREADS;
-    deeprmsa_fast_kernel<22, 5, JT, OBS64><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode);
+    deeprmsa_fast_kernel<5, JT, OBS64><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode);
 }
 
 int launch_step(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s) {
@@ -184,10 +184,9 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
         double load = cfg->mean_holding / cfg->mean_iat;
         double want = load + 8.0 * std::sqrt(load) + 16.0;
         double hard = cfg->kind == ORLG_RWA ? (double)p.E * p.S * C : (double)p.E * p.S * C / 2.0;
-        cap = (int)std::ceil(want < hard ? want : hard) + (int)HEAP_ROOT + 1;
+        cap = (int)std::ceil(want < hard ? want : hard);
     }
-    cap = ((cap + (int)HD - 1) / (int)HD) * (int)HD;
-    if (cap < 2 * (int)HD) cap = 2 * (int)HD;
+    if (cap < 8) cap = 8;
     p.heap_cap = cap;
 
     // ---- tables
@@ -248,15 +247,15 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     if (!rc) rc = dev_alloc(env, &p.req_index, n);
     if (!rc) rc = dev_alloc(env, &p.nheap, n);
     if (!rc) rc = dev_alloc(env, &p.heap_min, n);
-    if (!rc) rc = dev_alloc(env, &p.heap_time, n * (size_t)p.heap_cap, false);
-    if (!rc) rc = dev_alloc(env, &p.heap_pay, n * (size_t)p.heap_cap, false);
+    if (!rc) rc = dev_alloc(env, &p.ev_time, n * (size_t)p.heap_cap, false);
+    if (!rc) rc = dev_alloc(env, &p.ev_pay, n * (size_t)p.heap_cap, false);
     if (!rc) rc = dev_alloc(env, &p.cand, n * (size_t)p.cand_stride);
     if (!rc) rc = dev_alloc(env, &p.errors, n);
     if (rc) { orlg_destroy(env); return rc; }
 
     // ---- fast DeepRMSA kernel: small tables packed for shared-memory staging
     env->fast = false;
-    if (cfg->kind == ORLG_DEEPRMSA && p.E == 22 && p.k <= 5 && P <= 65535 && se_max <= 15 && !std::getenv("ORLG_FORCE_GENERIC")) {
+    if (cfg->kind == ORLG_DEEPRMSA && p.k <= 5 && P <= 65535 && se_max <= 15 && !std::getenv("ORLG_FORCE_GENERIC")) {
         std::vector<unsigned char> blob;
         auto put = [&blob](const void *src, size_t bytes) {
             size_t off = (blob.size() + 15) / 16 * 16;
@@ -283,20 +282,24 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
         p.off_pos = put(pos.data(), pos.size() * 4);
         p.off_nsl = put(nsl.data(), nsl.size() * 4);
         blob.resize((blob.size() + 15) / 16 * 16);
-        if (blob.size() <= 24 * 1024) {
+        if (blob.size() <= 24 * 1024 && blob.size() + (size_t)FAST_THREADS * 16 * 32 <= 100 * 1024) {
             std::vector<uint4> blob4(blob.size() / 16);
             std::memcpy(blob4.data(), blob.data(), blob.size());
             rc = dev_upload(env, &p.tab_blob, blob4);
             if (rc) { orlg_destroy(env); return rc; }
             p.tab_vec = (int)blob4.size();
             env->fast = true;
-            env->fast_smem = blob.size() + (size_t)FAST_THREADS * p.obs_dim * (p.obs_f64 ? 8 : 4);
+            size_t per_thread = (size_t)p.obs_dim * (p.obs_f64 ? 8 : 4);      // observation tile overlays the mask area
+            if (per_thread < (size_t)p.E * 16) per_thread = (size_t)p.E * 16;
+            env->fast_smem = blob.size() + (size_t)FAST_THREADS * per_thread;
+            p.node_top_step = 1;
+            while (p.node_top_step * 2 <= p.N - 1) p.node_top_step *= 2;
             cudaError_t ea = cudaSuccess;
             if (env->fast_smem > 48 * 1024) {
-                ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<22, 5, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
-                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<22, 5, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
-                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<22, 5, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
-                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<22, 5, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
+                ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<5, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
+                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<5, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
+                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<5, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
+                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<5, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
             }
             if (ea != cudaSuccess) env->fast = false;
         }
@@ -322,7 +325,7 @@ int orlg_destroy(orlg_env *env) {
 int orlg_action_dim(const orlg_env *env) { return env->p.kind == ORLG_DEEPRMSA ? 1 : (env->p.kind == ORLG_RMCSA ? 4 : 2); }
 int orlg_obs_dim(const orlg_env *env) { return env->p.obs_dim; }
 int orlg_mask_words(const orlg_env *env) { (void)env; return NW; }
-int orlg_heap_capacity(const orlg_env *env) { return env->p.heap_cap - (int)HEAP_ROOT; }
+int orlg_heap_capacity(const orlg_env *env) { return env->p.heap_cap; }
 int64_t orlg_state_bytes(const orlg_env *env) { return env->state_bytes; }
 
 int orlg_set_trace(orlg_env *env, const orlg_request *trace_dev, int64_t trace_len) {

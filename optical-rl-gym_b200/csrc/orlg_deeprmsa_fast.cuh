@@ -1,23 +1,37 @@
 // orlg_deeprmsa_fast.cuh -- latency-oriented DeepRMSA step kernel (the headline path).
 //
 // Same semantics as step_kernel<ORLG_DEEPRMSA> (orlg_kernels.cuh), reorganised so that one thread's
-// step is ONE round trip to HBM plus the release-heap chain:
-//   * all E link masks of the env (E x 16 B, coalesced across the warp) and the scalar block are
-//     requested at kernel entry and stay in registers; allocation, releases and the candidate-path
-//     AND-reduction are register-only, branch-free sweeps over the E links; only dirty links are
-//     written back;
+// step is ONE round trip to HBM plus the release-heap chain, with few registers:
+//   * the E link masks of the env (E x 16 B, contiguous across the warp) are brought into shared
+//     memory with cp.async (no registers, L1 bypass) at kernel entry, overlapping the scalar loads,
+//     the traffic draw and the heap work; allocation, releases and the candidate-path AND-reduction
+//     then index them dynamically in shared memory ([link][thread] layout: conflict-free LDS.128);
+//     only dirty links are written back;
 //   * the read-only topology tables (pair -> paths, path -> link bitmap / spectral efficiency,
 //     slots-per-bit-rate, node CDF, f32 normalisation tables) are staged once per CTA in shared memory;
-//   * the 5 candidate paths' block features are straight-line code (no data-dependent loops for j = 1),
-//     so their instruction streams interleave;
-//   * the observation tile of the CTA is staged in shared memory and written with full-line stores.
+//   * the observation tile of the CTA overlays the mask area once the masks are dead and is written
+//     to HBM with full-line stores.
 #pragma once
 #include "orlg_kernels.cuh"
 
 namespace orlg {
 
-constexpr int FAST_THREADS = 64;
-constexpr int FAST_MIN_BLOCKS = 7;     // 448 threads/SM x 148 SMs >= 65536 envs in one wave
+#ifndef ORLG_FAST_THREADS
+#define ORLG_FAST_THREADS 128
+#endif
+#ifndef ORLG_FAST_MIN_BLOCKS
+#define ORLG_FAST_MIN_BLOCKS 4
+#endif
+constexpr int FAST_THREADS = ORLG_FAST_THREADS;
+constexpr int FAST_MIN_BLOCKS = ORLG_FAST_MIN_BLOCKS;     // threads/SM x 148 SMs >= 65536 envs in one wave
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ Bits bits_runs_ge_flat(const Bits &a, int n) {
     // shift-AND doubling without a data-dependent loop for n <= 16 (larger n: generic path)
@@ -54,7 +68,15 @@ __device__ __forceinline__ int bits_run_length_flat(const Bits &a, int start) {
     return (pos < 0 ? MAX_SLOTS : pos) - start;
 }
 
-template <int ET, int KM, int JT, bool OBS64>
+// first i in [0, n-1] with r < thr[i] (n-1 if none): same result as the linear scan of pick_thr
+__device__ __forceinline__ int pick_thr_bsearch(const unsigned *thr, int n, int top_step, unsigned r) {
+    int i = 0;
+    for (int step = top_step; step > 0; step >>= 1)
+        if (i + step <= n - 1 && r >= thr[i + step - 1]) i += step;
+    return i;
+}
+
+template <int KM, int JT, bool OBS64>
 __global__ void __launch_bounds__(FAST_THREADS, FAST_MIN_BLOCKS)
 deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -63,18 +85,26 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
     const bool live = env < p.n;
     const int e = live ? env : p.n - 1;
     const int J = JT == 1 ? 1 : p.J;
+    const int E = p.E;
+    uint4 *sm = reinterpret_cast<uint4 *>(smem + p.tab_vec * 16) + tid;      // this thread's masks: sm[l * FAST_THREADS]
 
-    // ---------------- stage 1: every load whose address depends only on the env id
-    uint4 M[ET];
-    if (mode != MODE_FULL_RESET) {
-        const uint4 *mr = p.masks + e;
-#pragma unroll
-        for (int l = 0; l < ET; l++) M[l] = mr[(size_t)l * p.n];
-    } else {
-        uint4 full = bits_to(bits_range(0, p.S));
-#pragma unroll
-        for (int l = 0; l < ET; l++) M[l] = full;
+    // ---------------- stage 0: asynchronous copies (group 0 = tables, group 1 = this env's link masks)
+    {
+        uint4 *dst = reinterpret_cast<uint4 *>(smem);
+        for (int i = tid; i < p.tab_vec; i += FAST_THREADS) cp_async16(dst + i, p.tab_blob + i);
+        cp_async_commit();
+        if (mode != MODE_FULL_RESET) {
+            const uint4 *mr = p.masks + e;
+            unsigned sdst = (unsigned)__cvta_generic_to_shared(sm);
+            for (int l = 0; l < E; l++) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(mr) : "memory");
+                sdst += FAST_THREADS * 16;
+                mr += p.n;
+            }
+        }
+        cp_async_commit();
     }
+    // ---------------- stage 1: the scalar block
     double now = p.now[e];
     double hold = p.cur_hold[e];
     uint2 rq = p.cur_req[e];
@@ -88,14 +118,8 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
     const int act = (mode == MODE_STEP) ? io.actions[e] : -1;
     unsigned long long candw = 0;
     if (p.cand_stride == 8) candw = *reinterpret_cast<const unsigned long long *>(p.cand + (size_t)e * 8);
-    double *ht = p.heap_time + (size_t)e * p.heap_cap;
-    unsigned long long *hp = p.heap_pay + (size_t)e * p.heap_cap;
+    const EventTable ev = {p.ev_time, p.ev_pay, (size_t)p.n};
 
-    // ---------------- topology tables -> shared memory (one copy per CTA)
-    {
-        uint4 *dst = reinterpret_cast<uint4 *>(smem);
-        for (int i = tid; i < p.tab_vec; i += FAST_THREADS) dst[i] = p.tab_blob[i];
-    }
     const unsigned short *s_pair_first = reinterpret_cast<const unsigned short *>(smem + p.off_pair_first);
     const unsigned char *s_pair_count = smem + p.off_pair_count;
     const unsigned *s_path_lm = reinterpret_cast<const unsigned *>(smem + p.off_path_lm);
@@ -104,58 +128,54 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
     const unsigned *s_node_thr = reinterpret_cast<const unsigned *>(smem + p.off_node_thr);
     const float *s_pos = reinterpret_cast<const float *>(smem + p.off_pos);     // (2v - S) / S
     const float *s_nsl = reinterpret_cast<const float *>(smem + p.off_nsl);     // (2n - 11) / 7, n < 32
-    unsigned char *stage = smem + p.tab_vec * 16;
-    __syncthreads();
+
+    cp_async_wait<1>();          // tables landed (this thread's part) ...
+    __syncthreads();             // ... and everybody else's
 
     int src = rq.x & 0xff, dst = (rq.x >> 8) & 0xff, br = (int)(rq.x >> 16), sid = (int)rq.y;
     bool accepted = false, done = false;
     int d_row = -1, d_start = -1, d_n = -1;
     unsigned dirty = 0;
+    int npaths = 0;
+    int ns[KM];
+    Bits A[KM];
 
     if (mode == MODE_FULL_RESET) {
         now = 0.0; nheap = 0; hmin = ORLG_INF; ridx = 0; err = 0;
-        dirty = 0xFFFFFFFFu;
+        dirty = E >= 32 ? 0xFFFFFFFFu : ((1u << E) - 1u);
+        const uint4 full = bits_to(bits_range(0, p.S));
+        for (int l = 0; l < E; l++) sm[l * FAST_THREADS] = full;
 #pragma unroll
         for (int q = 0; q < 8; q++) cnt[q] = 0;
     }
 
     if (live) {
+        // ============ Phase A decision (deeprmsa_env.py:48-58): needs no mask, only the cached block starts
+        int a_row = 0, a_start = 0, a_n = 0;
+        unsigned a_lm = 0;
         if (mode == MODE_STEP) {
-            // ============ Phase A (deeprmsa_env.py:48-58 -> rmsa_env.py:163-209) ============
-            if (hmin <= now + 4.0 * p.mean_iat) {       // a release is likely this step: warm the heap's first level
-                prefetch_l2(ht + HD);
-                prefetch_l2(hp + HEAP_ROOT);
-            }
             const int pair = src * p.N + dst;
             const int first = s_pair_first[pair];
-            const int npaths = s_pair_count[pair];
+            const int np_a = s_pair_count[pair];
             if (act >= 0 && act < p.k * J) {
                 const int route = JT == 1 ? act : act / J;
-                if (route < npaths) {
-                    unsigned st = p.cand_stride == 8 ? (unsigned)((candw >> (8 * act)) & 0xffu)
-                                                     : (unsigned)p.cand[(size_t)e * p.cand_stride + act];
+                if (route < np_a) {
+                    const unsigned st = p.cand_stride == 8 ? (unsigned)((candw >> (8 * act)) & 0xffu)
+                                                           : (unsigned)p.cand[(size_t)e * p.cand_stride + act];
                     if (st != CAND_NONE) {
-                        if (nheap + HEAP_ROOT + 1 > (unsigned)p.heap_cap) {
+                        if (nheap + 1 > (unsigned)p.heap_cap) {
                             err |= ORLG_ERR_HEAP_OVERFLOW;
                         } else {
-                            const int row = first + route;
-                            const int se = s_path_se[row];
-                            const int n = br < 128 ? s_nslots[se * 128 + br] : p.nslots[se * (p.br_max + 1) + br];
-                            const unsigned lm = s_path_lm[row];
-                            const Bits rm = bits_range((int)st, (int)st + n);
-#pragma unroll
-                            for (int l = 0; l < ET; l++) {           // _provision_path: clear [start, start+n) on the path's links
-                                const unsigned sel = 0u - ((lm >> l) & 1u);
-                                M[l].x &= ~(rm.w[0] & sel); M[l].y &= ~(rm.w[1] & sel);
-                                M[l].z &= ~(rm.w[2] & sel); M[l].w &= ~(rm.w[3] & sel);
-                            }
-                            dirty |= lm;
+                            a_row = first + route;
+                            const int se = s_path_se[a_row];
+                            a_n = br < 128 ? s_nslots[se * 128 + br] : p.nslots[se * (p.br_max + 1) + br];
+                            a_lm = s_path_lm[a_row];
+                            a_start = (int)st;
                             const double rel = __dadd_rn(now, hold);
-                            heap_push(ht, hp, nheap, rel, pack_service(row, (int)st, n, 0, sid));
-                            hmin = fmin(hmin, rel);
+                            events_push(ev, env, nheap, hmin, rel, pack_service(a_row, a_start, a_n, 0, sid));
                             cnt[1] += 1; cnt[3] += 1; cnt[5] += br; cnt[7] += br;
                             accepted = true;
-                            d_row = row; d_start = (int)st; d_n = n;
+                            d_row = a_row; d_start = a_start; d_n = a_n;
                         }
                     }
                 } else {
@@ -173,12 +193,29 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             }
         }
 
+        // ============ Phase B draw: _next_service (rmsa_env.py:545-580)
         if (mode == MODE_STEP || mode == MODE_FULL_RESET) {
-            // ============ Phase B: _next_service (rmsa_env.py:545-597) ============
             double arrival, holding;
             int nsrc, ndst, nbr;
             if (p.traffic == ORLG_TRAFFIC_PHILOX) {
-                philox_request(p, s_node_thr, e, ridx, now, arrival, holding, nsrc, ndst, nbr);
+                const unsigned long long gid = (unsigned long long)(p.env_id_base + e);
+                uint32_t c[4] = {ridx, 0u, (uint32_t)gid, 0u};
+                uint32_t d[4] = {ridx, 0u, (uint32_t)gid, 1u};
+                philox4x32_10(c, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+                philox4x32_10(d, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+                arrival = __dadd_rn(now, __dmul_rn(neg_log_u32(c[0]), p.mean_iat));
+                holding = __dmul_rn(neg_log_u32(c[1]), p.mean_holding);
+                const int n = p.N;
+                nsrc = pick_thr_bsearch(s_node_thr, n, p.node_top_step, c[2]);
+                const unsigned lo = nsrc ? s_node_thr[nsrc - 1] : 0u;
+                const unsigned long long hi = (nsrc == n - 1) ? 4294967296ULL : (unsigned long long)s_node_thr[nsrc];
+                const unsigned long long mass = hi - lo;
+                unsigned long long tt = ((unsigned long long)c[3] * (4294967296ULL - mass)) >> 32;
+                if (tt >= lo) tt += mass;
+                ndst = pick_thr_bsearch(s_node_thr, n, p.node_top_step, (unsigned)tt);
+                if (ndst == nsrc) ndst = (nsrc + 1) % n;
+                if (p.n_bit_rates > 0) nbr = p.bit_rates[pick_thr(p.br_thr, p.n_bit_rates, d[0])];
+                else nbr = p.br_lo + (int)__umulhi(d[0], (unsigned)p.br_span);
             } else if ((long long)ridx < p.trace_len) {
                 const orlg_request r = p.trace[(size_t)e * p.trace_len + ridx];
                 arrival = r.arrival; holding = r.holding; nsrc = r.src; ndst = r.dst;
@@ -191,59 +228,88 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             now = arrival; hold = holding; src = nsrc; dst = ndst; br = nbr;
             sid = (int)cnt[2];
             cnt[0] += 1; cnt[2] += 1; cnt[4] += br; cnt[6] += br;
-            while (nheap > 0 && hmin <= now) {            // release loop, on the register-resident masks
-                const unsigned long long pl = heap_pop(ht, hp, nheap, hmin);
+        }
+
+        cp_async_wait<0>();          // this thread's masks are in shared memory
+
+        if (accepted) {              // _provision_path: clear [start, start+n) on the path's links
+            const Bits rm = bits_range(a_start, a_start + a_n);
+            unsigned m = a_lm;
+            while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                uint4 v = sm[l * FAST_THREADS];
+                v.x &= ~rm.w[0]; v.y &= ~rm.w[1]; v.z &= ~rm.w[2]; v.w &= ~rm.w[3];
+                sm[l * FAST_THREADS] = v;
+            }
+            dirty |= a_lm;
+        }
+        if (mode == MODE_STEP || mode == MODE_FULL_RESET) {
+            events_release(ev, env, nheap, hmin, now, [&](unsigned long long pl) {     // rmsa_env.py:591-597
                 const unsigned lm = s_path_lm[svc_row(pl)];
                 const int rs = svc_start(pl);
                 const Bits rm = bits_range(rs, rs + svc_slots(pl));
-#pragma unroll
-                for (int l = 0; l < ET; l++) {
-                    const unsigned sel = 0u - ((lm >> l) & 1u);
-                    M[l].x |= rm.w[0] & sel; M[l].y |= rm.w[1] & sel;
-                    M[l].z |= rm.w[2] & sel; M[l].w |= rm.w[3] & sel;
+                unsigned m = lm;
+                while (m) {
+                    const int l = __ffs(m) - 1;
+                    m &= m - 1;
+                    uint4 v = sm[l * FAST_THREADS];
+                    v.x |= rm.w[0]; v.y |= rm.w[1]; v.z |= rm.w[2]; v.w |= rm.w[3];
+                    sm[l * FAST_THREADS] = v;
                 }
                 dirty |= lm;
-            }
+            });
             done = (cnt[2] == (long long)p.episode_length);
         }
-
         if (mode == MODE_EPISODE_RESET || (mode == MODE_STEP && done && p.auto_reset)) {
             cnt[2] = 1; cnt[3] = 0; cnt[6] = br; cnt[7] = 0;      // rmsa_env.py:285-330
         }
 
-        // ============ Phase C: observation of the pending request (deeprmsa_env.py:60-121) ============
+        // ============ Phase C, part 1: free-slot mask of every candidate path of the pending request
         const int pair = src * p.N + dst;
         const int first = s_pair_first[pair];
-        const int npaths = min((int)s_pair_count[pair], KM);
-        unsigned lms[KM];
-        int ns[KM];
-        Bits A[KM];
+        npaths = min((int)s_pair_count[pair], KM);
+        unsigned pm[KM], many = 0;
 #pragma unroll
         for (int q = 0; q < KM; q++) {
-            A[q] = bits_ones();
-            lms[q] = 0; ns[q] = 1;
-            if (q < npaths) {
-                lms[q] = s_path_lm[first + q];
-                const int se = s_path_se[first + q];
-                ns[q] = br < 128 ? s_nslots[se * 128 + br] : p.nslots[se * (p.br_max + 1) + br];
-            }
+            const bool have = q < npaths;
+            const int row = have ? first + q : first;
+            const int se = s_path_se[row];
+            ns[q] = s_nslots[se * 128 + min(br, 127)];
+            if (br >= 128) ns[q] = p.nslots[se * (p.br_max + 1) + br];
+            pm[q] = have ? s_path_lm[row] : 0u;
+            many |= pm[q];
+            A[q] = have ? bits_ones() : Bits{{0u, 0u, 0u, 0u}};
         }
-#pragma unroll
-        for (int l = 0; l < ET; l++) {
+        while (many) {                                   // get_available_slots (rmsa_env.py:638-649), 5 paths in lockstep
+            many = 0;
 #pragma unroll
             for (int q = 0; q < KM; q++) {
-                const unsigned keep = ((lms[q] >> l) & 1u) - 1u;
-                A[q].w[0] &= M[l].x | keep; A[q].w[1] &= M[l].y | keep;
-                A[q].w[2] &= M[l].z | keep; A[q].w[3] &= M[l].w | keep;
+                if (pm[q]) {
+                    const int l = __ffs(pm[q]) - 1;
+                    pm[q] &= pm[q] - 1;
+                    const uint4 v = sm[l * FAST_THREADS];
+                    A[q].w[0] &= v.x; A[q].w[1] &= v.y; A[q].w[2] &= v.z; A[q].w[3] &= v.w;
+                }
+                many |= pm[q];
             }
         }
         {   // write back the links this step touched
             uint4 *mw = p.masks + env;
-#pragma unroll
-            for (int l = 0; l < ET; l++)
-                if ((dirty >> l) & 1u) mw[(size_t)l * p.n] = M[l];
+            unsigned m = dirty;
+            while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                mw[(size_t)l * p.n] = sm[l * FAST_THREADS];
+            }
         }
+    }
 
+    __syncthreads();        // every thread is done with its masks: the area becomes the observation tile
+    unsigned char *stage = smem + p.tab_vec * 16;
+
+    if (live) {
+        // ============ Phase C, part 2: block features (deeprmsa_env.py:60-121)
         const int W = 2 * J + 3;
         const bool want_obs = io.obs != nullptr;
         float *so32 = reinterpret_cast<float *>(stage) + (size_t)tid * p.obs_dim;
@@ -255,7 +321,14 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
                 so64[0] = __ddiv_rn((double)br, 100.0);
                 so64[1 + lo] = 1.0; so64[1 + p.N + hi] = 1.0;
             } else {
-                for (int q = 0; q < p.obs_dim; q++) so32[q] = (q > 2 * p.N) ? -1.0f : 0.0f;
+                // rows are 8-byte aligned (obs_dim even) or handled element-wise
+                const int head = 1 + 2 * p.N;
+                if ((p.obs_dim & 1) == 0) {
+                    float2 *r2 = reinterpret_cast<float2 *>(so32);
+                    for (int q = 0; q < p.obs_dim / 2; q++) r2[q] = (2 * q >= head) ? make_float2(-1.0f, -1.0f) : make_float2(0.0f, (2 * q + 1 >= head) ? -1.0f : 0.0f);
+                } else {
+                    for (int q = 0; q < p.obs_dim; q++) so32[q] = (q >= head) ? -1.0f : 0.0f;
+                }
                 so32[0] = __fdiv_rn((float)br, 100.0f);
                 so32[1 + lo] = 1.0f; so32[1 + p.N + hi] = 1.0f;
             }
@@ -323,7 +396,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
                     } else {
                         so32[ob + 2 * J] = n < 32 ? s_nsl[n] : __fdiv_rn((float)(2 * n - 11), 7.0f);
                         so32[ob + 2 * J + 1] = s_pos[total];
-                        if (runs > 0) so32[ob + 2 * J + 2] = __fdiv_rn((float)(total - 4 * runs), (float)(4 * runs));
+                        if (runs > 0) so32[ob + 2 * J + 2] = __fdividef((float)(total - 4 * runs), (float)(4 * runs));   // <= 2 ulp
                     }
                 }
                 if (io.obs_int) {
@@ -339,6 +412,19 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
         }
         if (io.obs_int)
             for (int q = npaths * W; q < p.k * W; q++) io.obs_int[(size_t)env * p.k * W + q] = -1;
+
+        if (mode != MODE_OBSERVE) {      // ---- store the scalar block
+            p.now[env] = now;
+            p.cur_hold[env] = hold;
+            p.cur_req[env] = make_uint2((unsigned)src | ((unsigned)dst << 8) | ((unsigned)br << 16), (unsigned)sid);
+#pragma unroll
+            for (int q = 0; q < 8; q++) p.counters[(size_t)q * p.n + env] = cnt[q];
+            p.req_index[env] = ridx;
+            p.nheap[env] = nheap;
+            p.heap_min[env] = hmin;
+            p.errors[env] = err;
+            if (mode == MODE_STEP && io.done) io.done[env] = done ? 1 : 0;
+        }
     }
 
     if (io.obs != nullptr) {
@@ -353,21 +439,16 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
         } else {
             const float *s = reinterpret_cast<const float *>(stage);
             float *g = reinterpret_cast<float *>(io.obs) + tile0;
-            for (int q = tid; q < total_el; q += FAST_THREADS) g[q] = s[q];
+            int done_el = 0;
+            if ((reinterpret_cast<size_t>(g) & 15) == 0) {
+                const int nv = total_el >> 2;
+                const float4 *s4 = reinterpret_cast<const float4 *>(s);
+                float4 *g4 = reinterpret_cast<float4 *>(g);
+                for (int q = tid; q < nv; q += FAST_THREADS) g4[q] = s4[q];
+                done_el = nv << 2;
+            }
+            for (int q = done_el + tid; q < total_el; q += FAST_THREADS) g[q] = s[q];
         }
-    }
-
-    if (live && mode != MODE_OBSERVE) {
-        p.now[env] = now;
-        p.cur_hold[env] = hold;
-        p.cur_req[env] = make_uint2((unsigned)src | ((unsigned)dst << 8) | ((unsigned)br << 16), (unsigned)sid);
-#pragma unroll
-        for (int q = 0; q < 8; q++) p.counters[(size_t)q * p.n + env] = cnt[q];
-        p.req_index[env] = ridx;
-        p.nheap[env] = nheap;
-        p.heap_min[env] = hmin;
-        p.errors[env] = err;
-        if (mode == MODE_STEP && io.done) io.done[env] = done ? 1 : 0;
     }
 }
 

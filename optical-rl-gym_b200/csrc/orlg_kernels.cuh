@@ -43,6 +43,7 @@ struct Params {
     const uint4 *tab_blob;
     int tab_vec;                       // size in 16-byte units
     int off_pair_first, off_pair_count, off_path_lm, off_path_se, off_nslots, off_node_thr, off_pos, off_nsl;
+    int node_top_step;                 // highest power of two <= N-1 (binary search over the node CDF)
     // ---- per-env state (struct of arrays)
     uint4 *masks;                      // [C*E][n]
     double *now;                       // [n] current_time
@@ -52,8 +53,8 @@ struct Params {
     unsigned *req_index;               // [n] requests generated since the last full reset
     unsigned *nheap;                   // [n]
     double *heap_min;                  // [n] earliest release time (+inf if none)
-    double *heap_time;                 // [n][heap_cap] release times (8-ary heap, see orlg_device.cuh)
-    unsigned long long *heap_pay;      // [n][heap_cap] packed services
+    double *ev_time;                   // [heap_cap][n] release times of the live services (unsorted, orlg_device.cuh)
+    unsigned long long *ev_pay;        // [heap_cap][n] packed services
     unsigned char *cand;               // [n][cand_stride] first-fit block starts of the pending request
     unsigned *errors;                  // [n]
 };
@@ -161,8 +162,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
     unsigned nheap = p.nheap[e];
     double hmin = p.heap_min[e];
     unsigned err = p.errors[e];
-    double *ht = p.heap_time + (size_t)e * p.heap_cap;
-    unsigned long long *hp = p.heap_pay + (size_t)e * p.heap_cap;
+    const EventTable ev = {p.ev_time, p.ev_pay, (size_t)p.n};
 
     bool accepted = false;
     int d_row = -1, d_start = -1, d_n = -1, d_core = -1, d_mod = -1;
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
                 }
             }
         }
-        if (accepted && nheap + HEAP_ROOT + 1 > (unsigned)p.heap_cap) {
+        if (accepted && nheap + 1 > (unsigned)p.heap_cap) {
             accepted = false;
             err |= ORLG_ERR_HEAP_OVERFLOW;
         }
@@ -251,8 +251,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
             if (live) {
                 path_update(p, env, lm, core, bits_range(start, start + n), false);
                 double rel = __dadd_rn(now, hold);          // arrival_time + holding_time (now == arrival)
-                heap_push(ht, hp, nheap, rel, pack_service(row, start, n, core, sid));
-                hmin = fmin(hmin, rel);
+                events_push(ev, env, nheap, hmin, rel, pack_service(row, start, n, core, sid));
             }
             cnt[1] += 1; cnt[3] += 1;                        // services_accepted (+episode)
             if (KIND != ORLG_RWA) { cnt[5] += br; cnt[7] += br; }   // bit_rate_provisioned (+episode)
@@ -302,11 +301,10 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
             cnt[4] += br; cnt[6] += br;                       // rmcsa_env.py:730-731
         }
         // release every service whose time has come (rmsa_env.py:591-597)
-        while (nheap > 0 && hmin <= now) {
-            unsigned long long pl = heap_pop(ht, hp, nheap, hmin);
-            int rs = svc_start(pl);
-            if (live) path_update(p, env, p.path_linkmask[svc_row(pl)], svc_core(pl), bits_range(rs, rs + svc_slots(pl)), true);
-        }
+        events_release(ev, env, nheap, hmin, now, [&](unsigned long long pl) {
+            const int rs = svc_start(pl);
+            path_update(p, env, p.path_linkmask[svc_row(pl)], svc_core(pl), bits_range(rs, rs + svc_slots(pl)), true);
+        });
         done = (cnt[2] == (long long)p.episode_length);
     }
 
@@ -581,10 +579,9 @@ __global__ void export_kernel(const Params p, unsigned *masks_out, int *alloc_ou
         // spectrum_slots_allocation rebuilt from the live services (rmsa_env.py:386-389)
         int *o = alloc_out + (size_t)env * CE * p.S;
         for (int q = 0; q < CE * p.S; q++) o[q] = -1;
-        const unsigned long long *h = p.heap_pay + (size_t)env * p.heap_cap;
         const unsigned nh = p.nheap[env];
         for (unsigned s = 0; s < nh; s++) {
-            unsigned long long pl = h[HEAP_ROOT + s];
+            unsigned long long pl = p.ev_pay[(size_t)s * p.n + env];
             unsigned lm = p.path_linkmask[svc_row(pl)];
             while (lm) {
                 int l = __ffs(lm) - 1;

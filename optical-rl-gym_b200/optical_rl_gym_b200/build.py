@@ -7,9 +7,9 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(PKG), "csrc")
 LIB = os.path.join(PKG, "liborlg.so")
 SOURCES = ["orlg_api.cu"]
-HEADERS = ["orlg_kernels.cuh", "orlg_device.cuh", os.path.join("..", "..", "include", "orlg.h")]
+HEADERS = ["orlg_kernels.cuh", "orlg_device.cuh", "orlg_deeprmsa_fast.cuh", os.path.join("..", "..", "include", "orlg.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "--use_fast_math=false" if False else "-Xptxas=-v", "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
+              "-Xptxas=-v", "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
 
 
 def nvcc_path():
@@ -26,7 +26,8 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("ORLG_NVCC_EXTRA", "").split()          # e.g. -DORLG_FAST_THREADS=64 (tuning experiments)
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout)
