@@ -184,9 +184,10 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
         double load = cfg->mean_holding / cfg->mean_iat;
         double want = load + 8.0 * std::sqrt(load) + 16.0;
         double hard = cfg->kind == ORLG_RWA ? (double)p.E * p.S * C : (double)p.E * p.S * C / 2.0;
-        cap = (int)std::ceil(want < hard ? want : hard);
+        cap = (int)std::ceil(want < hard ? want : hard) + (int)HEAP_ROOT + 1;
     }
-    if (cap < 8) cap = 8;
+    cap = ((cap + (int)HD - 1) / (int)HD) * (int)HD;
+    if (cap < 2 * (int)HD) cap = 2 * (int)HD;
     p.heap_cap = cap;
 
     // ---- tables
@@ -247,8 +248,8 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     if (!rc) rc = dev_alloc(env, &p.req_index, n);
     if (!rc) rc = dev_alloc(env, &p.nheap, n);
     if (!rc) rc = dev_alloc(env, &p.heap_min, n);
-    if (!rc) rc = dev_alloc(env, &p.ev_time, n * (size_t)p.heap_cap, false);
-    if (!rc) rc = dev_alloc(env, &p.ev_pay, n * (size_t)p.heap_cap, false);
+    if (!rc) rc = dev_alloc(env, &p.heap_time, n * (size_t)p.heap_cap, false);
+    if (!rc) rc = dev_alloc(env, &p.heap_pay, n * (size_t)p.heap_cap, false);
     if (!rc) rc = dev_alloc(env, &p.cand, n * (size_t)p.cand_stride);
     if (!rc) rc = dev_alloc(env, &p.errors, n);
     if (rc) { orlg_destroy(env); return rc; }
@@ -325,7 +326,7 @@ int orlg_destroy(orlg_env *env) {
 int orlg_action_dim(const orlg_env *env) { return env->p.kind == ORLG_DEEPRMSA ? 1 : (env->p.kind == ORLG_RMCSA ? 4 : 2); }
 int orlg_obs_dim(const orlg_env *env) { return env->p.obs_dim; }
 int orlg_mask_words(const orlg_env *env) { (void)env; return NW; }
-int orlg_heap_capacity(const orlg_env *env) { return env->p.heap_cap; }
+int orlg_heap_capacity(const orlg_env *env) { return env->p.heap_cap - (int)HEAP_ROOT; }
 int64_t orlg_state_bytes(const orlg_env *env) { return env->state_bytes; }
 
 int orlg_set_trace(orlg_env *env, const orlg_request *trace_dev, int64_t trace_len) {

@@ -118,7 +118,12 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
     const int act = (mode == MODE_STEP) ? io.actions[e] : -1;
     unsigned long long candw = 0;
     if (p.cand_stride == 8) candw = *reinterpret_cast<const unsigned long long *>(p.cand + (size_t)e * 8);
-    const EventTable ev = {p.ev_time, p.ev_pay, (size_t)p.n};
+    double *ht = p.heap_time + (size_t)e * p.heap_cap;
+    unsigned long long *hp = p.heap_pay + (size_t)e * p.heap_cap;
+    if (mode == MODE_STEP && hmin <= now + 4.0 * p.mean_iat) {     // a release is likely: warm the heap's first level
+        prefetch_l2(ht + HD);
+        prefetch_l2(hp + HEAP_ROOT);
+    }
 
     const unsigned short *s_pair_first = reinterpret_cast<const unsigned short *>(smem + p.off_pair_first);
     const unsigned char *s_pair_count = smem + p.off_pair_count;
@@ -163,7 +168,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
                     const unsigned st = p.cand_stride == 8 ? (unsigned)((candw >> (8 * act)) & 0xffu)
                                                            : (unsigned)p.cand[(size_t)e * p.cand_stride + act];
                     if (st != CAND_NONE) {
-                        if (nheap + 1 > (unsigned)p.heap_cap) {
+                        if (nheap + HEAP_ROOT + 1 > (unsigned)p.heap_cap) {
                             err |= ORLG_ERR_HEAP_OVERFLOW;
                         } else {
                             a_row = first + route;
@@ -172,7 +177,8 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
                             a_lm = s_path_lm[a_row];
                             a_start = (int)st;
                             const double rel = __dadd_rn(now, hold);
-                            events_push(ev, env, nheap, hmin, rel, pack_service(a_row, a_start, a_n, 0, sid));
+                            heap_push(ht, hp, nheap, rel, pack_service(a_row, a_start, a_n, 0, sid));
+                            hmin = fmin(hmin, rel);
                             cnt[1] += 1; cnt[3] += 1; cnt[5] += br; cnt[7] += br;
                             accepted = true;
                             d_row = a_row; d_start = a_start; d_n = a_n;
@@ -245,7 +251,8 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             dirty |= a_lm;
         }
         if (mode == MODE_STEP || mode == MODE_FULL_RESET) {
-            events_release(ev, env, nheap, hmin, now, [&](unsigned long long pl) {     // rmsa_env.py:591-597
+            while (nheap > 0 && hmin <= now) {            // release loop (rmsa_env.py:591-597)
+                const unsigned long long pl = heap_pop(ht, hp, nheap, hmin);
                 const unsigned lm = s_path_lm[svc_row(pl)];
                 const int rs = svc_start(pl);
                 const Bits rm = bits_range(rs, rs + svc_slots(pl));
@@ -258,7 +265,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
                     sm[l * FAST_THREADS] = v;
                 }
                 dirty |= lm;
-            });
+            }
             done = (cnt[2] == (long long)p.episode_length);
         }
         if (mode == MODE_EPISODE_RESET || (mode == MODE_STEP && done && p.auto_reset)) {

@@ -175,71 +175,97 @@ __device__ __forceinline__ double neg_log_u32(uint32_t r) {
     return __dadd_rn(22.180709777918249, -lnx);
 }
 
-// ---------------------------------------------------------------- per-env release-event table (HBM)
-// Replaces the reference's heapq of (release_time, service) (optical_network_env.py:143-154,
-// rmsa_env.py:591-597).  The reference only ever asks "which services have release_time <= now?",
-// and the order in which those are released does not change the masks, so the table is UNSORTED:
-//   * push   = append at slot n (two stores, no load) and fold the time into the cached minimum;
-//   * a step whose cached minimum is still in the future touches no table memory at all;
-//   * otherwise ONE pass over the n live release times (independent, coalesced loads: the table is
-//     laid out [slot][env]) finds the due slots and the new minimum, and the holes are filled from
-//     the tail.  No dependent pointer chasing, unlike a heap's sift-down (measured: the heap's
-//     serial DRAM round trips dominated the step, profiles/r1_notes.md).
+// ---------------------------------------------------------------- per-env release-time heap (HD-ary, HBM)
+// Replaces heapq in optical_network_env.py:143-154 / rmsa_env.py:591-597 (pop order by time is
+// identical for any heap arity because release times are distinct).  Two parallel arrays per env:
+// release times (f64) and payloads (u64).  Slots 0..HD-2 are unused so that the HD children of slot s
+// start at HD*(s-HD+2): one aligned 8*HD-byte group, i.e. a level of a sift-down is ONE independent
+// fetch.  With HD = 16, up to 272 live services need at most 2 levels.  Payload moves are deferred to
+// the end of a pop so that they cost one round trip in total instead of one per level.
+// (An unsorted table with a scan was measured 2x slower: profiles/r1_notes.md.)
+#ifndef ORLG_HEAP_ARITY
+#define ORLG_HEAP_ARITY 16
+#endif
+constexpr unsigned HD = ORLG_HEAP_ARITY;
+constexpr unsigned HEAP_ROOT = HD - 1;
+constexpr int HEAP_MAX_DEPTH = HD >= 16 ? 3 : 4;      // 16-ary: 4368 entries, 8-ary: 4680 entries
 #define ORLG_INF __longlong_as_double(0x7ff0000000000000LL)
-constexpr int EV_ROUND = 4;       // due services removed per scan round (more: another round)
 
-struct EventTable {
-    double *time;                 // [cap][n_envs]
-    unsigned long long *pay;      // [cap][n_envs]
-    size_t stride;                // n_envs
-};
+__device__ __forceinline__ unsigned heap_first_child(unsigned s) { return HD * (s - HD + 2); }
+__device__ __forceinline__ unsigned heap_parent(unsigned c) { return c / HD + HD - 2; }
 
 __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
-__device__ __forceinline__ void events_push(const EventTable &ev, int env, unsigned &n, double &tmin, double t,
-                                            unsigned long long payload) {
-    ev.time[(size_t)n * ev.stride + env] = t;
-    ev.pay[(size_t)n * ev.stride + env] = payload;
+__device__ __forceinline__ void heap_push(double *ht, unsigned long long *hp, unsigned &n, double t,
+                                          unsigned long long payload) {
+    unsigned i = n + HEAP_ROOT;
     n++;
-    tmin = fmin(tmin, t);
+    while (i > HEAP_ROOT) {
+        unsigned p = heap_parent(i);
+        double pt = ht[p];
+        if (pt <= t) break;
+        ht[i] = pt;
+        hp[i] = hp[p];
+        i = p;
+    }
+    ht[i] = t;
+    hp[i] = payload;
 }
 
-// Releases every service with time <= now; `apply(payload)` frees its slots.  Updates n and tmin.
-template <typename Apply>
-__device__ __forceinline__ void events_release(const EventTable &ev, int env, unsigned &n, double &tmin, double now,
-                                               Apply apply) {
-    while (n > 0 && tmin <= now) {
-        const double *tp = ev.time + env;
-        double newmin = ORLG_INF;
-        unsigned ndue = 0, d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-#pragma unroll 4
-        for (unsigned s = 0; s < n; s++) {
-            const double t = tp[(size_t)s * ev.stride];
-            if (t <= now) {
-                if (ndue == 0) d0 = s; else if (ndue == 1) d1 = s; else if (ndue == 2) d2 = s; else if (ndue == 3) d3 = s;
-                ndue++;
-            } else {
-                newmin = fmin(newmin, t);
-            }
-        }
-        const unsigned take = min(ndue, (unsigned)EV_ROUND);
-        // fill the holes from the tail, highest hole first (so the tail element is never itself due)
-#pragma unroll
-        for (int i = EV_ROUND - 1; i >= 0; i--) {
-            if ((unsigned)i < take) {
-                const unsigned h = i == 0 ? d0 : (i == 1 ? d1 : (i == 2 ? d2 : d3));
-                const unsigned long long pl = ev.pay[(size_t)h * ev.stride + env];
-                const unsigned last = n - 1;
-                if (h != last) {
-                    ev.time[(size_t)h * ev.stride + env] = tp[(size_t)last * ev.stride];
-                    ev.pay[(size_t)h * ev.stride + env] = ev.pay[(size_t)last * ev.stride + env];
-                }
-                n--;
-                apply(pl);
-            }
-        }
-        tmin = ndue > (unsigned)EV_ROUND ? now : newmin;      // leftovers are still due: go round again
+// pops the root; returns its payload and the new minimum time (+inf when empty)
+__device__ __forceinline__ unsigned long long heap_pop(double *ht, unsigned long long *hp, unsigned &n, double &new_min) {
+    const unsigned long long top = hp[HEAP_ROOT];
+    n--;
+    if (n == 0) {
+        new_min = ORLG_INF;
+        return top;
     }
+    const unsigned end = n + HEAP_ROOT;      // valid slots [HEAP_ROOT, end); the old last element sits at `end`
+    const double lt = ht[end];
+    const unsigned long long lp = hp[end];
+    unsigned i = HEAP_ROOT;
+    unsigned mv_src[HEAP_MAX_DEPTH];
+    int nm = 0;
+    bool go = true;
+    new_min = lt;
+#pragma unroll
+    for (int lev = 0; lev < HEAP_MAX_DEPTH; lev++) {
+        mv_src[lev] = 0;
+        const unsigned c0 = heap_first_child(i);
+        if (go && c0 < end) {
+            const double2 *g = reinterpret_cast<const double2 *>(ht + c0);
+            double bt = ORLG_INF;
+            unsigned bi = c0;
+#pragma unroll
+            for (unsigned q = 0; q < HD / 2; q++) {
+                const double2 v = g[q];
+                if (c0 + 2 * q < end && v.x < bt) { bt = v.x; bi = c0 + 2 * q; }
+                if (c0 + 2 * q + 1 < end && v.y < bt) { bt = v.y; bi = c0 + 2 * q + 1; }
+            }
+            if (lt <= bt) {
+                go = false;
+            } else {
+                ht[i] = bt;
+                if (lev == 0) new_min = bt;
+                mv_src[lev] = bi;          // payload of slot bi moves up into the slot visited at this level
+                nm = lev + 1;
+                i = bi;
+            }
+        } else {
+            go = false;
+        }
+    }
+    ht[i] = lt;
+    // deferred payload moves: level 0 writes the root, level k writes mv_src[k-1]
+    unsigned long long pv[HEAP_MAX_DEPTH];
+#pragma unroll
+    for (int lev = 0; lev < HEAP_MAX_DEPTH; lev++)
+        if (lev < nm) pv[lev] = hp[mv_src[lev]];
+#pragma unroll
+    for (int lev = 0; lev < HEAP_MAX_DEPTH; lev++)
+        if (lev < nm) hp[lev == 0 ? HEAP_ROOT : mv_src[lev - 1]] = pv[lev];
+    hp[i] = lp;
+    return top;
 }
 
 // payload: path row (20 bits) | start (9) | slots (8) | core (5) | service id (22)
