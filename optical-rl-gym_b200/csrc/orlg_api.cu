@@ -105,7 +105,8 @@ void launch_step_kind(const orlg_env *env, const StepIO &io, int mode, cudaStrea
 template <int JT, bool OBS64>
 void launch_fast(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s) {
     const int blocks = (env->p.n + FAST_THREADS - 1) / FAST_THREADS;
-    deeprmsa_fast_kernel<5, JT, OBS64><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode);
+    if (env->p.E == 22) deeprmsa_fast_kernel<22, 5, JT, OBS64><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode);
+    else deeprmsa_fast_kernel<0, 5, JT, OBS64><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode);
 }
 
 int launch_step(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s) {
@@ -184,10 +185,11 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
         double load = cfg->mean_holding / cfg->mean_iat;
         double want = load + 8.0 * std::sqrt(load) + 16.0;
         double hard = cfg->kind == ORLG_RWA ? (double)p.E * p.S * C : (double)p.E * p.S * C / 2.0;
-        cap = (int)std::ceil(want < hard ? want : hard) + (int)HEAP_ROOT + 1;
+        cap = (int)std::ceil(want < hard ? want : hard);
     }
-    cap = ((cap + (int)HD - 1) / (int)HD) * (int)HD;
-    if (cap < 2 * (int)HD) cap = 2 * (int)HD;
+    cap = ((cap + EV_GROUP - 1) / EV_GROUP) * EV_GROUP;
+    if (cap > 64 * EV_GROUP) cap = 64 * EV_GROUP;        // the directory bitmap is 64 bits wide
+    p.ev_groups = ((cap / EV_GROUP + 15) / 16) * 16;
     p.heap_cap = cap;
 
     // ---- tables
@@ -248,8 +250,10 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     if (!rc) rc = dev_alloc(env, &p.req_index, n);
     if (!rc) rc = dev_alloc(env, &p.nheap, n);
     if (!rc) rc = dev_alloc(env, &p.heap_min, n);
-    if (!rc) rc = dev_alloc(env, &p.heap_time, n * (size_t)p.heap_cap, false);
-    if (!rc) rc = dev_alloc(env, &p.heap_pay, n * (size_t)p.heap_cap, false);
+    if (!rc) rc = dev_alloc(env, &p.ev_time, n * (size_t)p.heap_cap, false);
+    if (!rc) rc = dev_alloc(env, &p.ev_pay, n * (size_t)p.heap_cap, false);
+    if (!rc) rc = dev_alloc(env, &p.ev_gmin, n * (size_t)p.ev_groups);
+    if (!rc) rc = dev_alloc(env, &p.ev_tail, n);
     if (!rc) rc = dev_alloc(env, &p.cand, n * (size_t)p.cand_stride);
     if (!rc) rc = dev_alloc(env, &p.errors, n);
     if (rc) { orlg_destroy(env); return rc; }
@@ -297,10 +301,14 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
             while (p.node_top_step * 2 <= p.N - 1) p.node_top_step *= 2;
             cudaError_t ea = cudaSuccess;
             if (env->fast_smem > 48 * 1024) {
-                ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<5, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
-                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<5, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
-                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<5, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
-                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<5, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
+                ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<22, 5, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
+                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<0, 5, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
+                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<22, 5, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
+                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<0, 5, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
+                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<22, 5, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
+                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<0, 5, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
+                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<22, 5, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
+                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<0, 5, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
             }
             if (ea != cudaSuccess) env->fast = false;
         }
@@ -326,7 +334,7 @@ int orlg_destroy(orlg_env *env) {
 int orlg_action_dim(const orlg_env *env) { return env->p.kind == ORLG_DEEPRMSA ? 1 : (env->p.kind == ORLG_RMCSA ? 4 : 2); }
 int orlg_obs_dim(const orlg_env *env) { return env->p.obs_dim; }
 int orlg_mask_words(const orlg_env *env) { (void)env; return NW; }
-int orlg_heap_capacity(const orlg_env *env) { return env->p.heap_cap - (int)HEAP_ROOT; }
+int orlg_heap_capacity(const orlg_env *env) { return env->p.heap_cap; }
 int64_t orlg_state_bytes(const orlg_env *env) { return env->state_bytes; }
 
 int orlg_set_trace(orlg_env *env, const orlg_request *trace_dev, int64_t trace_len) {
@@ -431,6 +439,19 @@ int orlg_export_state(orlg_env *env, uint32_t *masks_dev, int32_t *alloc_dev, do
 
 int orlg_error_flags(orlg_env *env, uint32_t *flags_dev, orlg_stream stream) {
     return run_export(env, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, flags_dev, stream);
+}
+
+// debug (instrumented builds only): cumulative per-phase cycles of the fast kernel, then reset
+int orlg_debug_phase_cycles(unsigned long long *out16) {
+#ifdef ORLG_PHASE_TIMING
+    CUDA_OK(cudaMemcpyFromSymbol(out16, g_phase_cycles, 16 * sizeof(unsigned long long)));
+    unsigned long long zero[16] = {0};
+    CUDA_OK(cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero)));
+    return ORLG_OK;
+#else
+    (void)out16;
+    return fail(ORLG_E_UNSUPPORTED, "built without -DORLG_PHASE_TIMING");
+#endif
 }
 
 int orlg_reduce_counters(orlg_env *env, int64_t *sums_dev, orlg_stream stream) {

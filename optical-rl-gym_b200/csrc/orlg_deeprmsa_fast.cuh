@@ -68,6 +68,22 @@ __device__ __forceinline__ int bits_run_length_flat(const Bits &a, int start) {
     return (pos < 0 ? MAX_SLOTS : pos) - start;
 }
 
+// index of the lowest set bit of a 128-bit mask, -1 if empty (select chain instead of 4 dependent branches)
+__device__ __forceinline__ int bits_ffs_flat(const Bits &a) {
+    const int p0 = __ffs(a.w[0]), p1 = __ffs(a.w[1]), p2 = __ffs(a.w[2]), p3 = __ffs(a.w[3]);
+    int r = p3 ? p3 + 95 : -1;
+    r = p2 ? p2 + 63 : r;
+    r = p1 ? p1 + 31 : r;
+    r = p0 ? p0 - 1 : r;
+    return r;
+}
+__device__ __forceinline__ Bits bits_shr1(const Bits &a) {
+    Bits r;
+#pragma unroll
+    for (int i = 0; i < NW; i++) r.w[i] = __funnelshift_r(a.w[i], i + 1 < NW ? a.w[i + 1] : 0u, 1);
+    return r;
+}
+
 // first i in [0, n-1] with r < thr[i] (n-1 if none): same result as the linear scan of pick_thr
 __device__ __forceinline__ int pick_thr_bsearch(const unsigned *thr, int n, int top_step, unsigned r) {
     int i = 0;
@@ -76,7 +92,23 @@ __device__ __forceinline__ int pick_thr_bsearch(const unsigned *thr, int n, int 
     return i;
 }
 
-template <int KM, int JT, bool OBS64>
+// Optional per-phase cycle accounting (build with -DORLG_PHASE_TIMING; read with orlg_debug_phase_cycles):
+// sum over warps of the cycles between consecutive marks.  Not part of the product build.
+#ifdef ORLG_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define PHASE_MARK(k)                                                        \
+    do {                                                                     \
+        long long t_now_ = clock64();                                        \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase_cycles[k], (unsigned long long)(t_now_ - t_prev_)); \
+        t_prev_ = t_now_;                                                    \
+    } while (0)
+#define PHASE_INIT() long long t_prev_ = clock64()
+#else
+#define PHASE_MARK(k) do { } while (0)
+#define PHASE_INIT() do { } while (0)
+#endif
+
+template <int ET, int KM, int JT, bool OBS64>
 __global__ void __launch_bounds__(FAST_THREADS, FAST_MIN_BLOCKS)
 deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -87,6 +119,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
     const int J = JT == 1 ? 1 : p.J;
     const int E = p.E;
     uint4 *sm = reinterpret_cast<uint4 *>(smem + p.tab_vec * 16) + tid;      // this thread's masks: sm[l * FAST_THREADS]
+    PHASE_INIT();
 
     // ---------------- stage 0: asynchronous copies (group 0 = tables, group 1 = this env's link masks)
     {
@@ -118,12 +151,9 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
     const int act = (mode == MODE_STEP) ? io.actions[e] : -1;
     unsigned long long candw = 0;
     if (p.cand_stride == 8) candw = *reinterpret_cast<const unsigned long long *>(p.cand + (size_t)e * 8);
-    double *ht = p.heap_time + (size_t)e * p.heap_cap;
-    unsigned long long *hp = p.heap_pay + (size_t)e * p.heap_cap;
-    if (mode == MODE_STEP && hmin <= now + 4.0 * p.mean_iat) {     // a release is likely: warm the heap's first level
-        prefetch_l2(ht + HD);
-        prefetch_l2(hp + HEAP_ROOT);
-    }
+    const Events ev = {p.ev_time + (size_t)e * p.heap_cap, p.ev_pay + (size_t)e * p.heap_cap, p.ev_gmin + (size_t)e * p.ev_groups};
+    double tailmin = p.ev_tail[e];
+    if (mode == MODE_STEP && hmin <= now + 4.0 * p.mean_iat) prefetch_l2(ev.gmin);     // a release is likely: warm the directory
 
     const unsigned short *s_pair_first = reinterpret_cast<const unsigned short *>(smem + p.off_pair_first);
     const unsigned char *s_pair_count = smem + p.off_pair_count;
@@ -134,8 +164,10 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
     const float *s_pos = reinterpret_cast<const float *>(smem + p.off_pos);     // (2v - S) / S
     const float *s_nsl = reinterpret_cast<const float *>(smem + p.off_nsl);     // (2n - 11) / 7, n < 32
 
+    PHASE_MARK(0);               // issue of the async copies + scalar loads
     cp_async_wait<1>();          // tables landed (this thread's part) ...
     __syncthreads();             // ... and everybody else's
+    PHASE_MARK(1);               // wait for tables (first round trip)
 
     int src = rq.x & 0xff, dst = (rq.x >> 8) & 0xff, br = (int)(rq.x >> 16), sid = (int)rq.y;
     bool accepted = false, done = false;
@@ -146,7 +178,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
     Bits A[KM];
 
     if (mode == MODE_FULL_RESET) {
-        now = 0.0; nheap = 0; hmin = ORLG_INF; ridx = 0; err = 0;
+        now = 0.0; nheap = 0; hmin = ORLG_INF; tailmin = ORLG_INF; ridx = 0; err = 0;
         dirty = E >= 32 ? 0xFFFFFFFFu : ((1u << E) - 1u);
         const uint4 full = bits_to(bits_range(0, p.S));
         for (int l = 0; l < E; l++) sm[l * FAST_THREADS] = full;
@@ -168,7 +200,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
                     const unsigned st = p.cand_stride == 8 ? (unsigned)((candw >> (8 * act)) & 0xffu)
                                                            : (unsigned)p.cand[(size_t)e * p.cand_stride + act];
                     if (st != CAND_NONE) {
-                        if (nheap + HEAP_ROOT + 1 > (unsigned)p.heap_cap) {
+                        if (nheap + 1 > (unsigned)p.heap_cap) {
                             err |= ORLG_ERR_HEAP_OVERFLOW;
                         } else {
                             a_row = first + route;
@@ -177,8 +209,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
                             a_lm = s_path_lm[a_row];
                             a_start = (int)st;
                             const double rel = __dadd_rn(now, hold);
-                            heap_push(ht, hp, nheap, rel, pack_service(a_row, a_start, a_n, 0, sid));
-                            hmin = fmin(hmin, rel);
+                            events_push(ev, nheap, hmin, tailmin, rel, pack_service(a_row, a_start, a_n, 0, sid));
                             cnt[1] += 1; cnt[3] += 1; cnt[5] += br; cnt[7] += br;
                             accepted = true;
                             d_row = a_row; d_start = a_start; d_n = a_n;
@@ -199,6 +230,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             }
         }
 
+        PHASE_MARK(2);               // phase A: decision + heap push
         // ============ Phase B draw: _next_service (rmsa_env.py:545-580)
         if (mode == MODE_STEP || mode == MODE_FULL_RESET) {
             double arrival, holding;
@@ -236,7 +268,9 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             cnt[0] += 1; cnt[2] += 1; cnt[4] += br; cnt[6] += br;
         }
 
+        PHASE_MARK(3);               // phase B: traffic draw
         cp_async_wait<0>();          // this thread's masks are in shared memory
+        PHASE_MARK(4);               // wait for masks
 
         if (accepted) {              // _provision_path: clear [start, start+n) on the path's links
             const Bits rm = bits_range(a_start, a_start + a_n);
@@ -251,8 +285,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             dirty |= a_lm;
         }
         if (mode == MODE_STEP || mode == MODE_FULL_RESET) {
-            while (nheap > 0 && hmin <= now) {            // release loop (rmsa_env.py:591-597)
-                const unsigned long long pl = heap_pop(ht, hp, nheap, hmin);
+            events_release(ev, nheap, hmin, tailmin, now, [&](unsigned long long pl) {     // rmsa_env.py:591-597
                 const unsigned lm = s_path_lm[svc_row(pl)];
                 const int rs = svc_start(pl);
                 const Bits rm = bits_range(rs, rs + svc_slots(pl));
@@ -265,12 +298,13 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
                     sm[l * FAST_THREADS] = v;
                 }
                 dirty |= lm;
-            }
+            });
             done = (cnt[2] == (long long)p.episode_length);
         }
         if (mode == MODE_EPISODE_RESET || (mode == MODE_STEP && done && p.auto_reset)) {
             cnt[2] = 1; cnt[3] = 0; cnt[6] = br; cnt[7] = 0;      // rmsa_env.py:285-330
         }
+        PHASE_MARK(5);               // allocation + release loop (heap pops)
 
         // ============ Phase C, part 1: free-slot mask of every candidate path of the pending request
         const int pair = src * p.N + dst;
@@ -288,19 +322,35 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             many |= pm[q];
             A[q] = have ? bits_ones() : Bits{{0u, 0u, 0u, 0u}};
         }
-        while (many) {                                   // get_available_slots (rmsa_env.py:638-649), 5 paths in lockstep
-            many = 0;
+        if (ET > 0) {
+            // get_available_slots (rmsa_env.py:638-649): one static sweep over the E links; every path keeps the
+            // AND of its own links (20 independent accumulator words -> the sweep is throughput-, not latency-bound)
 #pragma unroll
-            for (int q = 0; q < KM; q++) {
-                if (pm[q]) {
-                    const int l = __ffs(pm[q]) - 1;
-                    pm[q] &= pm[q] - 1;
-                    const uint4 v = sm[l * FAST_THREADS];
-                    A[q].w[0] &= v.x; A[q].w[1] &= v.y; A[q].w[2] &= v.z; A[q].w[3] &= v.w;
+            for (int l = 0; l < (ET > 0 ? ET : 1); l++) {
+                const uint4 v = sm[l * FAST_THREADS];
+#pragma unroll
+                for (int q = 0; q < KM; q++) {
+                    const unsigned keep = ((pm[q] >> l) & 1u) - 1u;          // on the path: 0, else all ones
+                    A[q].w[0] &= v.x | keep; A[q].w[1] &= v.y | keep;
+                    A[q].w[2] &= v.z | keep; A[q].w[3] &= v.w | keep;
                 }
-                many |= pm[q];
+            }
+        } else {
+            while (many) {                               // generic E: the 5 paths walk their link lists in lockstep
+                many = 0;
+#pragma unroll
+                for (int q = 0; q < KM; q++) {
+                    if (pm[q]) {
+                        const int l = __ffs(pm[q]) - 1;
+                        pm[q] &= pm[q] - 1;
+                        const uint4 v = sm[l * FAST_THREADS];
+                        A[q].w[0] &= v.x; A[q].w[1] &= v.y; A[q].w[2] &= v.z; A[q].w[3] &= v.w;
+                    }
+                    many |= pm[q];
+                }
             }
         }
+        PHASE_MARK(6);               // candidate-path AND
         {   // write back the links this step touched
             uint4 *mw = p.masks + env;
             unsigned m = dirty;
@@ -312,8 +362,10 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
         }
     }
 
+    PHASE_MARK(7);          // dirty write-back
     __syncthreads();        // every thread is done with its masks: the area becomes the observation tile
     unsigned char *stage = smem + p.tab_vec * 16;
+    PHASE_MARK(8);          // barrier (mask area -> observation tile)
 
     if (live) {
         // ============ Phase C, part 2: block features (deeprmsa_env.py:60-121)
@@ -330,7 +382,11 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             } else {
                 // rows are 8-byte aligned (obs_dim even) or handled element-wise
                 const int head = 1 + 2 * p.N;
-                if ((p.obs_dim & 1) == 0) {
+                if (JT == 1 && io.obs_int == nullptr && p.k == KM && (p.obs_dim & 1) == 0) {
+                    // every feature entry is written below: only the head (bit rate + one-hots) needs zeros
+                    float2 *r2 = reinterpret_cast<float2 *>(so32);
+                    for (int q = 0; q < (head + 1) / 2; q++) r2[q] = make_float2(0.0f, 0.0f);
+                } else if ((p.obs_dim & 1) == 0) {
                     float2 *r2 = reinterpret_cast<float2 *>(so32);
                     for (int q = 0; q < p.obs_dim / 2; q++) r2[q] = (2 * q >= head) ? make_float2(-1.0f, -1.0f) : make_float2(0.0f, (2 * q + 1 >= head) ? -1.0f : 0.0f);
                 } else {
@@ -341,6 +397,34 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             }
         }
         unsigned long long cand_out = 0xFFFFFFFFFFFFFFFFULL;
+        const bool flat = JT == 1 && !OBS64 && io.obs_int == nullptr && p.k == KM;
+        if (flat) {
+            // j = 1, float32: straight-line code, the KM paths are independent instruction streams.
+            // With B = positions where a free run of >= n slots starts-or-continues (shift-AND doubling):
+            //   first block start = lowest set bit of B; its B-run ends at the lowest set bit of B & ~(B >> 1),
+            //   so the full free run has length (that end) - start + n            (get_available_blocks, rmsa_env.py:667-697)
+#pragma unroll
+            for (int q = 0; q < KM; q++) {
+                const int n = ns[q];
+                const Bits B = bits_runs_ge_flat(A[q], n);
+                const int st = bits_ffs_flat(B);
+                const int fe = bits_ffs_flat(bits_andnot(B, bits_shr1(B)));
+                const int len = fe - st + n;
+                const int total = bits_popc(A[q]);
+                const int runs = bits_popc(bits_andnot(A[q], bits_shl1(A[q])));
+                const bool have = q < npaths;
+                const bool blk = st >= 0;
+                cand_out = blk ? ((cand_out & ~(0xFFULL << (8 * q))) | ((unsigned long long)st << (8 * q))) : cand_out;
+                if (want_obs) {
+                    const int ob = 1 + 2 * p.N + q * 5;
+                    so32[ob] = blk ? s_pos[max(st, 0)] : -1.0f;
+                    so32[ob + 1] = blk ? (float)(len - 8) * 0.125f : -1.0f;
+                    so32[ob + 2] = have ? (n < 32 ? s_nsl[n] : __fdiv_rn((float)(2 * n - 11), 7.0f)) : -1.0f;
+                    so32[ob + 3] = have ? s_pos[total] : -1.0f;
+                    so32[ob + 4] = runs > 0 ? __fdividef((float)(total - 4 * runs), (float)(4 * runs)) : -1.0f;   // <= 2 ulp
+                }
+            }
+        } else {
 #pragma unroll
         for (int q = 0; q < KM; q++) {
             if (q < npaths) {
@@ -412,6 +496,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
                 }
             }
         }
+        }
         if (p.cand_stride == 8) {
             *reinterpret_cast<unsigned long long *>(p.cand + (size_t)env * 8) = cand_out;
         } else {
@@ -420,6 +505,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
         if (io.obs_int)
             for (int q = npaths * W; q < p.k * W; q++) io.obs_int[(size_t)env * p.k * W + q] = -1;
 
+        PHASE_MARK(9);                   // block features + observation row
         if (mode != MODE_OBSERVE) {      // ---- store the scalar block
             p.now[env] = now;
             p.cur_hold[env] = hold;
@@ -429,13 +515,16 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             p.req_index[env] = ridx;
             p.nheap[env] = nheap;
             p.heap_min[env] = hmin;
+            p.ev_tail[env] = tailmin;
             p.errors[env] = err;
             if (mode == MODE_STEP && io.done) io.done[env] = done ? 1 : 0;
         }
     }
 
+    PHASE_MARK(10);         // scalar stores
     if (io.obs != nullptr) {
         __syncthreads();
+        PHASE_MARK(11);     // barrier before the tile copy
         const size_t tile0 = (size_t)blockIdx.x * FAST_THREADS * p.obs_dim;
         const int rows = min(FAST_THREADS, p.n - blockIdx.x * FAST_THREADS);
         const int total_el = rows * p.obs_dim;
@@ -457,6 +546,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             for (int q = done_el + tid; q < total_el; q += FAST_THREADS) g[q] = s[q];
         }
     }
+    PHASE_MARK(12);         // observation tile copy-out
 }
 
 }  // namespace orlg

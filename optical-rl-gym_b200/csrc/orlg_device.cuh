@@ -175,97 +175,122 @@ __device__ __forceinline__ double neg_log_u32(uint32_t r) {
     return __dadd_rn(22.180709777918249, -lnx);
 }
 
-// ---------------------------------------------------------------- per-env release-time heap (HD-ary, HBM)
-// Replaces heapq in optical_network_env.py:143-154 / rmsa_env.py:591-597 (pop order by time is
-// identical for any heap arity because release times are distinct).  Two parallel arrays per env:
-// release times (f64) and payloads (u64).  Slots 0..HD-2 are unused so that the HD children of slot s
-// start at HD*(s-HD+2): one aligned 8*HD-byte group, i.e. a level of a sift-down is ONE independent
-// fetch.  With HD = 16, up to 272 live services need at most 2 levels.  Payload moves are deferred to
-// the end of a pop so that they cost one round trip in total instead of one per level.
-// (An unsorted table with a scan was measured 2x slower: profiles/r1_notes.md.)
-#ifndef ORLG_HEAP_ARITY
-#define ORLG_HEAP_ARITY 16
-#endif
-constexpr unsigned HD = ORLG_HEAP_ARITY;
-constexpr unsigned HEAP_ROOT = HD - 1;
-constexpr int HEAP_MAX_DEPTH = HD >= 16 ? 3 : 4;      // 16-ary: 4368 entries, 8-ary: 4680 entries
+// ---------------------------------------------------------------- per-env release-event table (HBM)
+// Replaces the reference's heapq of (release_time, service) (optical_network_env.py:143-154,
+// rmsa_env.py:591-597).  The reference only ever asks "which services have release_time <= now?",
+// and the order in which those are released does not change the masks, so no total order is kept:
+//   * the n live services occupy slots [0, n) of two parallel arrays (f64 time, u64 payload), UNSORTED;
+//   * a directory holds, per group of EV_GROUP consecutive slots, a float LOWER BOUND of the group's
+//     earliest release time (the open tail group's bound lives in the scalar block), and the scalar
+//     `tmin` is a lower bound over all groups;
+//   * push   = two stores at slot n (no load at all);
+//   * a step with tmin > now touches nothing;
+//   * otherwise: ONE fetch of the directory, ONE fetch of each group whose bound is due (usually one
+//     128-byte line), ONE fetch of the due payloads + the tail entry that fills the hole.  Constant
+//     number of dependent round trips per step, however many services expire.
+// (A binary/d-ary heap costs 3-4 dependent DRAM round trips PER POP and was measured to dominate both
+//  the mean and the tail of the step; a plain scan of all n times is latency-bound too: profiles/.)
 #define ORLG_INF __longlong_as_double(0x7ff0000000000000LL)
+constexpr int EV_GROUP = 16;
 
-__device__ __forceinline__ unsigned heap_first_child(unsigned s) { return HD * (s - HD + 2); }
-__device__ __forceinline__ unsigned heap_parent(unsigned c) { return c / HD + HD - 2; }
+struct Events {
+    double *t;                    // [cap] release times of this env
+    unsigned long long *p;        // [cap] packed services
+    float *gmin;                  // [cap / EV_GROUP] lower bound of each full group's earliest time
+};
 
 __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
-__device__ __forceinline__ void heap_push(double *ht, unsigned long long *hp, unsigned &n, double t,
-                                          unsigned long long payload) {
-    unsigned i = n + HEAP_ROOT;
-    n++;
-    while (i > HEAP_ROOT) {
-        unsigned p = heap_parent(i);
-        double pt = ht[p];
-        if (pt <= t) break;
-        ht[i] = pt;
-        hp[i] = hp[p];
-        i = p;
+__device__ __forceinline__ float lower_f32(double x) { return __double2float_rd(x); }
+
+__device__ __forceinline__ void events_push(const Events &ev, unsigned &n, double &tmin, double &tail_min, double t,
+                                            unsigned long long payload) {
+    if ((n & (EV_GROUP - 1)) == 0) {             // opening a new tail group: publish the previous group's bound
+        if (n > 0) ev.gmin[(n / EV_GROUP) - 1] = lower_f32(tail_min);
+        tail_min = ORLG_INF;
     }
-    ht[i] = t;
-    hp[i] = payload;
+    ev.t[n] = t;
+    ev.p[n] = payload;
+    n++;
+    tail_min = fmin(tail_min, t);
+    tmin = fmin(tmin, t);
 }
 
-// pops the root; returns its payload and the new minimum time (+inf when empty)
-__device__ __forceinline__ unsigned long long heap_pop(double *ht, unsigned long long *hp, unsigned &n, double &new_min) {
-    const unsigned long long top = hp[HEAP_ROOT];
-    n--;
-    if (n == 0) {
-        new_min = ORLG_INF;
-        return top;
-    }
-    const unsigned end = n + HEAP_ROOT;      // valid slots [HEAP_ROOT, end); the old last element sits at `end`
-    const double lt = ht[end];
-    const unsigned long long lp = hp[end];
-    unsigned i = HEAP_ROOT;
-    unsigned mv_src[HEAP_MAX_DEPTH];
-    int nm = 0;
-    bool go = true;
-    new_min = lt;
+// Releases every service with time <= now; `apply(payload)` frees its slots.  Updates n, tmin, tail_min.
+// Invariants: gmin[g] <= every time in full group g; tail_min <= every time in the tail group;
+// tmin <= every time.  Due services can therefore only sit in groups whose bound is <= now; those are
+// scanned from the highest group down, so the tail entry that fills a hole is never itself due.
+template <typename Apply>
+__device__ __forceinline__ void events_release(const Events &ev, unsigned &n, double &tmin, double &tail_min,
+                                               const double now, Apply apply) {
+    if (n == 0 || tmin > now) return;
+    const unsigned ng = (n + EV_GROUP - 1) / EV_GROUP;
+    // ---- directory: which groups may hold a due service?
+    unsigned long long due_groups = 0;
+    double bound = ORLG_INF;                   // lower bound over everything that stays
+    for (unsigned c = 0; c < ng; c += 16) {
+        float4 d[4];
 #pragma unroll
-    for (int lev = 0; lev < HEAP_MAX_DEPTH; lev++) {
-        mv_src[lev] = 0;
-        const unsigned c0 = heap_first_child(i);
-        if (go && c0 < end) {
-            const double2 *g = reinterpret_cast<const double2 *>(ht + c0);
-            double bt = ORLG_INF;
-            unsigned bi = c0;
+        for (int q = 0; q < 4; q++)
+            if (c + 4 * q < ng) d[q] = reinterpret_cast<const float4 *>(ev.gmin + c)[q];
 #pragma unroll
-            for (unsigned q = 0; q < HD / 2; q++) {
-                const double2 v = g[q];
-                if (c0 + 2 * q < end && v.x < bt) { bt = v.x; bi = c0 + 2 * q; }
-                if (c0 + 2 * q + 1 < end && v.y < bt) { bt = v.y; bi = c0 + 2 * q + 1; }
+        for (int q = 0; q < 16; q++) {
+            const unsigned g = c + q;
+            if (g < ng) {
+                const float4 v = d[q >> 2];
+                const float f = (q & 3) == 0 ? v.x : ((q & 3) == 1 ? v.y : ((q & 3) == 2 ? v.z : v.w));
+                const double b = (g == ng - 1) ? tail_min : (double)f;
+                if (b <= now) due_groups |= 1ULL << g; else bound = fmin(bound, b);
             }
-            if (lt <= bt) {
-                go = false;
-            } else {
-                ht[i] = bt;
-                if (lev == 0) new_min = bt;
-                mv_src[lev] = bi;          // payload of slot bi moves up into the slot visited at this level
-                nm = lev + 1;
-                i = bi;
-            }
-        } else {
-            go = false;
         }
     }
-    ht[i] = lt;
-    // deferred payload moves: level 0 writes the root, level k writes mv_src[k-1]
-    unsigned long long pv[HEAP_MAX_DEPTH];
+    unsigned tail_pub = ng - 1;                // the group that `tail_min` currently describes
+    while (due_groups) {
+        const unsigned g = 63 - __clzll(due_groups);
+        due_groups &= ~(1ULL << g);
+        const unsigned s0 = g * EV_GROUP;
+        if (s0 >= n) continue;                 // the group vanished while the tail shrank
+        double tv[EV_GROUP];
 #pragma unroll
-    for (int lev = 0; lev < HEAP_MAX_DEPTH; lev++)
-        if (lev < nm) pv[lev] = hp[mv_src[lev]];
+        for (int q = 0; q < EV_GROUP / 2; q++) {
+            const double2 v = reinterpret_cast<const double2 *>(ev.t + s0)[q];
+            tv[2 * q] = v.x; tv[2 * q + 1] = v.y;
+        }
+        unsigned duebits = 0;
+        double gm = ORLG_INF;                  // exact earliest time of what stays in this group
 #pragma unroll
-    for (int lev = 0; lev < HEAP_MAX_DEPTH; lev++)
-        if (lev < nm) hp[lev == 0 ? HEAP_ROOT : mv_src[lev - 1]] = pv[lev];
-    hp[i] = lp;
-    return top;
+        for (int q = 0; q < EV_GROUP; q++) {
+            const bool valid = s0 + q < n;
+            const bool due = valid && tv[q] <= now;
+            duebits |= due ? (1u << q) : 0u;
+            gm = (valid && !due) ? fmin(gm, tv[q]) : gm;
+        }
+        while (duebits) {                      // highest slot first
+            const unsigned q = 31 - __clz(duebits);
+            duebits &= ~(1u << q);
+            const unsigned s = s0 + q;
+            const unsigned last = n - 1;
+            const unsigned long long pl = ev.p[s];
+            if (s != last) {                   // fill the hole with the tail entry (never due, see above)
+                const double lt = ev.t[last];
+                const unsigned long long lp = ev.p[last];
+                ev.t[s] = lt;
+                ev.p[s] = lp;
+                gm = fmin(gm, lt);
+            }
+            n--;
+            apply(pl);
+        }
+        if (s0 < n) {                          // publish the exact bound of what is left of this group
+            if (g == (n - 1) / EV_GROUP) { tail_min = gm; tail_pub = g; }
+            else ev.gmin[g] = lower_f32(gm);
+            bound = fmin(bound, gm);
+        }
+    }
+    if (n == 0) { tmin = ORLG_INF; tail_min = ORLG_INF; return; }
+    const unsigned tail_g = (n - 1) / EV_GROUP;
+    if (tail_g != tail_pub) tail_min = (double)ev.gmin[tail_g];    // the tail shrank into an older, published group
+    tmin = bound;
 }
 
 // payload: path row (20 bits) | start (9) | slots (8) | core (5) | service id (22)

@@ -53,8 +53,11 @@ struct Params {
     unsigned *req_index;               // [n] requests generated since the last full reset
     unsigned *nheap;                   // [n]
     double *heap_min;                  // [n] earliest release time (+inf if none)
-    double *heap_time;                 // [n][heap_cap] release times (HD-ary heap, see orlg_device.cuh)
-    unsigned long long *heap_pay;      // [n][heap_cap] packed services
+    double *ev_time;                   // [n][heap_cap] release times of the live services (unsorted, orlg_device.cuh)
+    unsigned long long *ev_pay;        // [n][heap_cap] packed services
+    float *ev_gmin;                    // [n][ev_groups] per-group lower bounds (directory)
+    double *ev_tail;                   // [n] lower bound of the open tail group
+    int ev_groups;                     // directory stride (multiple of 16)
     unsigned char *cand;               // [n][cand_stride] first-fit block starts of the pending request
     unsigned *errors;                  // [n]
 };
@@ -162,8 +165,8 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
     unsigned nheap = p.nheap[e];
     double hmin = p.heap_min[e];
     unsigned err = p.errors[e];
-    double *ht = p.heap_time + (size_t)e * p.heap_cap;
-    unsigned long long *hp = p.heap_pay + (size_t)e * p.heap_cap;
+    const Events ev = {p.ev_time + (size_t)e * p.heap_cap, p.ev_pay + (size_t)e * p.heap_cap, p.ev_gmin + (size_t)e * p.ev_groups};
+    double tailmin = p.ev_tail[e];
 
     bool accepted = false;
     int d_row = -1, d_start = -1, d_n = -1, d_core = -1, d_mod = -1;
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
         Bits full = bits_range(0, p.S);
         if (live)
             for (int l = 0; l < p.C * p.E; l++) p.masks[(size_t)l * p.n + env] = bits_to(full);
-        now = 0.0; nheap = 0; hmin = ORLG_INF; ridx = 0; err = 0;
+        now = 0.0; nheap = 0; hmin = ORLG_INF; tailmin = ORLG_INF; ridx = 0; err = 0;
 #pragma unroll
         for (int q = 0; q < 8; q++) cnt[q] = 0;
     }
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
                 }
             }
         }
-        if (accepted && nheap + HEAP_ROOT + 1 > (unsigned)p.heap_cap) {
+        if (accepted && nheap + 1 > (unsigned)p.heap_cap) {
             accepted = false;
             err |= ORLG_ERR_HEAP_OVERFLOW;
         }
@@ -252,8 +255,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
             if (live) {
                 path_update(p, env, lm, core, bits_range(start, start + n), false);
                 double rel = __dadd_rn(now, hold);          // arrival_time + holding_time (now == arrival)
-                heap_push(ht, hp, nheap, rel, pack_service(row, start, n, core, sid));
-                hmin = fmin(hmin, rel);
+                events_push(ev, nheap, hmin, tailmin, rel, pack_service(row, start, n, core, sid));
             }
             cnt[1] += 1; cnt[3] += 1;                        // services_accepted (+episode)
             if (KIND != ORLG_RWA) { cnt[5] += br; cnt[7] += br; }   // bit_rate_provisioned (+episode)
@@ -303,11 +305,10 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
             cnt[4] += br; cnt[6] += br;                       // rmcsa_env.py:730-731
         }
         // release every service whose time has come (rmsa_env.py:591-597)
-        while (nheap > 0 && hmin <= now) {
-            const unsigned long long pl = heap_pop(ht, hp, nheap, hmin);
+        events_release(ev, nheap, hmin, tailmin, now, [&](unsigned long long pl) {
             const int rs = svc_start(pl);
             path_update(p, env, p.path_linkmask[svc_row(pl)], svc_core(pl), bits_range(rs, rs + svc_slots(pl)), true);
-        }
+        });
         done = (cnt[2] == (long long)p.episode_length);
     }
 
@@ -450,6 +451,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
         p.req_index[env] = ridx;
         p.nheap[env] = nheap;
         p.heap_min[env] = hmin;
+        p.ev_tail[env] = tailmin;
         p.errors[env] = err;
         if (mode == MODE_STEP && io.done) io.done[env] = done ? 1 : 0;
     }
@@ -582,10 +584,10 @@ __global__ void export_kernel(const Params p, unsigned *masks_out, int *alloc_ou
         // spectrum_slots_allocation rebuilt from the live services (rmsa_env.py:386-389)
         int *o = alloc_out + (size_t)env * CE * p.S;
         for (int q = 0; q < CE * p.S; q++) o[q] = -1;
-        const unsigned long long *h = p.heap_pay + (size_t)env * p.heap_cap;
+        const unsigned long long *h = p.ev_pay + (size_t)env * p.heap_cap;
         const unsigned nh = p.nheap[env];
         for (unsigned s = 0; s < nh; s++) {
-            unsigned long long pl = h[HEAP_ROOT + s];
+            unsigned long long pl = h[s];
             unsigned lm = p.path_linkmask[svc_row(pl)];
             while (lm) {
                 int l = __ffs(lm) - 1;

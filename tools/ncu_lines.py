@@ -58,7 +58,7 @@ def line_table(kernel_re):
             if m:
                 cur_file, cur_line = os.path.basename(m.group(1)), int(m.group(2))
                 continue
-            if re.match(r"\s*/\*[0-9a-f]{4}\*/", ln):
+            if re.match(r"\s*/\*[0-9a-f]{4,}\*/", ln):
                 lines.append((cur_file, cur_line, ln.strip()))
     return lines
 
