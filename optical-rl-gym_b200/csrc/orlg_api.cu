@@ -282,12 +282,22 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
         p.off_pair_count = put(pair_count.data(), pair_count.size());
         p.off_path_lm = put(linkmask.data(), linkmask.size() * 4);
         p.off_path_se = put(pse.data(), pse.size());
+        std::vector<unsigned long long> pll(P, 0ULL);      // hop list: 5 bits per link index, hop count in bits 60..63
+        bool ll_ok = true;
+        for (int r = 0; r < P; r++) {
+            const int h0 = t->path_link_ptr[r], hn = t->path_link_ptr[r + 1] - h0;
+            if (hn > 12) { ll_ok = false; break; }
+            unsigned long long v = (unsigned long long)hn << 60;
+            for (int h = 0; h < hn; h++) v |= (unsigned long long)(t->path_links[h0 + h] & 31) << (5 * h);
+            pll[r] = v;
+        }
+        p.off_path_ll = put(pll.data(), pll.size() * 8);
         p.off_nslots = put(ns128.data(), ns128.size());
         p.off_node_thr = put(node_thr.data(), node_thr.size() * 4);
         p.off_pos = put(pos.data(), pos.size() * 4);
         p.off_nsl = put(nsl.data(), nsl.size() * 4);
         blob.resize((blob.size() + 15) / 16 * 16);
-        if (blob.size() <= 24 * 1024 && blob.size() + (size_t)FAST_THREADS * 16 * 32 <= 100 * 1024) {
+        if (ll_ok && blob.size() <= 24 * 1024 && blob.size() + (size_t)FAST_THREADS * 16 * 32 <= 100 * 1024) {
             std::vector<uint4> blob4(blob.size() / 16);
             std::memcpy(blob4.data(), blob.data(), blob.size());
             rc = dev_upload(env, &p.tab_blob, blob4);
@@ -296,7 +306,8 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
             env->fast = true;
             size_t per_thread = (size_t)p.obs_dim * (p.obs_f64 ? 8 : 4);      // observation tile overlays the mask area
             if (per_thread < (size_t)p.E * 16) per_thread = (size_t)p.E * 16;
-            env->fast_smem = blob.size() + (size_t)FAST_THREADS * per_thread;
+            p.warp_area_bytes = (int)((per_thread * 32 + 127) / 128 * 128);
+            env->fast_smem = blob.size() + (size_t)(FAST_THREADS / 32) * p.warp_area_bytes;
             p.node_top_step = 1;
             while (p.node_top_step * 2 <= p.N - 1) p.node_top_step *= 2;
             cudaError_t ea = cudaSuccess;

@@ -34,8 +34,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ Bits bits_runs_ge_flat(const Bits &a, int n) {
-    // shift-AND doubling without a data-dependent loop for n <= 16 (larger n: generic path)
-    if (n > 16) return bits_runs_ge(a, n);
+    // shift-AND doubling without any branch; valid for 1 <= n <= 16 (the caller takes the generic path otherwise)
     Bits b = a;
     int len = 1;
 #pragma unroll
@@ -95,7 +94,6 @@ __device__ __forceinline__ int pick_thr_bsearch(const unsigned *thr, int n, int 
 // Optional per-phase cycle accounting (build with -DORLG_PHASE_TIMING; read with orlg_debug_phase_cycles):
 // sum over warps of the cycles between consecutive marks.  Not part of the product build.
 #ifdef ORLG_PHASE_TIMING
-__device__ unsigned long long g_phase_cycles[16];
 #define PHASE_MARK(k)                                                        \
     do {                                                                     \
         long long t_now_ = clock64();                                        \
@@ -118,7 +116,12 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
     const int e = live ? env : p.n - 1;
     const int J = JT == 1 ? 1 : p.J;
     const int E = p.E;
-    uint4 *sm = reinterpret_cast<uint4 *>(smem + p.tab_vec * 16) + tid;      // this thread's masks: sm[l * FAST_THREADS]
+    // Work area after the tables: one region per warp, [link][lane] uint4 (conflict-free LDS.128).  Once the
+    // warp's masks are dead the same region holds the warp's 32 observation rows, so only __syncwarp() is
+    // needed between the two uses: no CTA-wide barrier after the table load.
+    const int lane = tid & 31, wid = tid >> 5;
+    unsigned char *warp_area = smem + p.tab_vec * 16 + (size_t)wid * p.warp_area_bytes;
+    uint4 *sm = reinterpret_cast<uint4 *>(warp_area) + lane;                   // this thread's masks: sm[l * 32]
     PHASE_INIT();
 
     // ---------------- stage 0: asynchronous copies (group 0 = tables, group 1 = this env's link masks)
@@ -131,7 +134,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             unsigned sdst = (unsigned)__cvta_generic_to_shared(sm);
             for (int l = 0; l < E; l++) {
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(mr) : "memory");
-                sdst += FAST_THREADS * 16;
+                sdst += 32 * 16;
                 mr += p.n;
             }
         }
@@ -145,7 +148,9 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
 #pragma unroll
     for (int q = 0; q < 8; q++) cnt[q] = p.counters[(size_t)q * p.n + e];
     unsigned ridx = p.req_index[e];
-    unsigned nheap = p.nheap[e];
+    unsigned nheap = p.nheap[e];              // live services | prefetch hint << 16
+    unsigned ehint = nheap >> 16;
+    nheap &= 0xffffu;
     double hmin = p.heap_min[e];
     unsigned err = p.errors[e];
     const int act = (mode == MODE_STEP) ? io.actions[e] : -1;
@@ -153,12 +158,13 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
     if (p.cand_stride == 8) candw = *reinterpret_cast<const unsigned long long *>(p.cand + (size_t)e * 8);
     const Events ev = {p.ev_time + (size_t)e * p.heap_cap, p.ev_pay + (size_t)e * p.heap_cap, p.ev_gmin + (size_t)e * p.ev_groups};
     double tailmin = p.ev_tail[e];
-    if (mode == MODE_STEP && hmin <= now + 4.0 * p.mean_iat) prefetch_l2(ev.gmin);     // a release is likely: warm the directory
+    if (mode == MODE_STEP && hmin <= now + 4.0 * p.mean_iat) events_prefetch(ev, nheap, ehint);     // a release is likely
 
     const unsigned short *s_pair_first = reinterpret_cast<const unsigned short *>(smem + p.off_pair_first);
     const unsigned char *s_pair_count = smem + p.off_pair_count;
     const unsigned *s_path_lm = reinterpret_cast<const unsigned *>(smem + p.off_path_lm);
     const unsigned char *s_path_se = smem + p.off_path_se;
+    const unsigned long long *s_path_ll = reinterpret_cast<const unsigned long long *>(smem + p.off_path_ll);   // packed hop lists
     const unsigned char *s_nslots = smem + p.off_nslots;              // [se][128]
     const unsigned *s_node_thr = reinterpret_cast<const unsigned *>(smem + p.off_node_thr);
     const float *s_pos = reinterpret_cast<const float *>(smem + p.off_pos);     // (2v - S) / S
@@ -178,10 +184,10 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
     Bits A[KM];
 
     if (mode == MODE_FULL_RESET) {
-        now = 0.0; nheap = 0; hmin = ORLG_INF; tailmin = ORLG_INF; ridx = 0; err = 0;
+        now = 0.0; nheap = 0; ehint = 0; hmin = ORLG_INF; tailmin = ORLG_INF; ridx = 0; err = 0;
         dirty = E >= 32 ? 0xFFFFFFFFu : ((1u << E) - 1u);
         const uint4 full = bits_to(bits_range(0, p.S));
-        for (int l = 0; l < E; l++) sm[l * FAST_THREADS] = full;
+        for (int l = 0; l < E; l++) sm[l * 32] = full;
 #pragma unroll
         for (int q = 0; q < 8; q++) cnt[q] = 0;
     }
@@ -209,7 +215,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
                             a_lm = s_path_lm[a_row];
                             a_start = (int)st;
                             const double rel = __dadd_rn(now, hold);
-                            events_push(ev, nheap, hmin, tailmin, rel, pack_service(a_row, a_start, a_n, 0, sid));
+                            events_push(ev, nheap, ehint, hmin, tailmin, rel, pack_service(a_row, a_start, a_n, 0, sid));
                             cnt[1] += 1; cnt[3] += 1; cnt[5] += br; cnt[7] += br;
                             accepted = true;
                             d_row = a_row; d_start = a_start; d_n = a_n;
@@ -278,14 +284,14 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             while (m) {
                 const int l = __ffs(m) - 1;
                 m &= m - 1;
-                uint4 v = sm[l * FAST_THREADS];
+                uint4 v = sm[l * 32];
                 v.x &= ~rm.w[0]; v.y &= ~rm.w[1]; v.z &= ~rm.w[2]; v.w &= ~rm.w[3];
-                sm[l * FAST_THREADS] = v;
+                sm[l * 32] = v;
             }
             dirty |= a_lm;
         }
         if (mode == MODE_STEP || mode == MODE_FULL_RESET) {
-            events_release(ev, nheap, hmin, tailmin, now, [&](unsigned long long pl) {     // rmsa_env.py:591-597
+            events_release(ev, nheap, ehint, hmin, tailmin, now, [&](unsigned long long pl) {     // rmsa_env.py:591-597
                 const unsigned lm = s_path_lm[svc_row(pl)];
                 const int rs = svc_start(pl);
                 const Bits rm = bits_range(rs, rs + svc_slots(pl));
@@ -293,9 +299,9 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
                 while (m) {
                     const int l = __ffs(m) - 1;
                     m &= m - 1;
-                    uint4 v = sm[l * FAST_THREADS];
+                    uint4 v = sm[l * 32];
                     v.x |= rm.w[0]; v.y |= rm.w[1]; v.z |= rm.w[2]; v.w |= rm.w[3];
-                    sm[l * FAST_THREADS] = v;
+                    sm[l * 32] = v;
                 }
                 dirty |= lm;
             });
@@ -310,7 +316,12 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
         const int pair = src * p.N + dst;
         const int first = s_pair_first[pair];
         npaths = min((int)s_pair_count[pair], KM);
-        unsigned pm[KM], many = 0;
+        // get_available_slots (rmsa_env.py:638-649): every candidate path walks its packed hop list
+        // (5 bits per link, hop count in the top 4 bits); the KM paths advance in lockstep so that the
+        // LDS -> AND chains of different paths overlap.
+        unsigned long long ll[KM];
+        unsigned pm[KM];
+        int hops[KM], mh = 0;
 #pragma unroll
         for (int q = 0; q < KM; q++) {
             const bool have = q < npaths;
@@ -318,16 +329,18 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             const int se = s_path_se[row];
             ns[q] = s_nslots[se * 128 + min(br, 127)];
             if (br >= 128) ns[q] = p.nslots[se * (p.br_max + 1) + br];
+            ll[q] = s_path_ll[row];
             pm[q] = have ? s_path_lm[row] : 0u;
-            many |= pm[q];
+            hops[q] = have ? (int)(ll[q] >> 60) : 0;
+            mh = max(mh, hops[q]);
             A[q] = have ? bits_ones() : Bits{{0u, 0u, 0u, 0u}};
         }
         if (ET > 0) {
-            // get_available_slots (rmsa_env.py:638-649): one static sweep over the E links; every path keeps the
-            // AND of its own links (20 independent accumulator words -> the sweep is throughput-, not latency-bound)
+            // known link count: one static sweep over the E links, 20 independent accumulator words
+            // (more instructions than walking the hop lists, but throughput- instead of latency-bound)
 #pragma unroll
             for (int l = 0; l < (ET > 0 ? ET : 1); l++) {
-                const uint4 v = sm[l * FAST_THREADS];
+                const uint4 v = sm[l * 32];
 #pragma unroll
                 for (int q = 0; q < KM; q++) {
                     const unsigned keep = ((pm[q] >> l) & 1u) - 1u;          // on the path: 0, else all ones
@@ -336,17 +349,15 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
                 }
             }
         } else {
-            while (many) {                               // generic E: the 5 paths walk their link lists in lockstep
-                many = 0;
+            for (int h = 0; h < mh; h++) {
 #pragma unroll
                 for (int q = 0; q < KM; q++) {
-                    if (pm[q]) {
-                        const int l = __ffs(pm[q]) - 1;
-                        pm[q] &= pm[q] - 1;
-                        const uint4 v = sm[l * FAST_THREADS];
+                    if (h < hops[q]) {
+                        const int l = (int)(ll[q] & 31u);
+                        const uint4 v = sm[l * 32];
                         A[q].w[0] &= v.x; A[q].w[1] &= v.y; A[q].w[2] &= v.z; A[q].w[3] &= v.w;
                     }
-                    many |= pm[q];
+                    ll[q] >>= 5;
                 }
             }
         }
@@ -357,22 +368,22 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             while (m) {
                 const int l = __ffs(m) - 1;
                 m &= m - 1;
-                mw[(size_t)l * p.n] = sm[l * FAST_THREADS];
+                mw[(size_t)l * p.n] = sm[l * 32];
             }
         }
     }
 
     PHASE_MARK(7);          // dirty write-back
-    __syncthreads();        // every thread is done with its masks: the area becomes the observation tile
-    unsigned char *stage = smem + p.tab_vec * 16;
+    __syncwarp();           // every lane is done with its masks: the warp's area becomes its observation tile
+    unsigned char *stage = warp_area;
     PHASE_MARK(8);          // barrier (mask area -> observation tile)
 
     if (live) {
         // ============ Phase C, part 2: block features (deeprmsa_env.py:60-121)
         const int W = 2 * J + 3;
         const bool want_obs = io.obs != nullptr;
-        float *so32 = reinterpret_cast<float *>(stage) + (size_t)tid * p.obs_dim;
-        double *so64 = reinterpret_cast<double *>(stage) + (size_t)tid * p.obs_dim;
+        float *so32 = reinterpret_cast<float *>(stage) + (size_t)lane * p.obs_dim;
+        double *so64 = reinterpret_cast<double *>(stage) + (size_t)lane * p.obs_dim;
         if (want_obs) {
             const int lo = min(src, dst), hi = max(src, dst);
             if (OBS64) {
@@ -397,7 +408,10 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             }
         }
         unsigned long long cand_out = 0xFFFFFFFFFFFFFFFFULL;
-        const bool flat = JT == 1 && !OBS64 && io.obs_int == nullptr && p.k == KM;
+        int n_max = 0;
+#pragma unroll
+        for (int q = 0; q < KM; q++) n_max = max(n_max, ns[q]);
+        const bool flat = JT == 1 && !OBS64 && io.obs_int == nullptr && p.k == KM && n_max <= 16;
         if (flat) {
             // j = 1, float32: straight-line code, the KM paths are independent instruction streams.
             // With B = positions where a free run of >= n slots starts-or-continues (shift-AND doubling):
@@ -419,7 +433,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
                     const int ob = 1 + 2 * p.N + q * 5;
                     so32[ob] = blk ? s_pos[max(st, 0)] : -1.0f;
                     so32[ob + 1] = blk ? (float)(len - 8) * 0.125f : -1.0f;
-                    so32[ob + 2] = have ? (n < 32 ? s_nsl[n] : __fdiv_rn((float)(2 * n - 11), 7.0f)) : -1.0f;
+                    so32[ob + 2] = have ? s_nsl[n] : -1.0f;                 // n <= 16 here
                     so32[ob + 3] = have ? s_pos[total] : -1.0f;
                     so32[ob + 4] = runs > 0 ? __fdividef((float)(total - 4 * runs), (float)(4 * runs)) : -1.0f;   // <= 2 ulp
                 }
@@ -429,7 +443,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
         for (int q = 0; q < KM; q++) {
             if (q < npaths) {
                 const int n = ns[q];
-                const Bits B = bits_runs_ge_flat(A[q], n);
+                const Bits B = n <= 16 ? bits_runs_ge_flat(A[q], n) : bits_runs_ge(A[q], n);
                 Bits starts = bits_andnot(B, bits_shl1(B));
                 const int total = bits_popc(A[q]);
                 const int runs = bits_popc(bits_andnot(A[q], bits_shl1(A[q])));
@@ -513,7 +527,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
 #pragma unroll
             for (int q = 0; q < 8; q++) p.counters[(size_t)q * p.n + env] = cnt[q];
             p.req_index[env] = ridx;
-            p.nheap[env] = nheap;
+            p.nheap[env] = nheap | (ehint << 16);
             p.heap_min[env] = hmin;
             p.ev_tail[env] = tailmin;
             p.errors[env] = err;
@@ -523,27 +537,30 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
 
     PHASE_MARK(10);         // scalar stores
     if (io.obs != nullptr) {
-        __syncthreads();
-        PHASE_MARK(11);     // barrier before the tile copy
-        const size_t tile0 = (size_t)blockIdx.x * FAST_THREADS * p.obs_dim;
-        const int rows = min(FAST_THREADS, p.n - blockIdx.x * FAST_THREADS);
-        const int total_el = rows * p.obs_dim;
-        if (OBS64) {
-            const double *s = reinterpret_cast<const double *>(stage);
-            double *g = reinterpret_cast<double *>(io.obs) + tile0;
-            for (int q = tid; q < total_el; q += FAST_THREADS) g[q] = s[q];
-        } else {
-            const float *s = reinterpret_cast<const float *>(stage);
-            float *g = reinterpret_cast<float *>(io.obs) + tile0;
-            int done_el = 0;
-            if ((reinterpret_cast<size_t>(g) & 15) == 0) {
-                const int nv = total_el >> 2;
-                const float4 *s4 = reinterpret_cast<const float4 *>(s);
-                float4 *g4 = reinterpret_cast<float4 *>(g);
-                for (int q = tid; q < nv; q += FAST_THREADS) g4[q] = s4[q];
-                done_el = nv << 2;
+        __syncwarp();
+        PHASE_MARK(11);     // (warp-level sync before the tile copy)
+        const int row0 = blockIdx.x * FAST_THREADS + wid * 32;          // first env of this warp
+        const int rows = min(32, p.n - row0);
+        if (rows > 0) {
+            const size_t tile0 = (size_t)row0 * p.obs_dim;
+            const int total_el = rows * p.obs_dim;
+            if (OBS64) {
+                const double *s = reinterpret_cast<const double *>(stage);
+                double *g = reinterpret_cast<double *>(io.obs) + tile0;
+                for (int q = lane; q < total_el; q += 32) g[q] = s[q];
+            } else {
+                const float *s = reinterpret_cast<const float *>(stage);
+                float *g = reinterpret_cast<float *>(io.obs) + tile0;
+                int done_el = 0;
+                if ((reinterpret_cast<size_t>(g) & 15) == 0) {
+                    const int nv = total_el >> 2;
+                    const float4 *s4 = reinterpret_cast<const float4 *>(s);
+                    float4 *g4 = reinterpret_cast<float4 *>(g);
+                    for (int q = lane; q < nv; q += 32) g4[q] = s4[q];
+                    done_el = nv << 2;
+                }
+                for (int q = done_el + lane; q < total_el; q += 32) g[q] = s[q];
             }
-            for (int q = done_el + tid; q < total_el; q += FAST_THREADS) g[q] = s[q];
         }
     }
     PHASE_MARK(12);         // observation tile copy-out

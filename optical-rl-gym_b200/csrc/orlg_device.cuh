@@ -193,6 +193,21 @@ __device__ __forceinline__ double neg_log_u32(uint32_t r) {
 #define ORLG_INF __longlong_as_double(0x7ff0000000000000LL)
 constexpr int EV_GROUP = 16;
 
+// Optional cycle accounting (instrumented builds only: -DORLG_PHASE_TIMING, tools/phase_timing.py)
+#ifdef ORLG_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define SUBPHASE_BEGIN() long long sub_t_ = clock64()
+#define SUBPHASE_MARK(k)                                                                 \
+    do {                                                                                 \
+        long long sub_n_ = clock64();                                                    \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase_cycles[k], (unsigned long long)(sub_n_ - sub_t_)); \
+        sub_t_ = sub_n_;                                                                 \
+    } while (0)
+#else
+#define SUBPHASE_BEGIN() do { } while (0)
+#define SUBPHASE_MARK(k) do { } while (0)
+#endif
+
 struct Events {
     double *t;                    // [cap] release times of this env
     unsigned long long *p;        // [cap] packed services
@@ -202,9 +217,11 @@ struct Events {
 __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
 __device__ __forceinline__ float lower_f32(double x) { return __double2float_rd(x); }
+// plain minimum of finite values (fmin()'s NaN handling costs several extra instructions)
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
 
-__device__ __forceinline__ void events_push(const Events &ev, unsigned &n, double &tmin, double &tail_min, double t,
-                                            unsigned long long payload) {
+__device__ __forceinline__ void events_push(const Events &ev, unsigned &n, unsigned &hint, double &tmin, double &tail_min,
+                                            double t, unsigned long long payload) {
     if ((n & (EV_GROUP - 1)) == 0) {             // opening a new tail group: publish the previous group's bound
         if (n > 0) ev.gmin[(n / EV_GROUP) - 1] = lower_f32(tail_min);
         tail_min = ORLG_INF;
@@ -212,8 +229,20 @@ __device__ __forceinline__ void events_push(const Events &ev, unsigned &n, doubl
     ev.t[n] = t;
     ev.p[n] = payload;
     n++;
-    tail_min = fmin(tail_min, t);
-    tmin = fmin(tmin, t);
+    tail_min = dmin(tail_min, t);
+    if (t < tmin) { tmin = t; hint = (n - 1) / EV_GROUP; }
+}
+
+// Issue (early, no registers) the fetches a release in this step would need: the directory, the group that
+// holds the earliest bound (`hint`: a prefetch hint only, correctness never depends on it) and the tail entry.
+__device__ __forceinline__ void events_prefetch(const Events &ev, unsigned n, unsigned hint) {
+    if (n == 0) return;
+    prefetch_l2(ev.gmin);
+    const unsigned g = min(hint, (n - 1) / EV_GROUP);
+    prefetch_l2(ev.t + g * EV_GROUP);
+    prefetch_l2(ev.p + g * EV_GROUP);
+    prefetch_l2(ev.t + (n - 1));
+    prefetch_l2(ev.p + (n - 1));
 }
 
 // Releases every service with time <= now; `apply(payload)` frees its slots.  Updates n, tmin, tail_min.
@@ -221,29 +250,38 @@ __device__ __forceinline__ void events_push(const Events &ev, unsigned &n, doubl
 // tmin <= every time.  Due services can therefore only sit in groups whose bound is <= now; those are
 // scanned from the highest group down, so the tail entry that fills a hole is never itself due.
 template <typename Apply>
-__device__ __forceinline__ void events_release(const Events &ev, unsigned &n, double &tmin, double &tail_min,
+__device__ __forceinline__ void events_release(const Events &ev, unsigned &n, unsigned &hint, double &tmin, double &tail_min,
                                                const double now, Apply apply) {
+    SUBPHASE_BEGIN();
     if (n == 0 || tmin > now) return;
     const unsigned ng = (n + EV_GROUP - 1) / EV_GROUP;
     // ---- directory: which groups may hold a due service?
     unsigned long long due_groups = 0;
-    double bound = ORLG_INF;                   // lower bound over everything that stays
-    for (unsigned c = 0; c < ng; c += 16) {
+    unsigned arg = 0;                           // group of the smallest staying bound (next step's prefetch hint)
+    float fbound = __int_as_float(0x7f800000);  // lower bound (float) over the full groups that stay
+    const float now_up = __double2float_ru(now);   // conservative: f <= now_up whenever (double)f <= now
+    for (unsigned c = 0; c + 1 < ng; c += 16) {    // full groups only: the tail group is handled below
         float4 d[4];
 #pragma unroll
         for (int q = 0; q < 4; q++)
-            if (c + 4 * q < ng) d[q] = reinterpret_cast<const float4 *>(ev.gmin + c)[q];
+            if (c + 4 * q + 1 < ng) d[q] = reinterpret_cast<const float4 *>(ev.gmin + c)[q];
 #pragma unroll
         for (int q = 0; q < 16; q++) {
             const unsigned g = c + q;
-            if (g < ng) {
-                const float4 v = d[q >> 2];
-                const float f = (q & 3) == 0 ? v.x : ((q & 3) == 1 ? v.y : ((q & 3) == 2 ? v.z : v.w));
-                const double b = (g == ng - 1) ? tail_min : (double)f;
-                if (b <= now) due_groups |= 1ULL << g; else bound = fmin(bound, b);
-            }
+            const float4 v = d[q >> 2];
+            const float f = (q & 3) == 0 ? v.x : ((q & 3) == 1 ? v.y : ((q & 3) == 2 ? v.z : v.w));
+            const bool in = g + 1 < ng;
+            const bool due = in && f <= now_up;
+            due_groups |= due ? (1ULL << g) : 0ULL;
+            const bool lower = in && !due && f < fbound;
+            arg = lower ? g : arg;
+            fbound = lower ? f : fbound;
         }
     }
+    double bound = (double)fbound;
+    if (tail_min <= now) due_groups |= 1ULL << (ng - 1);
+    else if (tail_min < bound) { bound = tail_min; arg = ng - 1; }
+    SUBPHASE_MARK(13);                         // directory
     unsigned tail_pub = ng - 1;                // the group that `tail_min` currently describes
     while (due_groups) {
         const unsigned g = 63 - __clzll(due_groups);
@@ -263,8 +301,9 @@ __device__ __forceinline__ void events_release(const Events &ev, unsigned &n, do
             const bool valid = s0 + q < n;
             const bool due = valid && tv[q] <= now;
             duebits |= due ? (1u << q) : 0u;
-            gm = (valid && !due) ? fmin(gm, tv[q]) : gm;
+            gm = (valid && !due && tv[q] < gm) ? tv[q] : gm;
         }
+        SUBPHASE_MARK(14);                     // group fetch + classify
         while (duebits) {                      // highest slot first
             const unsigned q = 31 - __clz(duebits);
             duebits &= ~(1u << q);
@@ -276,21 +315,23 @@ __device__ __forceinline__ void events_release(const Events &ev, unsigned &n, do
                 const unsigned long long lp = ev.p[last];
                 ev.t[s] = lt;
                 ev.p[s] = lp;
-                gm = fmin(gm, lt);
+                gm = dmin(gm, lt);
             }
             n--;
             apply(pl);
         }
+        SUBPHASE_MARK(15);                     // payload fetch, hole fill, apply
         if (s0 < n) {                          // publish the exact bound of what is left of this group
             if (g == (n - 1) / EV_GROUP) { tail_min = gm; tail_pub = g; }
             else ev.gmin[g] = lower_f32(gm);
-            bound = fmin(bound, gm);
+            if (gm < bound) { bound = gm; arg = g; }
         }
     }
-    if (n == 0) { tmin = ORLG_INF; tail_min = ORLG_INF; return; }
+    if (n == 0) { tmin = ORLG_INF; tail_min = ORLG_INF; hint = 0; return; }
     const unsigned tail_g = (n - 1) / EV_GROUP;
     if (tail_g != tail_pub) tail_min = (double)ev.gmin[tail_g];    // the tail shrank into an older, published group
     tmin = bound;
+    hint = arg;
 }
 
 // payload: path row (20 bits) | start (9) | slots (8) | core (5) | service id (22)

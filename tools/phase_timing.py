@@ -36,3 +36,5 @@ tot = sum(buf[:13])
 print("avg cycles per warp per step: %.0f" % (tot / warps / steps))
 for i, nm in enumerate(NAMES):
     print("%-20s %8.0f cycles  %5.1f%%" % (nm, buf[i] / warps / steps, 100.0 * buf[i] / tot))
+for i, nm in ((13, "  rel: directory"), (14, "  rel: group scan"), (15, "  rel: payload+apply")):
+    print("%-20s %8.0f cycles" % (nm, buf[i] / warps / steps))
