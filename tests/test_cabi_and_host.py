@@ -1,0 +1,117 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol declared in include/orlg.h
+(no compute call: there is no GPU here), host topology pre-processing, and the product never
+touching the oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "orlg.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(orlg_[a-z_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from optical_rl_gym_b200 import _native
+
+    lib = _native.lib()
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), "liborlg.so does not export %s" % s
+    assert sorted(_native.EXPORTED) == syms, "python binding list and header disagree"
+    assert lib.orlg_version() == 1
+
+
+def test_struct_layouts_match_header():
+    """The ctypes mirrors must have the C layout of orlg_config / orlg_tables / orlg_request."""
+    from optical_rl_gym_b200 import _native
+
+    assert ctypes.sizeof(_native.Config) == 104          # 2*i32, i64, 12*i32, u64, 4*f64 (with padding)
+    assert _native.Config.seed.offset % 8 == 0 and _native.Config.env_id_base.offset == 8
+    assert ctypes.sizeof(_native.Tables) == 6 * 4 + 14 * 8
+    assert _native.REQUEST_DTYPE.itemsize == 32
+    assert [_native.REQUEST_DTYPE.fields[n][1] for n in ("arrival", "holding", "src", "dst", "bit_rate")] == [0, 8, 16, 20, 24]
+
+
+def test_create_fails_cleanly_without_gpu_or_with_bad_arguments():
+    from optical_rl_gym_b200 import _native
+
+    lib = _native.lib()
+    out = ctypes.c_void_p()
+    assert lib.orlg_create(None, None, 0, ctypes.byref(out)) == -1
+    assert b"null" in lib.orlg_last_error()
+    cfg = _native.Config(kind=7, num_envs=4)
+    tab = _native.Tables()
+    assert lib.orlg_create(ctypes.byref(cfg), ctypes.byref(tab), 0, ctypes.byref(out)) == -1
+
+
+def test_product_fails_loudly_without_cuda():
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the GPU-less container")
+    from optical_rl_gym_b200 import OpticalVecEnv, _native
+
+    with pytest.raises(_native.NativeError):
+        OpticalVecEnv("DeepRMSA-v0", 4, helpers.golden_tables())
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "optical-rl-gym_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower() or f == "orlg_device.cuh" and "oracle reproduces" in text, \
+                    "%s mentions the oracle" % os.path.join(dirpath, f)
+
+
+def test_nsfnet_tables_equal_reference_pickle_tables():
+    """optical_rl_gym_b200.topology.nsfnet() (own link list + NetworkX KSP) == tables extracted from the
+    reference's nsfnet_chen_5-paths_6-modulations.h5 (tests/golden/nsfnet_tables.npz)."""
+    import dataclasses
+
+    from optical_rl_gym_b200.topology import nsfnet
+
+    a, b = nsfnet(), helpers.golden_tables()
+    assert (a.num_nodes, a.num_links, a.num_paths, a.k_paths) == (14, 22, 455, 5)
+    for f in dataclasses.fields(a):
+        if f.name == "name":
+            continue
+        x, y = getattr(a, f.name), getattr(b, f.name)
+        assert np.array_equal(x, y) if isinstance(x, np.ndarray) else x == y, f.name
+    # SURVEY.md section 8 facts
+    assert a.path_hops.min() == 1 and a.path_hops.max() == 9
+    assert int((a.path_se == 1).sum()) == 372
+
+
+def test_topology_roundtrip_and_synthetic(tmp_path):
+    from optical_rl_gym_b200.topology import TopologyTables, synthetic_ring_chords
+
+    t = synthetic_ring_chords(num_nodes=12, num_chords=10, k_paths=3, seed=3)
+    assert t.num_links == 22 and t.num_nodes == 12 and t.k_paths == 3
+    assert (t.pair_count[t.pair_first >= 0] >= 1).all()
+    p = tmp_path / "t.npz"
+    t.save(p)
+    u = TopologyTables.load(p)
+    assert np.array_equal(t.path_links, u.path_links) and u.node_names == t.node_names
+    for row in range(t.num_paths):                      # CSR consistency: hops == number of links, links chain the nodes
+        links = t.links_of(row)
+        assert len(links) == t.path_hops[row]
+
+
+def test_number_of_slots_integer_form_matches_reference_float_expression():
+    """ceil(b / (SE*12.5)) + 1 == (2b + 25SE - 1)//(25SE) + 1 for every table entry the library builds."""
+    import math
+
+    for se in range(1, 7):
+        for b in range(1, 1024):
+            assert math.ceil(b / (se * 12.5)) + 1 == (2 * b + 25 * se - 1) // (25 * se) + 1
