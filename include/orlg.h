@@ -36,7 +36,8 @@ enum { ORLG_OK = 0, ORLG_E_INVALID = -1, ORLG_E_UNSUPPORTED = -2, ORLG_E_CUDA = 
 enum {
     ORLG_ERR_TRACE_EXHAUSTED = 1,  /* the recorded trace has no request left */
     ORLG_ERR_HEAP_OVERFLOW = 2,    /* more live services than heap_capacity: the request was blocked */
-    ORLG_ERR_NO_SUCH_PATH = 4      /* action chose path >= number of candidate paths (reference: IndexError) */
+    ORLG_ERR_NO_SUCH_PATH = 4,     /* action chose path >= number of candidate paths (reference: IndexError) */
+    ORLG_ERR_LOCKSTEP = 8          /* internal: an env's request counter left the handle's lockstep count */
 };
 
 typedef struct orlg_env orlg_env;     /* opaque handle: owns all per-environment state in HBM */

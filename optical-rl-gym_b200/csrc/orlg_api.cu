@@ -363,7 +363,9 @@ int orlg_reset(orlg_env *env, int full, void *obs_dev, orlg_stream stream) {
     StepIO io;
     std::memset(&io, 0, sizeof(io));
     io.obs = env->p.obs_dim ? obs_dev : nullptr;
-    return launch_step(env, io, full ? MODE_FULL_RESET : MODE_EPISODE_RESET, (cudaStream_t)stream);
+    int rc = launch_step(env, io, full ? MODE_FULL_RESET : MODE_EPISODE_RESET, (cudaStream_t)stream);
+    if (rc == ORLG_OK && full) env->p.lockstep_ridx = 1;      // every env has drawn its first request
+    return rc;
 }
 
 int orlg_step(orlg_env *env, const int32_t *actions_dev, void *obs_dev, float *reward_dev, uint8_t *done_dev,
@@ -377,7 +379,9 @@ int orlg_step(orlg_env *env, const int32_t *actions_dev, void *obs_dev, float *r
     io.decision = decision_dev;
     io.info = reinterpret_cast<long long *>(info_dev);
     io.obs_int = nullptr;
-    return launch_step(env, io, MODE_STEP, (cudaStream_t)stream);
+    int rc = launch_step(env, io, MODE_STEP, (cudaStream_t)stream);
+    if (rc == ORLG_OK) env->p.lockstep_ridx++;
+    return rc;
 }
 
 int orlg_observation(orlg_env *env, void *obs_dev, orlg_stream stream) {

@@ -141,6 +141,21 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
         cp_async_commit();
     }
     // ---------------- stage 1: the scalar block
+    // The traffic draw of _next_service needs only (seed, global env id, request index).  All envs of a
+    // handle are reset and stepped together, so the request index is a launch parameter and the Philox
+    // rounds + the two logarithms run while the loads above are still in flight.
+    uint32_t rc_[4] = {0u, 0u, 0u, 0u}, rd_[4] = {0u, 0u, 0u, 0u};
+    double e_iat = 0.0, e_hold = 0.0;
+    if (p.traffic == ORLG_TRAFFIC_PHILOX && (mode == MODE_STEP || mode == MODE_FULL_RESET)) {
+        const unsigned long long gid = (unsigned long long)(p.env_id_base + e);
+        const unsigned r0 = mode == MODE_FULL_RESET ? 0u : p.lockstep_ridx;
+        rc_[0] = r0; rc_[2] = (uint32_t)gid; rc_[3] = 0u;
+        rd_[0] = r0; rd_[2] = (uint32_t)gid; rd_[3] = 1u;
+        philox4x32_10(rc_, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+        philox4x32_10(rd_, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+        e_iat = __dmul_rn(neg_log_u32(rc_[0]), p.mean_iat);
+        e_hold = __dmul_rn(neg_log_u32(rc_[1]), p.mean_holding);
+    }
     double now = p.now[e];
     double hold = p.cur_hold[e];
     uint2 rq = p.cur_req[e];
@@ -242,13 +257,10 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             double arrival, holding;
             int nsrc, ndst, nbr;
             if (p.traffic == ORLG_TRAFFIC_PHILOX) {
-                const unsigned long long gid = (unsigned long long)(p.env_id_base + e);
-                uint32_t c[4] = {ridx, 0u, (uint32_t)gid, 0u};
-                uint32_t d[4] = {ridx, 0u, (uint32_t)gid, 1u};
-                philox4x32_10(c, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-                philox4x32_10(d, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-                arrival = __dadd_rn(now, __dmul_rn(neg_log_u32(c[0]), p.mean_iat));
-                holding = __dmul_rn(neg_log_u32(c[1]), p.mean_holding);
+                const uint32_t *c = rc_, *d = rd_;
+                if (ridx != (mode == MODE_FULL_RESET ? 0u : p.lockstep_ridx)) err |= ORLG_ERR_LOCKSTEP;
+                arrival = __dadd_rn(now, e_iat);
+                holding = e_hold;
                 const int n = p.N;
                 nsrc = pick_thr_bsearch(s_node_thr, n, p.node_top_step, c[2]);
                 const unsigned lo = nsrc ? s_node_thr[nsrc - 1] : 0u;

@@ -45,6 +45,7 @@ struct Params {
     int off_pair_first, off_pair_count, off_path_lm, off_path_se, off_path_ll, off_nslots, off_node_thr, off_pos, off_nsl;
     int node_top_step;                 // highest power of two <= N-1 (binary search over the node CDF)
     int warp_area_bytes;               // fast kernel: shared-memory work area per warp (masks, then observation rows)
+    unsigned lockstep_ridx;            // requests drawn so far by EVERY env (all envs reset and step together)
     // ---- per-env state (struct of arrays)
     uint4 *masks;                      // [C*E][n]
     double *now;                       // [n] current_time
