@@ -220,6 +220,41 @@ def main():
     elapsed_ms = float(t.item())
     value = n * world * args.steps / (elapsed_ms * 1e-3)
 
+    # ---- end to end through the public API with HOST buffers (pinned): H2D actions, step, D2H obs/reward/done.
+    # Every rank runs it at the same time (they share the host's PCIe / memory), max over ranks.
+    e2e_result = None
+    if not args.no_e2e:
+        h_act = torch.zeros((n, 1), dtype=torch.int32).pin_memory()
+        h_obs = torch.zeros((n, env.obs_dim), dtype=torch.float32).pin_memory()
+        h_rew = torch.zeros(n, dtype=torch.float32).pin_memory()
+        h_done = torch.zeros(n, dtype=torch.uint8).pin_memory()
+        h_act.copy_(actions.cpu())
+        k_e2e = max(20, min(args.steps, 300))
+
+        def e2e_step():
+            d_act = h_act.to(dev, non_blocking=True)
+            obs, rew, done, _ = env.step(d_act)
+            h_obs.copy_(obs, non_blocking=True)
+            h_rew.copy_(rew, non_blocking=True)
+            h_done.copy_(done, non_blocking=True)
+            torch.cuda.synchronize()            # the host policy needs the observation before it can act
+
+        for _ in range(5):
+            e2e_step()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            e2e_step()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_result = {"value": n * world * k_e2e / float(dt.item()), "unit": "env-steps/s",
+                      "h2d_bytes_per_step": h_act.numel() * 4 * world,
+                      "d2h_bytes_per_step": (h_obs.numel() * 4 + h_rew.numel() * 4 + h_done.numel()) * world,
+                      "steps": k_e2e, "n_gpus": world,
+                      "note": "VecEnv.step with pinned host buffers on every rank concurrently, synchronised every step"}
+
     out = None
     if rank == 0:
         # ---- roofline of the dominant kernel (step_kernel): events around each step launch only
@@ -235,7 +270,7 @@ def main():
         peak, peak_src = read_peaks()
         achieved = B_STEP * n / (step_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "step_kernel<DEEPRMSA,5>", "kernel_ms": step_ms,
+                    "traffic": None, "kernel": "deeprmsa_fast_kernel<22,5,1,false>", "kernel_ms": step_ms,
                     "algorithmic_bytes_per_env_step": B_STEP, "peak_source": peak_src}
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -258,38 +293,7 @@ def main():
         del flush
         cold_ms = sorted(cold)[len(cold) // 2]
 
-        # ---- end to end through the public API with HOST buffers (pinned): H2D actions, step, D2H obs/reward/done
-        e2e = None
-        if not args.no_e2e:
-            h_act = torch.zeros((n, 1), dtype=torch.int32).pin_memory()
-            h_obs = torch.zeros((n, env.obs_dim), dtype=torch.float32).pin_memory()
-            h_rew = torch.zeros(n, dtype=torch.float32).pin_memory()
-            h_done = torch.zeros(n, dtype=torch.uint8).pin_memory()
-            h_act.copy_(actions.cpu())
-            k_e2e = max(20, min(args.steps, 300))
-
-            def e2e_step():
-                d_act = h_act.to(dev, non_blocking=True)
-                obs, rew, done, _ = env.step(d_act)
-                h_obs.copy_(obs, non_blocking=True)
-                h_rew.copy_(rew, non_blocking=True)
-                h_done.copy_(done, non_blocking=True)
-                torch.cuda.synchronize()            # the host policy needs the observation before it can act
-
-            for _ in range(5):
-                e2e_step()
-            t0 = time.perf_counter()
-            for _ in range(k_e2e):
-                e2e_step()
-            dt = time.perf_counter() - t0
-            e2e = {"value": n * k_e2e / dt, "unit": "env-steps/s", "h2d_bytes_per_step": h_act.numel() * 4,
-                   "d2h_bytes_per_step": h_obs.numel() * 4 + h_rew.numel() * 4 + h_done.numel(),
-                   "steps": k_e2e, "n_gpus": 1,
-                   "note": "VecEnv.step with pinned host buffers, synchronised every step; rank 0's shard"}
-            if world > 1:
-                e2e["value"] *= world
-                e2e["n_gpus"] = world
-                e2e["note"] += "; scaled by world size (ranks are independent)"
+        e2e = e2e_result
 
         cpu = None if args.no_cpu_baseline else cpu_baseline(os.cpu_count() or 1)
         out = {
