@@ -363,6 +363,10 @@ int orlg_reset(orlg_env *env, int full, void *obs_dev, orlg_stream stream) {
     StepIO io;
     std::memset(&io, 0, sizeof(io));
     io.obs = env->p.obs_dim ? obs_dev : nullptr;
+    if (full) {
+        fill_events_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(env->p);
+        CUDA_OK(cudaGetLastError());
+    }
     int rc = launch_step(env, io, full ? MODE_FULL_RESET : MODE_EPISODE_RESET, (cudaStream_t)stream);
     if (rc == ORLG_OK && full) env->p.lockstep_ridx = 1;      // every env has drawn its first request
     return rc;
@@ -465,6 +469,17 @@ int orlg_debug_phase_cycles(unsigned long long *out16) {
     return ORLG_OK;
 #else
     (void)out16;
+    return fail(ORLG_E_UNSUPPORTED, "built without -DORLG_PHASE_TIMING");
+#endif
+}
+
+// debug (instrumented builds only): per-warp globaltimer entry/exit of the last fast-kernel launch
+int orlg_debug_warp_timeline(unsigned long long *out, int n_warps) {
+#ifdef ORLG_PHASE_TIMING
+    CUDA_OK(cudaMemcpyFromSymbol(out, g_warp_timeline, (size_t)2 * n_warps * sizeof(unsigned long long)));
+    return ORLG_OK;
+#else
+    (void)out; (void)n_warps;
     return fail(ORLG_E_UNSUPPORTED, "built without -DORLG_PHASE_TIMING");
 #endif
 }

@@ -100,8 +100,16 @@ __device__ __forceinline__ int pick_thr_bsearch(const unsigned *thr, int n, int 
         if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase_cycles[k], (unsigned long long)(t_now_ - t_prev_)); \
         t_prev_ = t_now_;                                                    \
     } while (0)
-#define PHASE_INIT() long long t_prev_ = clock64()
+#define PHASE_INIT() long long t_prev_ = clock64(); unsigned long long gt0_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0_))
+__device__ unsigned long long g_warp_timeline[2 * 65536];      // per warp: globaltimer at entry / exit (ns), last launch
+#define PHASE_END()                                                                          \
+    do {                                                                                     \
+        unsigned long long gt1_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1_));    \
+        const unsigned w_ = (blockIdx.x * FAST_THREADS + threadIdx.x) >> 5;                   \
+        if ((threadIdx.x & 31) == 0 && w_ < 65536) { g_warp_timeline[2 * w_] = gt0_; g_warp_timeline[2 * w_ + 1] = gt1_; } \
+    } while (0)
 #else
+#define PHASE_END() do { } while (0)
 #define PHASE_MARK(k) do { } while (0)
 #define PHASE_INIT() do { } while (0)
 #endif
@@ -163,9 +171,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
 #pragma unroll
     for (int q = 0; q < 8; q++) cnt[q] = p.counters[(size_t)q * p.n + e];
     unsigned ridx = p.req_index[e];
-    unsigned nheap = p.nheap[e];              // live services | prefetch hint << 16
-    unsigned ehint = nheap >> 16;
-    nheap &= 0xffffu;
+    unsigned nheap = p.nheap[e];
     double hmin = p.heap_min[e];
     unsigned err = p.errors[e];
     const int act = (mode == MODE_STEP) ? io.actions[e] : -1;
@@ -173,7 +179,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
     if (p.cand_stride == 8) candw = *reinterpret_cast<const unsigned long long *>(p.cand + (size_t)e * 8);
     const Events ev = {p.ev_time + (size_t)e * p.heap_cap, p.ev_pay + (size_t)e * p.heap_cap, p.ev_gmin + (size_t)e * p.ev_groups};
     double tailmin = p.ev_tail[e];
-    if (mode == MODE_STEP && hmin <= now + 4.0 * p.mean_iat) events_prefetch(ev, nheap, ehint);     // a release is likely
+    if (mode == MODE_STEP && hmin <= now + 4.0 * p.mean_iat) prefetch_l2(ev.gmin);     // a release is likely: warm the directory
 
     const unsigned short *s_pair_first = reinterpret_cast<const unsigned short *>(smem + p.off_pair_first);
     const unsigned char *s_pair_count = smem + p.off_pair_count;
@@ -199,7 +205,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
     Bits A[KM];
 
     if (mode == MODE_FULL_RESET) {
-        now = 0.0; nheap = 0; ehint = 0; hmin = ORLG_INF; tailmin = ORLG_INF; ridx = 0; err = 0;
+        now = 0.0; nheap = 0; hmin = ORLG_INF; tailmin = ORLG_INF; ridx = 0; err = 0;
         dirty = E >= 32 ? 0xFFFFFFFFu : ((1u << E) - 1u);
         const uint4 full = bits_to(bits_range(0, p.S));
         for (int l = 0; l < E; l++) sm[l * 32] = full;
@@ -230,7 +236,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
                             a_lm = s_path_lm[a_row];
                             a_start = (int)st;
                             const double rel = __dadd_rn(now, hold);
-                            events_push(ev, nheap, ehint, hmin, tailmin, rel, pack_service(a_row, a_start, a_n, 0, sid));
+                            events_push(ev, nheap, hmin, tailmin, rel, pack_service(a_row, a_start, a_n, 0, sid));
                             cnt[1] += 1; cnt[3] += 1; cnt[5] += br; cnt[7] += br;
                             accepted = true;
                             d_row = a_row; d_start = a_start; d_n = a_n;
@@ -303,7 +309,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             dirty |= a_lm;
         }
         if (mode == MODE_STEP || mode == MODE_FULL_RESET) {
-            events_release(ev, nheap, ehint, hmin, tailmin, now, [&](unsigned long long pl) {     // rmsa_env.py:591-597
+            events_release(ev, nheap, hmin, tailmin, now, [&](unsigned long long pl) {     // rmsa_env.py:591-597
                 const unsigned lm = s_path_lm[svc_row(pl)];
                 const int rs = svc_start(pl);
                 const Bits rm = bits_range(rs, rs + svc_slots(pl));
@@ -539,7 +545,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
 #pragma unroll
             for (int q = 0; q < 8; q++) p.counters[(size_t)q * p.n + env] = cnt[q];
             p.req_index[env] = ridx;
-            p.nheap[env] = nheap | (ehint << 16);
+            p.nheap[env] = nheap;
             p.heap_min[env] = hmin;
             p.ev_tail[env] = tailmin;
             p.errors[env] = err;
@@ -576,6 +582,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
         }
     }
     PHASE_MARK(12);         // observation tile copy-out
+    PHASE_END();
 }
 
 }  // namespace orlg

@@ -209,19 +209,20 @@ __device__ unsigned long long g_phase_cycles[16];
 #endif
 
 struct Events {
-    double *t;                    // [cap] release times of this env
+    double *t;                    // [cap] release times of this env; every slot >= n holds +INF
     unsigned long long *p;        // [cap] packed services
-    float *gmin;                  // [cap / EV_GROUP] lower bound of each full group's earliest time
+    float *gmin;                  // [cap / EV_GROUP] lower bound of each FULL group's earliest time; +INF from the tail group on
 };
 
 __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
 __device__ __forceinline__ float lower_f32(double x) { return __double2float_rd(x); }
+#define ORLG_INF_F __int_as_float(0x7f800000)
 // plain minimum of finite values (fmin()'s NaN handling costs several extra instructions)
 __device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
 
-__device__ __forceinline__ void events_push(const Events &ev, unsigned &n, unsigned &hint, double &tmin, double &tail_min,
-                                            double t, unsigned long long payload) {
+__device__ __forceinline__ void events_push(const Events &ev, unsigned &n, double &tmin, double &tail_min, double t,
+                                            unsigned long long payload) {
     if ((n & (EV_GROUP - 1)) == 0) {             // opening a new tail group: publish the previous group's bound
         if (n > 0) ev.gmin[(n / EV_GROUP) - 1] = lower_f32(tail_min);
         tail_min = ORLG_INF;
@@ -230,78 +231,58 @@ __device__ __forceinline__ void events_push(const Events &ev, unsigned &n, unsig
     ev.p[n] = payload;
     n++;
     tail_min = dmin(tail_min, t);
-    if (t < tmin) { tmin = t; hint = (n - 1) / EV_GROUP; }
-}
-
-// Issue (early, no registers) the fetches a release in this step would need: the directory, the group that
-// holds the earliest bound (`hint`: a prefetch hint only, correctness never depends on it) and the tail entry.
-__device__ __forceinline__ void events_prefetch(const Events &ev, unsigned n, unsigned hint) {
-    if (n == 0) return;
-    prefetch_l2(ev.gmin);
-    const unsigned g = min(hint, (n - 1) / EV_GROUP);
-    prefetch_l2(ev.t + g * EV_GROUP);
-    prefetch_l2(ev.p + g * EV_GROUP);
-    prefetch_l2(ev.t + (n - 1));
-    prefetch_l2(ev.p + (n - 1));
+    tmin = dmin(tmin, t);
 }
 
 // Releases every service with time <= now; `apply(payload)` frees its slots.  Updates n, tmin, tail_min.
-// Invariants: gmin[g] <= every time in full group g; tail_min <= every time in the tail group;
-// tmin <= every time.  Due services can therefore only sit in groups whose bound is <= now; those are
-// scanned from the highest group down, so the tail entry that fills a hole is never itself due.
+// Invariants: gmin[g] <= every time in full group g (g < tail group) and +INF from the tail group on;
+// tail_min <= every time in the tail group; tmin <= every time; t[s] = +INF for s >= n.  Due services can
+// therefore only sit in groups whose bound is <= now; those are scanned from the highest group down, so the
+// tail entry that fills a hole is never itself due.  All bounds are lower bounds (floats rounded down), which
+// is all the gate needs; the comparisons that decide a release use the exact float64 times.
 template <typename Apply>
-__device__ __forceinline__ void events_release(const Events &ev, unsigned &n, unsigned &hint, double &tmin, double &tail_min,
+__device__ __forceinline__ void events_release(const Events &ev, unsigned &n, double &tmin, double &tail_min,
                                                const double now, Apply apply) {
     SUBPHASE_BEGIN();
     if (n == 0 || tmin > now) return;
-    const unsigned ng = (n + EV_GROUP - 1) / EV_GROUP;
-    // ---- directory: which groups may hold a due service?
+    const unsigned tail0 = (n - 1) / EV_GROUP;     // tail group on entry
+    // ---- directory: which full groups may hold a due service?  (entries >= tail0 are +INF)
     unsigned long long due_groups = 0;
-    unsigned arg = 0;                           // group of the smallest staying bound (next step's prefetch hint)
-    float fbound = __int_as_float(0x7f800000);  // lower bound (float) over the full groups that stay
-    const float now_up = __double2float_ru(now);   // conservative: f <= now_up whenever (double)f <= now
-    for (unsigned c = 0; c + 1 < ng; c += 16) {    // full groups only: the tail group is handled below
+    float fbound = ORLG_INF_F;                      // lower bound over the full groups that stay
+    const float now_up = __double2float_ru(now);    // f <= now_up whenever (double)f <= now
+    for (unsigned c = 0; c < tail0; c += 16) {
         float4 d[4];
 #pragma unroll
-        for (int q = 0; q < 4; q++)
-            if (c + 4 * q + 1 < ng) d[q] = reinterpret_cast<const float4 *>(ev.gmin + c)[q];
+        for (int q = 0; q < 4; q++) d[q] = reinterpret_cast<const float4 *>(ev.gmin + c)[q];
+        unsigned m16 = 0;
 #pragma unroll
         for (int q = 0; q < 16; q++) {
-            const unsigned g = c + q;
             const float4 v = d[q >> 2];
             const float f = (q & 3) == 0 ? v.x : ((q & 3) == 1 ? v.y : ((q & 3) == 2 ? v.z : v.w));
-            const bool in = g + 1 < ng;
-            const bool due = in && f <= now_up;
-            due_groups |= due ? (1ULL << g) : 0ULL;
-            const bool lower = in && !due && f < fbound;
-            arg = lower ? g : arg;
-            fbound = lower ? f : fbound;
+            const bool due = f <= now_up;
+            m16 |= due ? (1u << q) : 0u;
+            fbound = fminf(fbound, due ? ORLG_INF_F : f);
         }
+        due_groups |= (unsigned long long)m16 << c;
     }
-    double bound = (double)fbound;
-    if (tail_min <= now) due_groups |= 1ULL << (ng - 1);
-    else if (tail_min < bound) { bound = tail_min; arg = ng - 1; }
+    float fb = fbound;
+    if (tail_min <= now) due_groups |= 1ULL << tail0; else fb = fminf(fb, lower_f32(tail_min));
     SUBPHASE_MARK(13);                         // directory
-    unsigned tail_pub = ng - 1;                // the group that `tail_min` currently describes
+    unsigned tail_pub = tail0;                 // the group that `tail_min` currently describes
     while (due_groups) {
         const unsigned g = 63 - __clzll(due_groups);
         due_groups &= ~(1ULL << g);
         const unsigned s0 = g * EV_GROUP;
         if (s0 >= n) continue;                 // the group vanished while the tail shrank
-        double tv[EV_GROUP];
+        unsigned duebits = 0;
+        float gm = ORLG_INF_F;                 // lower bound of what stays in this group
 #pragma unroll
         for (int q = 0; q < EV_GROUP / 2; q++) {
             const double2 v = reinterpret_cast<const double2 *>(ev.t + s0)[q];
-            tv[2 * q] = v.x; tv[2 * q + 1] = v.y;
-        }
-        unsigned duebits = 0;
-        double gm = ORLG_INF;                  // exact earliest time of what stays in this group
-#pragma unroll
-        for (int q = 0; q < EV_GROUP; q++) {
-            const bool valid = s0 + q < n;
-            const bool due = valid && tv[q] <= now;
-            duebits |= due ? (1u << q) : 0u;
-            gm = (valid && !due && tv[q] < gm) ? tv[q] : gm;
+            const bool d0 = v.x <= now, d1 = v.y <= now;        // slots >= n hold +INF: never due
+            duebits |= (d0 ? (1u << (2 * q)) : 0u) | (d1 ? (2u << (2 * q)) : 0u);
+            gm = fminf(gm, d0 ? ORLG_INF_F : lower_f32(v.x));
+            gm = fminf(gm, d1 ? ORLG_INF_F : lower_f32(v.y));
         }
         SUBPHASE_MARK(14);                     // group fetch + classify
         while (duebits) {                      // highest slot first
@@ -315,23 +296,28 @@ __device__ __forceinline__ void events_release(const Events &ev, unsigned &n, un
                 const unsigned long long lp = ev.p[last];
                 ev.t[s] = lt;
                 ev.p[s] = lp;
-                gm = dmin(gm, lt);
+                gm = fminf(gm, lower_f32(lt));
             }
+            ev.t[last] = ORLG_INF;             // keep "t[s] = +INF for s >= n"
             n--;
             apply(pl);
         }
         SUBPHASE_MARK(15);                     // payload fetch, hole fill, apply
-        if (s0 < n) {                          // publish the exact bound of what is left of this group
-            if (g == (n - 1) / EV_GROUP) { tail_min = gm; tail_pub = g; }
-            else ev.gmin[g] = lower_f32(gm);
-            if (gm < bound) { bound = gm; arg = g; }
+        if (s0 < n) {                          // publish the bound of what is left of this group
+            if (g == (n - 1) / EV_GROUP) { tail_min = (double)gm; tail_pub = g; }
+            else ev.gmin[g] = gm;
+            fb = fminf(fb, gm);
         }
     }
-    if (n == 0) { tmin = ORLG_INF; tail_min = ORLG_INF; hint = 0; return; }
+    if (n == 0) {
+        for (unsigned g = 0; g <= tail0; g++) ev.gmin[g] = ORLG_INF_F;
+        tmin = ORLG_INF; tail_min = ORLG_INF;
+        return;
+    }
     const unsigned tail_g = (n - 1) / EV_GROUP;
     if (tail_g != tail_pub) tail_min = (double)ev.gmin[tail_g];    // the tail shrank into an older, published group
-    tmin = bound;
-    hint = arg;
+    for (unsigned g = tail_g; g < tail0; g++) ev.gmin[g] = ORLG_INF_F;   // directory is +INF from the (new) tail group on
+    tmin = (double)fb;
 }
 
 // payload: path row (20 bits) | start (9) | slots (8) | core (5) | service id (22)

@@ -164,9 +164,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
 #pragma unroll
     for (int q = 0; q < 8; q++) cnt[q] = p.counters[(size_t)q * p.n + e];
     unsigned ridx = p.req_index[e];
-    unsigned nheap = p.nheap[e];              // live services | prefetch hint << 16
-    unsigned ehint = nheap >> 16;
-    nheap &= 0xffffu;
+    unsigned nheap = p.nheap[e];
     double hmin = p.heap_min[e];
     unsigned err = p.errors[e];
     const Events ev = {p.ev_time + (size_t)e * p.heap_cap, p.ev_pay + (size_t)e * p.heap_cap, p.ev_gmin + (size_t)e * p.ev_groups};
@@ -182,7 +180,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
         Bits full = bits_range(0, p.S);
         if (live)
             for (int l = 0; l < p.C * p.E; l++) p.masks[(size_t)l * p.n + env] = bits_to(full);
-        now = 0.0; nheap = 0; ehint = 0; hmin = ORLG_INF; tailmin = ORLG_INF; ridx = 0; err = 0;
+        now = 0.0; nheap = 0; hmin = ORLG_INF; tailmin = ORLG_INF; ridx = 0; err = 0;
 #pragma unroll
         for (int q = 0; q < 8; q++) cnt[q] = 0;
     }
@@ -259,7 +257,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
             if (live) {
                 path_update(p, env, lm, core, bits_range(start, start + n), false);
                 double rel = __dadd_rn(now, hold);          // arrival_time + holding_time (now == arrival)
-                events_push(ev, nheap, ehint, hmin, tailmin, rel, pack_service(row, start, n, core, sid));
+                events_push(ev, nheap, hmin, tailmin, rel, pack_service(row, start, n, core, sid));
             }
             cnt[1] += 1; cnt[3] += 1;                        // services_accepted (+episode)
             if (KIND != ORLG_RWA) { cnt[5] += br; cnt[7] += br; }   // bit_rate_provisioned (+episode)
@@ -309,7 +307,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
             cnt[4] += br; cnt[6] += br;                       // rmcsa_env.py:730-731
         }
         // release every service whose time has come (rmsa_env.py:591-597)
-        events_release(ev, nheap, ehint, hmin, tailmin, now, [&](unsigned long long pl) {
+        events_release(ev, nheap, hmin, tailmin, now, [&](unsigned long long pl) {
             const int rs = svc_start(pl);
             path_update(p, env, p.path_linkmask[svc_row(pl)], svc_core(pl), bits_range(rs, rs + svc_slots(pl)), true);
         });
@@ -453,7 +451,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
 #pragma unroll
         for (int q = 0; q < 8; q++) p.counters[(size_t)q * p.n + env] = cnt[q];
         p.req_index[env] = ridx;
-        p.nheap[env] = nheap | (ehint << 16);
+        p.nheap[env] = nheap;
         p.heap_min[env] = hmin;
         p.ev_tail[env] = tailmin;
         p.errors[env] = err;
@@ -572,6 +570,14 @@ __global__ void random_action_kernel(const Params p, int *actions) {
     }
 }
 
+// full reset: empty release-event tables (every time slot and every directory entry = +INF)
+__global__ void fill_events_kernel(const Params p) {
+    const size_t nt = (size_t)p.n * p.heap_cap, ng = (size_t)p.n * p.ev_groups;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += stride) p.ev_time[i] = ORLG_INF;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ng; i += stride) p.ev_gmin[i] = ORLG_INF_F;
+}
+
 // ---------------------------------------------------------------- introspection kernels
 __global__ void export_kernel(const Params p, unsigned *masks_out, int *alloc_out, double *now_out, int *nheap_out,
                               long long *counters_out, orlg_request *req_out, int *sid_out, unsigned *err_out) {
@@ -589,7 +595,7 @@ __global__ void export_kernel(const Params p, unsigned *masks_out, int *alloc_ou
         int *o = alloc_out + (size_t)env * CE * p.S;
         for (int q = 0; q < CE * p.S; q++) o[q] = -1;
         const unsigned long long *h = p.ev_pay + (size_t)env * p.heap_cap;
-        const unsigned nh = p.nheap[env] & 0xffffu;
+        const unsigned nh = p.nheap[env];
         for (unsigned s = 0; s < nh; s++) {
             unsigned long long pl = h[s];
             unsigned lm = p.path_linkmask[svc_row(pl)];
@@ -601,7 +607,7 @@ __global__ void export_kernel(const Params p, unsigned *masks_out, int *alloc_ou
         }
     }
     if (now_out) now_out[env] = p.now[env];
-    if (nheap_out) nheap_out[env] = (int)(p.nheap[env] & 0xffffu);
+    if (nheap_out) nheap_out[env] = (int)p.nheap[env];
     if (counters_out)
         for (int q = 0; q < 8; q++) counters_out[(size_t)env * 8 + q] = p.counters[(size_t)q * p.n + env];
     if (req_out) {
