@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "orlg_deeprmsa_fast.cuh"
+#include "orlg_step_wide.cuh"
 
 using namespace orlg;
 
@@ -30,6 +31,7 @@ struct orlg_env {
     int device;
     int km;                       // KM template instance (5 or 8)
     bool fast;                    // DeepRMSA fast kernel applicable (NSFNET-class: 22 links, k <= 5)
+    bool wide;                    // beyond 32 links / 128 slots / 8 paths: CSR link lists, multi-word masks
     size_t fast_smem;
     size_t obs_smem;
     int64_t state_bytes;
@@ -109,7 +111,39 @@ void launch_fast(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s
     else deeprmsa_fast_kernel<0, 5, JT, OBS64><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode);
 }
 
+template <int KIND>
+void launch_wide_kind(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s) {
+    const int blocks = (env->p.n + 127) / 128;
+    switch (env->p.nwv) {
+    case 1: step_wide_kernel<KIND, 1><<<blocks, 128, 0, s>>>(env->p, io, mode); break;
+    case 2: step_wide_kernel<KIND, 2><<<blocks, 128, 0, s>>>(env->p, io, mode); break;
+    case 3: step_wide_kernel<KIND, 3><<<blocks, 128, 0, s>>>(env->p, io, mode); break;
+    default: step_wide_kernel<KIND, 4><<<blocks, 128, 0, s>>>(env->p, io, mode); break;
+    }
+}
+
+template <int KIND>
+void launch_heuristic_wide(const orlg_env *env, int which, int *actions, cudaStream_t s) {
+    const int blocks = (env->p.n + 127) / 128;
+    switch (env->p.nwv) {
+    case 1: heuristic_wide_kernel<KIND, 1><<<blocks, 128, 0, s>>>(env->p, which, actions); break;
+    case 2: heuristic_wide_kernel<KIND, 2><<<blocks, 128, 0, s>>>(env->p, which, actions); break;
+    case 3: heuristic_wide_kernel<KIND, 3><<<blocks, 128, 0, s>>>(env->p, which, actions); break;
+    default: heuristic_wide_kernel<KIND, 4><<<blocks, 128, 0, s>>>(env->p, which, actions); break;
+    }
+}
+
 int launch_step(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s) {
+    if (env->wide) {
+        switch (env->p.kind) {
+        case ORLG_RWA: launch_wide_kind<ORLG_RWA>(env, io, mode, s); break;
+        case ORLG_RMSA: launch_wide_kind<ORLG_RMSA>(env, io, mode, s); break;
+        case ORLG_DEEPRMSA: launch_wide_kind<ORLG_DEEPRMSA>(env, io, mode, s); break;
+        default: launch_wide_kind<ORLG_RMCSA>(env, io, mode, s); break;
+        }
+        CUDA_OK(cudaGetLastError());
+        return ORLG_OK;
+    }
     if (env->fast) {
         if (env->p.J == 1) { if (env->p.obs_f64) launch_fast<1, true>(env, io, mode, s); else launch_fast<1, false>(env, io, mode, s); }
         else { if (env->p.obs_f64) launch_fast<0, true>(env, io, mode, s); else launch_fast<0, false>(env, io, mode, s); }
@@ -139,10 +173,11 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     *out = nullptr;
     if (cfg->kind < ORLG_RWA || cfg->kind > ORLG_RMCSA) return fail(ORLG_E_INVALID, "unknown env kind");
     if (cfg->num_envs <= 0) return fail(ORLG_E_INVALID, "num_envs must be positive");
-    if (t->num_links > 32 || cfg->num_slots > MAX_SLOTS || cfg->num_slots <= 0)
-        return fail(ORLG_E_UNSUPPORTED, "this build handles <= 32 links and <= 128 slots per link (NSFNET class)");
+    if (cfg->num_slots > 512 || cfg->num_slots <= 0) return fail(ORLG_E_UNSUPPORTED, "1..512 slots per link");
+    if (t->num_links < 1 || t->num_links > 65535) return fail(ORLG_E_UNSUPPORTED, "1..65535 links");
     if (t->num_nodes > 255 || t->num_nodes < 2) return fail(ORLG_E_UNSUPPORTED, "2..255 nodes");
-    if (t->k_paths > KMAX || t->k_paths < 1) return fail(ORLG_E_UNSUPPORTED, "k_paths must be 1..8");
+    if (t->k_paths > 16 || t->k_paths < 1) return fail(ORLG_E_UNSUPPORTED, "k_paths must be 1..16");
+    const bool wide = t->num_links > 32 || cfg->num_slots > MAX_SLOTS || t->k_paths > KMAX;
     if (t->num_paths >= (1 << 20)) return fail(ORLG_E_UNSUPPORTED, "too many paths");
     const int C = cfg->kind == ORLG_RMCSA ? cfg->num_cores : 1;
     if (C < 1 || C > 31) return fail(ORLG_E_UNSUPPORTED, "1..31 cores");
@@ -159,6 +194,7 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     env->cfg = *cfg;
     env->device = device;
     env->state_bytes = 0;
+    env->wide = wide;
     Params &p = env->p;
     std::memset(&p, 0, sizeof(p));
     p.kind = cfg->kind; p.n = cfg->num_envs; p.N = t->num_nodes; p.E = t->num_links; p.C = C; p.S = cfg->num_slots;
@@ -175,6 +211,7 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     p.mean_holding = cfg->mean_holding; p.mean_iat = cfg->mean_iat;
     p.obs_dim = cfg->kind == ORLG_DEEPRMSA ? 1 + 2 * p.N + (2 * J + 3) * p.k : 0;
     p.cand_stride = ((p.k * J + 7) / 8) * 8;
+    p.nwv = wide ? (p.S + 127) / 128 : 1;
     env->km = p.k <= 5 ? 5 : KMAX;
     env->obs_smem = (size_t)STEP_THREADS * p.obs_dim * (p.obs_f64 ? 8 : 4);
     if (env->obs_smem > 200 * 1024) { delete env; return fail(ORLG_E_UNSUPPORTED, "observation too large for the staging tile"); }
@@ -202,7 +239,11 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     int se_max = 1;
     for (int r = 0; r < P; r++) {
         unsigned lm = 0;
-        for (int h = t->path_link_ptr[r]; h < t->path_link_ptr[r + 1]; h++) lm |= 1u << t->path_links[h];
+        for (int h = t->path_link_ptr[r]; h < t->path_link_ptr[r + 1]; h++) {
+            if (t->path_links[h] < 0 || t->path_links[h] >= p.E) { delete env; return fail(ORLG_E_INVALID, "path link index out of range"); }
+            if (!wide) lm |= 1u << t->path_links[h];
+        }
+        if (t->path_hops[r] > 255 || t->path_link_ptr[r + 1] - t->path_link_ptr[r] != t->path_hops[r]) { delete env; return fail(ORLG_E_INVALID, "inconsistent path hop counts"); }
         linkmask[r] = lm;
         int se = t->path_se[r] < 1 ? 1 : t->path_se[r];
         meta[r] = (unsigned)(t->path_hops[r] & 0xff) | ((unsigned)(se & 0xff) << 8) | ((unsigned)(t->path_mod[r] & 0xff) << 16);
@@ -234,6 +275,13 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     if (!rc) rc = dev_upload(env, &p.path_linkmask, linkmask);
     if (!rc) rc = dev_upload(env, &p.path_meta, meta);
     if (!rc) rc = dev_upload(env, &p.path_length, plen);
+    {
+        std::vector<int> lptr(t->path_link_ptr, t->path_link_ptr + P + 1);
+        std::vector<unsigned short> l16(lptr[P] > 0 ? lptr[P] : 1, 0);
+        for (int h = 0; h < lptr[P]; h++) l16[h] = (unsigned short)t->path_links[h];
+        if (!rc) rc = dev_upload(env, &p.path_link_ptr, lptr);
+        if (!rc) rc = dev_upload(env, &p.path_links16, l16);
+    }
     if (!rc) rc = dev_upload(env, &p.nslots, nslots);
     if (!rc) rc = dev_upload(env, &p.mod_se, mod_se);
     if (!rc) rc = dev_upload(env, &p.reach, reach);
@@ -242,7 +290,7 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     if (!rc) rc = dev_upload(env, &p.bit_rates, bit_rates);
     // ---- state
     const size_t n = (size_t)p.n;
-    if (!rc) rc = dev_alloc(env, &p.masks, (size_t)C * p.E * n);
+    if (!rc) rc = dev_alloc(env, &p.masks, (size_t)C * p.E * p.nwv * n);
     if (!rc) rc = dev_alloc(env, &p.now, n);
     if (!rc) rc = dev_alloc(env, &p.cur_hold, n);
     if (!rc) rc = dev_alloc(env, &p.cur_req, n);
@@ -255,12 +303,13 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     if (!rc) rc = dev_alloc(env, &p.ev_gmin, n * (size_t)p.ev_groups);
     if (!rc) rc = dev_alloc(env, &p.ev_tail, n);
     if (!rc) rc = dev_alloc(env, &p.cand, n * (size_t)p.cand_stride);
+    if (!rc && wide && cfg->kind == ORLG_DEEPRMSA) rc = dev_alloc(env, &p.cand16, n * (size_t)p.cand_stride);
     if (!rc) rc = dev_alloc(env, &p.errors, n);
     if (rc) { orlg_destroy(env); return rc; }
 
     // ---- fast DeepRMSA kernel: small tables packed for shared-memory staging
     env->fast = false;
-    if (cfg->kind == ORLG_DEEPRMSA && p.k <= 5 && P <= 65535 && se_max <= 15 && !std::getenv("ORLG_FORCE_GENERIC")) {
+    if (!wide && cfg->kind == ORLG_DEEPRMSA && p.k <= 5 && P <= 65535 && se_max <= 15 && !std::getenv("ORLG_FORCE_GENERIC")) {
         std::vector<unsigned char> blob;
         auto put = [&blob](const void *src, size_t bytes) {
             size_t off = (blob.size() + 15) / 16 * 16;
@@ -344,7 +393,7 @@ int orlg_destroy(orlg_env *env) {
 
 int orlg_action_dim(const orlg_env *env) { return env->p.kind == ORLG_DEEPRMSA ? 1 : (env->p.kind == ORLG_RMCSA ? 4 : 2); }
 int orlg_obs_dim(const orlg_env *env) { return env->p.obs_dim; }
-int orlg_mask_words(const orlg_env *env) { (void)env; return NW; }
+int orlg_mask_words(const orlg_env *env) { return NW * env->p.nwv; }
 int orlg_heap_capacity(const orlg_env *env) { return env->p.heap_cap; }
 int64_t orlg_state_bytes(const orlg_env *env) { return env->state_bytes; }
 
@@ -411,6 +460,18 @@ int orlg_heuristic(orlg_env *env, int which, int32_t *actions_dev, orlg_stream s
     if (which < 0 || which > ORLG_HEUR_SAP_LF) return fail(ORLG_E_INVALID, "unknown heuristic");
     const int threads = 128, blocks = (env->p.n + threads - 1) / threads;
     cudaStream_t s = (cudaStream_t)stream;
+    if (env->wide) {
+        if (env->p.kind == ORLG_RMSA && which == ORLG_HEUR_SAP_LF) return fail(ORLG_E_UNSUPPORTED, "last-fit exists for RWA only");
+        if (env->p.kind == ORLG_DEEPRMSA && which > ORLG_HEUR_SAP_FF) return fail(ORLG_E_UNSUPPORTED, "DeepRMSA has SP-FF and SAP-FF only");
+        switch (env->p.kind) {
+        case ORLG_RWA: launch_heuristic_wide<ORLG_RWA>(env, which, actions_dev, s); break;
+        case ORLG_RMSA: launch_heuristic_wide<ORLG_RMSA>(env, which, actions_dev, s); break;
+        case ORLG_DEEPRMSA: launch_heuristic_wide<ORLG_DEEPRMSA>(env, which, actions_dev, s); break;
+        default: launch_heuristic_wide<ORLG_RMCSA>(env, which, actions_dev, s); break;
+        }
+        CUDA_OK(cudaGetLastError());
+        return ORLG_OK;
+    }
     switch (env->p.kind) {
     case ORLG_RWA: heuristic_kernel<ORLG_RWA><<<blocks, threads, 0, s>>>(env->p, which, actions_dev); break;
     case ORLG_RMSA:
@@ -437,6 +498,11 @@ static int run_export(orlg_env *env, uint32_t *masks, int32_t *alloc, double *no
                       orlg_request *req, int32_t *sid, uint32_t *err, orlg_stream stream) {
     if (!env) return fail(ORLG_E_INVALID, "null handle");
     const int threads = 128, blocks = (env->p.n + threads - 1) / threads;
+    if (env->wide && (masks || alloc)) {
+        export_wide_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->p, masks, alloc);
+        CUDA_OK(cudaGetLastError());
+        masks = nullptr; alloc = nullptr;
+    }
     export_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->p, masks, alloc, now, nheap,
                                                                 reinterpret_cast<long long *>(counters), req, sid, err);
     CUDA_OK(cudaGetLastError());

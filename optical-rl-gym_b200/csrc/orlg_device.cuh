@@ -268,6 +268,17 @@ __device__ __forceinline__ void events_release(const Events &ev, unsigned &n, do
     float fb = fbound;
     if (tail_min <= now) due_groups |= 1ULL << tail0; else fb = fminf(fb, lower_f32(tail_min));
     SUBPHASE_MARK(13);                         // directory
+    {   // start every fetch the scans below will need (times + payloads of the due groups, the tail entry)
+        unsigned long long m = due_groups;
+        while (m) {
+            const unsigned g = 63 - __clzll(m);
+            m &= ~(1ULL << g);
+            prefetch_l2(ev.t + g * EV_GROUP);
+            prefetch_l2(ev.p + g * EV_GROUP);
+        }
+        prefetch_l2(ev.t + (n - 1));
+        prefetch_l2(ev.p + (n - 1));
+    }
     unsigned tail_pub = tail0;                 // the group that `tail_min` currently describes
     while (due_groups) {
         const unsigned g = 63 - __clzll(due_groups);

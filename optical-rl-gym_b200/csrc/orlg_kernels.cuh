@@ -31,6 +31,8 @@ struct Params {
     const unsigned *path_linkmask;     // [P]  bit l = link l on the path (E <= 32)
     const unsigned *path_meta;         // [P]  hops | se << 8 | mod << 16
     const double *path_length;         // [P]
+    const int *path_link_ptr;          // [P+1] CSR of the hop lists (wide kernels)
+    const unsigned short *path_links16;  // link index of every hop
     const unsigned char *nslots;       // [(se or mod-se) * (br_max+1) + bit_rate]  rmsa_env.py:610-621
     const unsigned char *mod_se;       // [M]
     const double *reach;               // [M * (br_max+1)] min(lmax_snr, lmax_xt) of rmcsa_env.py:341-384
@@ -61,6 +63,8 @@ struct Params {
     double *ev_tail;                   // [n] lower bound of the open tail group
     int ev_groups;                     // directory stride (multiple of 16)
     unsigned char *cand;               // [n][cand_stride] first-fit block starts of the pending request
+    unsigned short *cand16;            // same for the wide layout (S > 128)
+    int nwv;                           // 128-bit word groups per (core, link): 1 unless wide
     unsigned *errors;                  // [n]
 };
 

@@ -241,9 +241,90 @@ def test_rejects_unsupported_and_missing_trace():
 
     tables = helpers.golden_tables()
     with pytest.raises(_native.NativeError):
-        OpticalVecEnv("RMSA-v0", 4, tables, num_spectrum_resources=320)        # > 128 slots: next-row config
+        OpticalVecEnv("RMSA-v0", 4, tables, num_spectrum_resources=1000)       # > 512 slots per link
     env = OpticalVecEnv("RMSA-v0", 4, tables, traffic="trace")
     with pytest.raises(_native.NativeError):
         env.reset(full=True)                                                    # no trace set
     with pytest.raises(TypeError):
         OpticalVecEnv("RWA-v0", 4, tables, j=3)
+
+
+# ------------------------------------------------------------------ beyond the NSFNET class (BASELINE configs[3], [4])
+_WIDE_TABLES = {}
+
+
+def wide_tables(name):
+    """Seeded synthetic 2-edge-connected graphs (ring + chords), k-shortest paths by NetworkX (host, once)."""
+    from optical_rl_gym_b200.topology import synthetic_ring_chords
+
+    if name not in _WIDE_TABLES:
+        if name == "ring30":
+            _WIDE_TABLES[name] = synthetic_ring_chords(num_nodes=30, num_chords=45, k_paths=10, seed=7)     # 75 links
+        else:
+            _WIDE_TABLES[name] = synthetic_ring_chords(num_nodes=20, num_chords=22, k_paths=6, seed=11)    # 42 links
+    return _WIDE_TABLES[name]
+
+
+WIDE_CASES = [
+    # configs[3] shape: RMSA-v0 on a synthetic >32-link graph, 320 slots, k = 10, SAP-FF actions
+    ("RMSA-v0", "ring30", dict(episode_length=60, load=900, mean_service_holding_time=25, num_spectrum_resources=320,
+                               allow_rejection=True), "sap_ff", 48, 300),
+    ("RMSA-v0", "ring30", dict(episode_length=60, load=600, mean_service_holding_time=25, num_spectrum_resources=320,
+                               allow_rejection=True), "random", 32, 200),
+    ("RMSA-v0", "ring20", dict(episode_length=40, load=300, mean_service_holding_time=25, num_spectrum_resources=200,
+                               allow_rejection=True), "llp_ff", 32, 300),
+    # configs[4] shape: RMCSA-v0 on NSFNET, 7 cores x 320 slots, first-core first-fit heuristic
+    ("RMCSA-v0", "nsfnet", dict(episode_length=80, load=3000, mean_service_holding_time=25, num_spectrum_resources=320,
+                                num_spatial_resources=7, worst_xt=-84.7, allow_rejection=True), "heuristic", 32, 400),
+    ("RMCSA-v0", "nsfnet", dict(episode_length=80, load=800, mean_service_holding_time=25, num_spectrum_resources=320,
+                                num_spatial_resources=3, worst_xt=-84.7, allow_rejection=True), "random", 32, 200),
+    ("DeepRMSA-v0", "ring20", dict(episode_length=45, j=2, num_spectrum_resources=160, mean_service_holding_time=25.0,
+                                   mean_service_inter_arrival_time=0.05), "sap", 32, 300),
+    ("DeepRMSA-v0", "ring30", dict(episode_length=45, j=1, num_spectrum_resources=320, mean_service_holding_time=25.0,
+                                   mean_service_inter_arrival_time=0.04, allow_rejection=True), "random", 32, 250),
+    ("RWA-v0", "ring20", dict(episode_length=64, load=400, mean_service_holding_time=25, num_spectrum_resources=160), "sap_lf", 32, 300),
+]
+
+
+@pytest.mark.parametrize("kind,topo,env_args,policy,n_envs,T", WIDE_CASES)
+def test_wide_layout_matches_oracle(kind, topo, env_args, policy, n_envs, T):
+    from optical_rl_gym_b200 import OpticalVecEnv
+    from oracle import oracle
+
+    tables = helpers.golden_tables() if topo == "nsfnet" else wide_tables(topo)
+    seed, base = 21, 500
+    env = OpticalVecEnv(kind, n_envs, tables, traffic="philox", record_decisions=True, obs_dtype=torch.float64,
+                        env_id_base=base, seed=seed, **env_args)
+    okw = helpers.sim_kwargs(dict(kind=kind, env_args=env_args))
+    oracles = []
+    for i in range(n_envs):
+        o = oracle.OracleEnv(kind, tables, **okw)
+        o.set_philox(seed, base + i)
+        o.reset(full=True)
+        oracles.append(o)
+    pol = {"random": 1}.get(policy)
+    hid = helpers.HEURISTIC_ID.get(policy)
+    ref = [o.rollout(T, policy=pol if pol is not None else 10 + hid, want_obs=(kind == "DeepRMSA-v0")) for o in oracles]
+    n_acc = 0
+    for t in range(T):
+        a = env.sample_actions() if pol is not None else env.heuristic(hid)
+        assert np.array_equal(a.cpu().numpy(), np.stack([r["actions"][t] for r in ref])), ("actions", t)
+        obs, reward, done, info = env.step(a)
+        d = env.decisions.cpu().numpy()
+        assert np.array_equal(d[:, :4], np.stack([r["decisions"][t] for r in ref])), ("decision", t)
+        assert np.array_equal(done.cpu().numpy(), np.array([r["dones"][t] for r in ref])), ("done", t)
+        if kind == "DeepRMSA-v0":
+            assert np.array_equal(obs.cpu().numpy(), np.stack([r["obs"][t] for r in ref])), ("obs", t)
+        n_acc += int(d[:, 0].sum())
+    assert n_acc > 0.05 * n_envs * T, "case exercises too few accepts (%d)" % n_acc
+    m, alloc, now, nheap = env.export_state(allocation=True)
+    avail = env.available_slots().cpu().numpy()
+    cnt = env.counters().cpu().numpy()
+    for i, o in enumerate(oracles):
+        oa, oal, onow, onh = o.state()
+        assert np.array_equal(avail[i].reshape(oa.shape), oa), ("avail", i)
+        assert np.array_equal(alloc[i].cpu().numpy(), oal), ("alloc", i)
+        assert now[i].item() == onow and nheap[i].item() == onh
+        assert np.array_equal(cnt[i], o.counters())
+    assert int(env.error_flags().abs().sum()) == 0
+    env.close()
