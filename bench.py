@@ -95,8 +95,9 @@ class ClockSampler:
 
 
 def oracle_kwargs():
+    # stats=False: like the GPU arm, the CPU arm computes obs / reward / done / counters, not the float statistics of info
     return dict(num_slots=100, episode_length=ENV_ARGS["episode_length"], j=1, mean_holding=25.0,
-                mean_iat=1 / float((25.0 / 0.1) / 25.0))
+                mean_iat=1 / float((25.0 / 0.1) / 25.0), stats=False)
 
 
 def cpu_baseline(threads, seconds=12.0):

@@ -37,7 +37,8 @@ enum {
     ORLG_ERR_TRACE_EXHAUSTED = 1,  /* the recorded trace has no request left */
     ORLG_ERR_HEAP_OVERFLOW = 2,    /* more live services than heap_capacity: the request was blocked */
     ORLG_ERR_NO_SUCH_PATH = 4,     /* action chose path >= number of candidate paths (reference: IndexError) */
-    ORLG_ERR_LOCKSTEP = 8          /* internal: an env's request counter left the handle's lockstep count */
+    ORLG_ERR_LOCKSTEP = 8,         /* internal: an env's request counter left the handle's lockstep count */
+    ORLG_ERR_STATS_ORDER = 16      /* > 24 services released in one step: float statistics updated out of time order */
 };
 
 typedef struct orlg_env orlg_env;     /* opaque handle: owns all per-environment state in HBM */
@@ -84,6 +85,7 @@ typedef struct orlg_tables {
     const double *node_prob;       /* [N] node_request_probabilities */
     const int32_t *bit_rates;      /* [num_bit_rates] discrete bit-rate selection (0 = continuous) */
     const double *bit_rate_prob;   /* [num_bit_rates] */
+    const int32_t *link_order;     /* [E] link indices in topology.edges() iteration order (np.mean over links); NULL = 0..E-1 */
 } orlg_tables;
 
 /* One recorded request of a trace (ORLG_TRAFFIC_TRACE): what _next_service draws,
@@ -133,6 +135,15 @@ int orlg_reset(orlg_env *env, int full, void *obs_dev, orlg_stream stream);
  *                 provisioned, episode requested, episode provisioned (NULL: skip)            */
 int orlg_step(orlg_env *env, const int32_t *actions_dev, void *obs_dev, float *reward_dev, uint8_t *done_dev,
               int32_t *decision_dev, int64_t *info_dev, orlg_stream stream);
+
+/* Float statistics of `info` (rmsa_env.py:229-264, 439-543, 699-744; RMSA-v0 / DeepRMSA-v0, <= 32 links,
+ * <= 128 slots): after this call every orlg_step also writes, per env, float64
+ *   stats_dev[env][0..3] = network_compactness, network_compactness_difference,
+ *                          avg_link_compactness, avg_link_utilization
+ * bit-identical to the reference (same float64 operation order, releases applied in time order, numpy's
+ * pairwise mean).  Call before orlg_reset(full = 1).  stats_dev = NULL disables it again.  The statistics
+ * path uses the generic kernel (slower than the default path). */
+int orlg_enable_stats(orlg_env *env, double *stats_dev);
 
 /* env.observation() of the pending request (deeprmsa_env.py:60-121) */
 int orlg_observation(orlg_env *env, void *obs_dev, orlg_stream stream);

@@ -144,7 +144,7 @@ int launch_step(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s)
         CUDA_OK(cudaGetLastError());
         return ORLG_OK;
     }
-    if (env->fast) {
+    if (env->fast && !env->p.stats) {
         if (env->p.J == 1) { if (env->p.obs_f64) launch_fast<1, true>(env, io, mode, s); else launch_fast<1, false>(env, io, mode, s); }
         else { if (env->p.obs_f64) launch_fast<0, true>(env, io, mode, s); else launch_fast<0, false>(env, io, mode, s); }
         CUDA_OK(cudaGetLastError());
@@ -267,6 +267,8 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     std::vector<double> plen(t->path_length, t->path_length + P);
     std::vector<unsigned> node_thr = thresholds(t->node_prob, p.N);
     std::vector<unsigned> br_thr = t->num_bit_rates > 0 ? thresholds(t->bit_rate_prob, t->num_bit_rates) : std::vector<unsigned>(1, 0u);
+    std::vector<int> link_order(p.E);
+    for (int l = 0; l < p.E; l++) link_order[l] = t->link_order ? t->link_order[l] : l;
     std::vector<int> bit_rates(t->num_bit_rates > 0 ? t->num_bit_rates : 1, 0);
     for (int i = 0; i < t->num_bit_rates; i++) bit_rates[i] = t->bit_rates[i];
 
@@ -288,6 +290,7 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     if (!rc) rc = dev_upload(env, &p.node_thr, node_thr);
     if (!rc) rc = dev_upload(env, &p.br_thr, br_thr);
     if (!rc) rc = dev_upload(env, &p.bit_rates, bit_rates);
+    if (!rc) rc = dev_upload(env, &p.link_order, link_order);
     // ---- state
     const size_t n = (size_t)p.n;
     if (!rc) rc = dev_alloc(env, &p.masks, (size_t)C * p.E * p.nwv * n);
@@ -548,6 +551,25 @@ int orlg_debug_warp_timeline(unsigned long long *out, int n_warps) {
     (void)out; (void)n_warps;
     return fail(ORLG_E_UNSUPPORTED, "built without -DORLG_PHASE_TIMING");
 #endif
+}
+
+int orlg_enable_stats(orlg_env *env, double *stats_dev) {
+    if (!env) return fail(ORLG_E_INVALID, "null handle");
+    Params &p = env->p;
+    if (!stats_dev) { p.stats = 0; p.stats_out = nullptr; return ORLG_OK; }
+    if (p.kind != ORLG_RMSA && p.kind != ORLG_DEEPRMSA) return fail(ORLG_E_UNSUPPORTED, "info has float statistics for RMSA-v0 / DeepRMSA-v0 only");
+    if (env->wide || p.E > 128) return fail(ORLG_E_UNSUPPORTED, "statistics path handles <= 32 links and <= 128 slots");
+    if (!p.link_util) {
+        const size_t n = (size_t)p.n;
+        int rc = dev_alloc(env, &p.link_util, (size_t)p.E * n);
+        if (!rc) rc = dev_alloc(env, &p.link_comp, (size_t)p.E * n);
+        if (!rc) rc = dev_alloc(env, &p.link_last, (size_t)p.E * n);
+        if (!rc) rc = dev_alloc(env, &p.sum_nh, n);
+        if (rc) return rc;
+    }
+    p.stats = 1;
+    p.stats_out = stats_dev;
+    return ORLG_OK;
 }
 
 int orlg_reduce_counters(orlg_env *env, int64_t *sums_dev, orlg_stream stream) {

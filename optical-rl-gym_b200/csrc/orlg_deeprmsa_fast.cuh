@@ -309,7 +309,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             dirty |= a_lm;
         }
         if (mode == MODE_STEP || mode == MODE_FULL_RESET) {
-            events_release(ev, nheap, hmin, tailmin, now, [&](unsigned long long pl) {     // rmsa_env.py:591-597
+            events_release(ev, nheap, hmin, tailmin, now, apply_payload([&](unsigned long long pl) {     // rmsa_env.py:591-597
                 const unsigned lm = s_path_lm[svc_row(pl)];
                 const int rs = svc_start(pl);
                 const Bits rm = bits_range(rs, rs + svc_slots(pl));
@@ -322,7 +322,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
                     sm[l * 32] = v;
                 }
                 dirty |= lm;
-            });
+            }));
             done = (cnt[2] == (long long)p.episode_length);
         }
         if (mode == MODE_EPISODE_RESET || (mode == MODE_STEP && done && p.auto_reset)) {

@@ -240,6 +240,25 @@ __device__ __forceinline__ void events_push(const Events &ev, unsigned &n, doubl
 // therefore only sit in groups whose bound is <= now; those are scanned from the highest group down, so the
 // tail entry that fills a hole is never itself due.  All bounds are lower bounds (floats rounded down), which
 // is all the gate needs; the comparisons that decide a release use the exact float64 times.
+// adapter: a plain lambda taking the payload (release order irrelevant: masks only)
+template <typename F>
+struct ApplyPayload {
+    static constexpr bool wants_time = false;
+    F f;
+    __device__ __forceinline__ void operator()(unsigned long long pl, double) const { f(pl); }
+};
+template <typename F>
+__device__ __forceinline__ ApplyPayload<F> apply_payload(F f) { return ApplyPayload<F>{f}; }
+// adapter: payload + exact release time (row f1 needs the reference's release order = by time)
+template <typename F>
+struct ApplyTimed {
+    static constexpr bool wants_time = true;
+    F f;
+    __device__ __forceinline__ void operator()(unsigned long long pl, double t) const { f(pl, t); }
+};
+template <typename F>
+__device__ __forceinline__ ApplyTimed<F> apply_timed(F f) { return ApplyTimed<F>{f}; }
+
 template <typename Apply>
 __device__ __forceinline__ void events_release(const Events &ev, unsigned &n, double &tmin, double &tail_min,
                                                const double now, Apply apply) {
@@ -302,6 +321,7 @@ __device__ __forceinline__ void events_release(const Events &ev, unsigned &n, do
             const unsigned s = s0 + q;
             const unsigned last = n - 1;
             const unsigned long long pl = ev.p[s];
+            const double pt = Apply::wants_time ? ev.t[s] : 0.0;
             if (s != last) {                   // fill the hole with the tail entry (never due, see above)
                 const double lt = ev.t[last];
                 const unsigned long long lp = ev.p[last];
@@ -311,7 +331,7 @@ __device__ __forceinline__ void events_release(const Events &ev, unsigned &n, do
             }
             ev.t[last] = ORLG_INF;             // keep "t[s] = +INF for s >= n"
             n--;
-            apply(pl);
+            apply(pl, pt);
         }
         SUBPHASE_MARK(15);                     // payload fetch, hole fill, apply
         if (s0 < n) {                          // publish the bound of what is left of this group

@@ -66,6 +66,12 @@ struct Params {
     unsigned short *cand16;            // same for the wide layout (S > 128)
     int nwv;                           // 128-bit word groups per (core, link): 1 unless wide
     unsigned *errors;                  // [n]
+    // ---- float statistics of `info` (row f1: rmsa_env.py:439-543, 699-744); allocated by orlg_enable_stats
+    int stats;
+    double *link_util, *link_comp, *link_last;   // [E][n] time-averaged utilisation / compactness, last update time
+    long long *sum_nh;                 // [n] sum over running services of number_slots * hops
+    double *stats_out;                 // [n][4] network_compactness, its difference, avg link compactness, avg link utilisation
+    const int *link_order;             // [E] link indices in topology.edges() order (np.mean over the links)
 };
 
 struct StepIO {
@@ -137,6 +143,91 @@ __device__ __forceinline__ void philox_request(const Params &p, const unsigned *
         philox4x32_10(d, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
         if (p.n_bit_rates > 0) br = p.bit_rates[pick_thr(p.br_thr, p.n_bit_rates, d[0])];
         else br = p.br_lo + (int)__umulhi(d[0], (unsigned)p.br_span);
+    }
+}
+
+// ---------------------------------------------------------------- row f1: float statistics (generic kernel only)
+// Per link, from the packed mask (identities checked against the reference):
+// used = ~free; used blocks = popc(used & ~(used << 1)); lambda_min = ffs(used), lambda_max = fls(used) + 1;
+// free runs inside [lambda_min, lambda_max) = popc(F & ~(F << 1)) with F = free restricted to the window.
+struct LinkShape {
+    int free_cnt, used_runs, span, free_runs_in;
+};
+__device__ __forceinline__ LinkShape link_shape(const Bits &fr, int S) {
+    LinkShape r;
+    const Bits valid = bits_range(0, S);
+    const Bits used = bits_andnot(valid, fr);
+    r.free_cnt = bits_popc(fr);
+    r.used_runs = bits_popc(bits_andnot(used, bits_shl1(used)));
+    r.span = 0; r.free_runs_in = 0;
+    if (r.used_runs > 1) {
+        const int lo = bits_ffs(used), hi = bits_fls(used) + 1;
+        r.span = hi - lo;
+        const Bits F = bits_and(fr, bits_range(lo, hi));
+        r.free_runs_in = bits_popc(bits_andnot(F, bits_shl1(F)));
+    }
+    return r;
+}
+
+// _get_network_compactness (rmsa_env.py:699-744)
+__device__ __forceinline__ double network_compactness(const Params &p, int env, long long sum_nh) {
+    long long occupied = 0, unused = 0;
+    for (int l = 0; l < p.E; l++) {
+        const LinkShape s = link_shape(bits_from(p.masks[(size_t)l * p.n + env]), p.S);
+        occupied += s.span; unused += s.free_runs_in;
+    }
+    if (unused > 0) return __dmul_rn(__ddiv_rn((double)occupied, (double)sum_nh), __ddiv_rn((double)p.E, (double)unused));
+    return 1.0;
+}
+
+// _update_link_stats (rmsa_env.py:464-543) for link l whose (already updated) mask is `fr`
+__device__ __forceinline__ void update_link_stats(const Params &p, int env, int l, const Bits &fr, double now) {
+    const size_t i = (size_t)l * p.n + env;
+    const double last_update = p.link_last[i];
+    const double time_diff = __dadd_rn(now, -last_update);
+    if (now > 0) {
+        const LinkShape s = link_shape(fr, p.S);
+        const double cur_util = __ddiv_rn((double)(p.S - s.free_cnt), (double)p.S);
+        p.link_util[i] = __ddiv_rn(__dadd_rn(__dmul_rn(p.link_util[i], last_update), __dmul_rn(cur_util, time_diff)), now);
+        double cur_comp = 0.0;
+        if (s.free_cnt > 0)
+            cur_comp = s.used_runs > 1 ? __dmul_rn(__ddiv_rn((double)s.span, (double)(p.S - s.free_cnt)), __ddiv_rn(1.0, (double)s.used_runs)) : 1.0;
+        p.link_comp[i] = __ddiv_rn(__dadd_rn(__dmul_rn(p.link_comp[i], last_update), __dmul_rn(cur_comp, time_diff)), now);
+    }
+    p.link_last[i] = now;
+}
+
+// np.mean over the links in topology.edges() order: numpy's pairwise summation (8 partial sums), E <= 128
+__device__ __forceinline__ double mean_over_links(const Params &p, const double *per_link, int env) {
+    const int n = p.E;
+    double res;
+    if (n < 8) {
+        res = 0.0;
+        for (int i = 0; i < n; i++) res = __dadd_rn(res, per_link[(size_t)p.link_order[i] * p.n + env]);
+    } else {
+        double r[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] = per_link[(size_t)p.link_order[j] * p.n + env];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], per_link[(size_t)p.link_order[i + j] * p.n + env]);
+        }
+        res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < n; i++) res = __dadd_rn(res, per_link[(size_t)p.link_order[i] * p.n + env]);
+    }
+    return __ddiv_rn(res, (double)n);
+}
+
+// _provision_path / _release_path with the per-link statistics, links in hop order (rmsa_env.py:381-396, 418-436)
+__device__ __forceinline__ void path_update_stats(const Params &p, int env, int row, const Bits &rm, bool set, double now) {
+    for (int h = p.path_link_ptr[row]; h < p.path_link_ptr[row + 1]; h++) {
+        const int l = p.path_links16[h];
+        uint4 *m = p.masks + (size_t)l * p.n + env;
+        Bits b = bits_from(*m);
+        b = set ? bits_or(b, rm) : bits_andnot(b, rm);
+        *m = bits_to(b);
+        update_link_stats(p, env, l, b, now);
     }
 }
 
@@ -257,8 +348,15 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
             accepted = false;
             err |= ORLG_ERR_HEAP_OVERFLOW;
         }
+        const bool do_stats = p.stats && (KIND == ORLG_RMSA || KIND == ORLG_DEEPRMSA);
+        long long snh = do_stats ? p.sum_nh[env] : 0;
+        const double prev_compactness = do_stats ? network_compactness(p, env, snh) : 0.0;     // rmsa_env.py:168-170
         if (accepted) {
             if (live) {
+                if (do_stats) {
+                    path_update_stats(p, env, row, bits_range(start, start + n), false, now);
+                    snh += (long long)n * meta_hops(p.path_meta[row]);
+                } else
                 path_update(p, env, lm, core, bits_range(start, start + n), false);
                 double rel = __dadd_rn(now, hold);          // arrival_time + holding_time (now == arrival)
                 events_push(ev, nheap, hmin, tailmin, rel, pack_service(row, start, n, core, sid));
@@ -283,7 +381,21 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
 #pragma unroll
                 for (int q = 0; q < 8; q++) io.info[(size_t)env * 8 + q] = cnt[q];
             }
+            if (do_stats) {                                     // rmsa_env.py:229-264
+                p.sum_nh[env] = snh;
+                const double cur = network_compactness(p, env, snh);
+                double *so = p.stats_out + (size_t)env * 4;
+                so[0] = cur;
+                so[1] = __dadd_rn(prev_compactness, -cur);
+                so[2] = mean_over_links(p, p.link_comp, env);
+                so[3] = mean_over_links(p, p.link_util, env);
+            }
         }
+    }
+
+    if (mode == MODE_FULL_RESET && p.stats && (KIND == ORLG_RMSA || KIND == ORLG_DEEPRMSA)) {
+        for (int l = 0; l < p.E; l++) { p.link_util[(size_t)l * p.n + env] = 0.0; p.link_comp[(size_t)l * p.n + env] = 0.0; p.link_last[(size_t)l * p.n + env] = 0.0; }
+        p.sum_nh[env] = 0;
     }
 
     if (mode == MODE_STEP || mode == MODE_FULL_RESET) {
@@ -311,10 +423,42 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
             cnt[4] += br; cnt[6] += br;                       // rmcsa_env.py:730-731
         }
         // release every service whose time has come (rmsa_env.py:591-597)
-        events_release(ev, nheap, hmin, tailmin, now, [&](unsigned long long pl) {
+        if (p.stats && (KIND == ORLG_RMSA || KIND == ORLG_DEEPRMSA)) {
+            // the reference releases in heap order (by time) and every release updates the float statistics of
+            // its links, so the due services are collected, sorted by release time and applied in that order
+            constexpr int MAXR = 24;
+            double rt[MAXR];
+            unsigned long long rp[MAXR];
+            int nr = 0;
+            events_release(ev, nheap, hmin, tailmin, now, apply_timed([&](unsigned long long pl, double t) {
+                if (nr < MAXR) { rt[nr] = t; rp[nr] = pl; nr++; }
+                else {                                           // overflow: masks stay exact, statistics order is not
+                    err |= ORLG_ERR_STATS_ORDER;
+                    const int rs = svc_start(pl);
+                    path_update_stats(p, env, svc_row(pl), bits_range(rs, rs + svc_slots(pl)), true, now);
+                    p.sum_nh[env] -= (long long)svc_slots(pl) * meta_hops(p.path_meta[svc_row(pl)]);
+                }
+            }));
+            for (int a = 1; a < nr; a++) {                       // insertion sort by release time
+                const double t = rt[a];
+                const unsigned long long q = rp[a];
+                int b = a - 1;
+                while (b >= 0 && rt[b] > t) { rt[b + 1] = rt[b]; rp[b + 1] = rp[b]; b--; }
+                rt[b + 1] = t; rp[b + 1] = q;
+            }
+            long long snh = p.sum_nh[env];
+            for (int a = 0; a < nr; a++) {
+                const unsigned long long pl = rp[a];
+                const int rs = svc_start(pl);
+                path_update_stats(p, env, svc_row(pl), bits_range(rs, rs + svc_slots(pl)), true, now);
+                snh -= (long long)svc_slots(pl) * meta_hops(p.path_meta[svc_row(pl)]);
+            }
+            p.sum_nh[env] = snh;
+        } else
+        events_release(ev, nheap, hmin, tailmin, now, apply_payload([&](unsigned long long pl) {
             const int rs = svc_start(pl);
             path_update(p, env, p.path_linkmask[svc_row(pl)], svc_core(pl), bits_range(rs, rs + svc_slots(pl)), true);
-        });
+        }));
         done = (cnt[2] == (long long)p.episode_length);
     }
 

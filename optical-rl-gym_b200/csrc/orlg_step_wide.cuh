@@ -260,9 +260,9 @@ __global__ void __launch_bounds__(128) step_wide_kernel(const Params p, const St
         sid = (int)cnt[2];
         if (KIND == ORLG_RMSA || KIND == ORLG_DEEPRMSA) { cnt[0] += 1; cnt[2] += 1; cnt[4] += br; cnt[6] += br; }
         else if (KIND == ORLG_RMCSA) { cnt[4] += br; cnt[6] += br; }
-        events_release(ev, nheap, hmin, tailmin, now, [&](unsigned long long pl) {
+        events_release(ev, nheap, hmin, tailmin, now, apply_payload([&](unsigned long long pl) {
             wide_path_update<NWV>(p, env, svc_row(pl), svc_core(pl), svc_start(pl), svc_slots(pl), true);
-        });
+        }));
         done = (cnt[2] == (long long)p.episode_length);
     }
 

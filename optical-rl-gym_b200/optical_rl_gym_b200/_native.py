@@ -15,7 +15,7 @@ HEURISTICS = {"shortest_path_first_fit": 0, "sp_ff": 0, "sp": 0,
               "shortest_available_path_best_modulation_first_core_first_fit": 1,
               "least_loaded_path_first_fit": 2, "llp_ff": 2,
               "shortest_available_path_last_fit": 3, "sap_lf": 3}
-ERR_TRACE_EXHAUSTED, ERR_HEAP_OVERFLOW, ERR_NO_SUCH_PATH, ERR_LOCKSTEP = 1, 2, 4, 8
+ERR_TRACE_EXHAUSTED, ERR_HEAP_OVERFLOW, ERR_NO_SUCH_PATH, ERR_LOCKSTEP, ERR_STATS_ORDER = 1, 2, 4, 8, 16
 MAX_BIT_RATE = 1023       # bit rates (Gb/s) are tabulated up to here (orlg_api.cu)
 
 
@@ -33,7 +33,7 @@ class Tables(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("num_nodes", "num_links", "k_paths", "num_paths", "num_mods", "num_bit_rates")] + [
         (n, C.c_void_p) for n in ("pair_first", "pair_count", "path_hops", "path_se", "path_mod", "path_link_ptr",
                                   "path_links", "path_length", "mod_se", "mod_osnr", "mod_xt", "node_prob",
-                                  "bit_rates", "bit_rate_prob")]
+                                  "bit_rates", "bit_rate_prob", "link_order")]
 
 
 REQUEST_DTYPE = np.dtype([("arrival", np.float64), ("holding", np.float64), ("src", np.int32), ("dst", np.int32),
@@ -79,6 +79,7 @@ def lib():
     L.orlg_export_state.argtypes = [vp, vp, vp, vp, vp, vp]
     L.orlg_error_flags.argtypes = [vp, vp, vp]
     L.orlg_reduce_counters.argtypes = [vp, vp, vp]
+    L.orlg_enable_stats.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -91,4 +92,4 @@ def check(rc):
 EXPORTED = ["orlg_create", "orlg_destroy", "orlg_last_error", "orlg_version", "orlg_action_dim", "orlg_obs_dim",
             "orlg_mask_words", "orlg_heap_capacity", "orlg_state_bytes", "orlg_set_trace", "orlg_reset", "orlg_step",
             "orlg_observation", "orlg_observation_int", "orlg_heuristic", "orlg_random_actions", "orlg_get_counters",
-            "orlg_get_requests", "orlg_export_state", "orlg_error_flags", "orlg_reduce_counters"]
+            "orlg_get_requests", "orlg_export_state", "orlg_error_flags", "orlg_reduce_counters", "orlg_enable_stats"]

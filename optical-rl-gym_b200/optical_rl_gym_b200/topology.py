@@ -63,6 +63,11 @@ class TopologyTables:
     mod_reach: np.ndarray       # float64 [M]
     mod_osnr: np.ndarray        # float64 [M]
     mod_xt: np.ndarray          # float64 [M]
+    link_order: Optional[np.ndarray] = None   # int32 [E] link indices in nx.Graph.edges() iteration order (np.mean over links)
+
+    def __post_init__(self):
+        if self.link_order is None:
+            self.link_order = np.arange(self.num_links, dtype=np.int32)
 
     @property
     def num_paths(self) -> int:
@@ -87,6 +92,7 @@ class TopologyTables:
     def load(cls, file) -> "TopologyTables":
         with np.load(file, allow_pickle=False) as z:
             d = {k: z[k] for k in z.files}
+        d.setdefault("link_order", None)
         d["name"] = str(d["name"])
         d["node_names"] = tuple(str(x) for x in d["node_names"])
         d["mod_names"] = tuple(str(x) for x in d["mod_names"])
@@ -144,6 +150,7 @@ class TopologyTables:
             mod_reach=np.array([m.maximum_length for m in mods], np.float64),
             mod_osnr=np.array([m.minimum_osnr if m.minimum_osnr is not None else np.nan for m in mods], np.float64),
             mod_xt=np.array([m.inband_xt if m.inband_xt is not None else np.nan for m in mods], np.float64),
+            link_order=np.array([data["index"] for _, _, data in graph.edges(data=True)], np.int32),
         )
 
     @classmethod
@@ -203,6 +210,7 @@ class TopologyTables:
             mod_reach=np.array([m[1] for m in mods], np.float64),
             mod_osnr=np.array([m[3] for m in mods], np.float64),
             mod_xt=np.array([m[4] for m in mods], np.float64),
+            link_order=np.array([data["index"] for _, _, data in graph.edges(data=True)], np.int32),
         )
 
 

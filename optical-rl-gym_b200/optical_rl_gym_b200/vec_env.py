@@ -43,6 +43,7 @@ METRICS = {   # metadata["metrics"], rmsa_env.py:20-27 / rwa_env.py:17
                 "episode_bit_rate_blocking_rate"],
     "RWA-v0": ["service_blocking_rate", "episode_service_blocking_rate"],
 }
+STAT_KEYS = ["network_compactness", "network_compactness_difference", "avg_link_compactness", "avg_link_utilization"]
 METRICS["DeepRMSA-v0"] = METRICS["RMSA-v0"]
 METRICS["RMCSA-v0"] = METRICS["RMSA-v0"]
 
@@ -58,9 +59,10 @@ class StepInfo:
     _COL = {"service_blocking_rate": (0, 1), "episode_service_blocking_rate": (2, 3),
             "bit_rate_blocking_rate": (4, 5), "episode_bit_rate_blocking_rate": (6, 7)}
 
-    def __init__(self, counters: torch.Tensor, keys):
+    def __init__(self, counters: torch.Tensor, keys, stats: Optional[torch.Tensor] = None):
         self.counters = counters       # int64 [N, 8]
-        self._keys = list(keys)
+        self.stats = stats             # float64 [N, 4] (rmsa_env.py:249-263) when link_stats=True
+        self._keys = list(keys) + (STAT_KEYS if stats is not None else [])
 
     def keys(self):
         return list(self._keys)
@@ -74,6 +76,8 @@ class StepInfo:
     def __getitem__(self, key):
         if key not in self._keys:
             raise KeyError(key)
+        if key in STAT_KEYS:
+            return self.stats[:, STAT_KEYS.index(key)]
         a, b = self._COL[key]
         c = self.counters
         return (c[:, a] - c[:, b]).to(torch.float64) / c[:, a].to(torch.float64)
@@ -101,7 +105,7 @@ class OpticalVecEnv:
 
     def __init__(self, env_id: str, num_envs: int, topology, *, device=None, env_id_base: int = 0,
                  traffic: str = "philox", obs_dtype=torch.float32, auto_reset: bool = True, collect_info: bool = True,
-                 record_decisions: bool = False, heap_capacity: int = 0, **env_args):
+                 record_decisions: bool = False, heap_capacity: int = 0, link_stats: bool = False, **env_args):
         if env_id not in nat.KIND:
             raise ValueError("unknown env id %r (have %s)" % (env_id, sorted(nat.KIND)))
         if not torch.cuda.is_available():
@@ -184,7 +188,8 @@ class OpticalVecEnv:
                          mod_xt=arr("mx", t.mod_xt, np.float64),
                          node_prob=arr("np", self.node_request_probabilities, np.float64),
                          bit_rates=arr("br", self.bit_rates if len(self.bit_rates) else [0], np.int32),
-                         bit_rate_prob=arr("bp", self.bit_rate_probabilities if len(self.bit_rates) else [1.0], np.float64))
+                         bit_rate_prob=arr("bp", self.bit_rate_probabilities if len(self.bit_rates) else [1.0], np.float64),
+                         link_order=arr("lo", t.link_order, np.int32))
         self._lib = nat.lib()
         self._h = C.c_void_p()
         self._closed = False
@@ -218,6 +223,11 @@ class OpticalVecEnv:
         self._decision = torch.zeros((n, 6), dtype=torch.int32, device=dev) if record_decisions else None
         self._actions = None
         self._trace = None
+        # float statistics of info (network / link compactness, utilisation): opt-in, uses the generic kernel
+        self._stats = None
+        if link_stats:
+            self._stats = torch.zeros((n, 4), dtype=torch.float64, device=dev)
+            nat.check(self._lib.orlg_enable_stats(self._h, _ptr(self._stats)))
         if traffic == "philox" and a.get("reset", True):
             self.reset(full=True)
 
@@ -285,7 +295,7 @@ class OpticalVecEnv:
     def step_wait(self):
         nat.check(self._lib.orlg_step(self._h, _ptr(self._actions), _ptr(self._obs), _ptr(self._reward), _ptr(self._done),
                                       _ptr(self._decision), _ptr(self._info), self._stream()))
-        info = StepInfo(self._info, self.metadata["metrics"]) if self._info is not None else None
+        info = StepInfo(self._info, self.metadata["metrics"], self._stats) if self._info is not None else None
         return self._obs, self._reward, self._done, info
 
     def step(self, actions):

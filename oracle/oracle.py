@@ -26,20 +26,20 @@ def build(force=False):
 class Cfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "kind", "num_nodes", "num_links", "k_paths", "num_paths", "num_slots", "num_cores", "num_mods", "j",
-        "episode_length", "allow_rejection", "bit_rate_lo", "bit_rate_hi", "num_bit_rates")] + [
+        "episode_length", "allow_rejection", "bit_rate_lo", "bit_rate_hi", "num_bit_rates", "stats")] + [
         (n, C.c_double) for n in ("channel_width", "mean_holding", "mean_iat", "worst_xt")]
 
 
 class Tab(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "pair_first", "pair_count", "path_hops", "path_se", "path_mod", "path_link_ptr", "path_links",
-        "path_length", "mod_se", "mod_osnr", "mod_xt", "node_prob", "bit_rates", "bit_rate_prob")]
+        "path_length", "mod_se", "mod_osnr", "mod_xt", "node_prob", "bit_rates", "bit_rate_prob", "link_order")]
 
 
 class StepOut(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "accepted", "path_row", "initial_slot", "number_slots", "core", "mod", "service_id", "done")] + [
-        ("reward", C.c_double), ("info_counters", C.c_int64 * 8)]
+        ("reward", C.c_double), ("info_counters", C.c_int64 * 8), ("stats", C.c_double * 4)]
 
 
 _lib = None
@@ -90,7 +90,7 @@ def _ptr(a):
 
 def make_cfg_tab(env_id, tables, *, num_slots, episode_length=1000, j=1, num_cores=1, allow_rejection=False,
                  mean_holding=25.0, mean_iat=0.1, channel_width=12.5, bit_rate_lo=25, bit_rate_hi=100,
-                 bit_rates=None, bit_rate_prob=None, node_prob=None, worst_xt=-84.7):
+                 bit_rates=None, bit_rate_prob=None, node_prob=None, worst_xt=-84.7, stats=True):
     """Returns (Cfg, Tab, keepalive list of numpy arrays)."""
     t = tables
     keep = {}
@@ -107,7 +107,7 @@ def make_cfg_tab(env_id, tables, *, num_slots, episode_length=1000, j=1, num_cor
     cfg = Cfg(kind=KINDS[env_id], num_nodes=t.num_nodes, num_links=t.num_links, k_paths=t.k_paths,
               num_paths=t.num_paths, num_slots=num_slots, num_cores=num_cores, num_mods=len(t.mod_se), j=j,
               episode_length=episode_length, allow_rejection=int(allow_rejection), bit_rate_lo=int(bit_rate_lo),
-              bit_rate_hi=int(bit_rate_hi), num_bit_rates=nbr, channel_width=channel_width,
+              bit_rate_hi=int(bit_rate_hi), num_bit_rates=nbr, stats=int(stats), channel_width=channel_width,
               mean_holding=mean_holding, mean_iat=mean_iat, worst_xt=worst_xt)
     tab = Tab(pair_first=arr("pf", t.pair_first, np.int32), pair_count=arr("pc", t.pair_count, np.int32),
               path_hops=arr("ph", t.path_hops, np.int32), path_se=arr("ps", t.path_se, np.int32),
@@ -116,7 +116,8 @@ def make_cfg_tab(env_id, tables, *, num_slots, episode_length=1000, j=1, num_cor
               mod_se=arr("ms", t.mod_se, np.int32), mod_osnr=arr("mo", t.mod_osnr, np.float64),
               mod_xt=arr("mx", t.mod_xt, np.float64), node_prob=arr("np", node_prob, np.float64),
               bit_rates=arr("br", bit_rates if nbr else [0], np.int32),
-              bit_rate_prob=arr("bp", bit_rate_prob if nbr else [1.0], np.float64))
+              bit_rate_prob=arr("bp", bit_rate_prob if nbr else [1.0], np.float64),
+              link_order=arr("lo", t.link_order, np.int32))
     return cfg, tab, keep
 
 

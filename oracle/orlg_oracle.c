@@ -40,6 +40,7 @@ typedef struct {
     int32_t allow_rejection;
     int32_t bit_rate_lo, bit_rate_hi;   /* continuous mode randint bounds */
     int32_t num_bit_rates;              /* >0: discrete mode (Philox traffic only) */
+    int32_t stats;                      /* 1: maintain the float statistics of info (row f1) */
     double channel_width;
     double mean_holding, mean_iat;
     double worst_xt;                    /* RMCSA, before the +4 dB margin */
@@ -54,6 +55,7 @@ typedef struct {
     const double *node_prob;                  /* [N] node_request_probabilities */
     const int32_t *bit_rates;                 /* [num_bit_rates] */
     const double *bit_rate_prob;
+    const int32_t *link_order;                /* [E] link indices in topology.edges() iteration order */
 } otab_t;
 
 typedef struct {
@@ -85,6 +87,9 @@ typedef struct {
     uint32_t src_thr[256];      /* integer CDF thresholds for Philox src/dst draws */
     uint32_t br_thr[64];
     int error;
+    /* float statistics of row f1 (rmsa_env.py:439-543, 699-744) */
+    double *link_util, *link_comp, *link_last;   /* [E] time-averaged utilisation / compactness, last update time */
+    long sum_nh;                                  /* sum over running services of number_slots * hops */
 } oenv_t;
 
 /* ------------------------------------------------------------------ tables */
@@ -260,12 +265,102 @@ static int is_path_free(const oenv_t *e, int row, int core, int initial_slot, in
     return 1;
 }
 
-/* rmsa_env.py:364-415 (masks + allocation ids only; link lists / float stats are row f1) */
+static int rle(const int8_t *a, int n, int *starts, int *values, int *lengths);
+
+/* rmsa_env.py:651-665 on one link row */
+static int rle_link(const oenv_t *e, int l, int lo, int hi, int *starts, int *values, int *lengths) {
+    int8_t row[1024];
+    for (int s = lo; s < hi; s++) row[s - lo] = AV(e, 0, l, s);
+    return rle(row, hi - lo, starts, values, lengths);
+}
+
+/* rmsa_env.py:464-543 (_update_link_stats), utilisation and compactness */
+static void update_link_stats(oenv_t *e, int l) {
+    int S = e->c.num_slots;
+    double last_update = e->link_last[l];
+    double time_diff = e->now - e->link_last[l];
+    if (e->now > 0) {
+        double last_util = e->link_util[l];
+        long free_sum = 0;
+        for (int s = 0; s < S; s++) free_sum += AV(e, 0, l, s);
+        double cur_util = (double)(S - free_sum) / (double)S;
+        e->link_util[l] = ((last_util * last_update) + (cur_util * time_diff)) / e->now;
+        double last_compactness = e->link_comp[l];
+        double cur_link_compactness = 0.0;
+        if (free_sum > 0) {
+            int st[1024], va[1024], le[1024];
+            int nr = rle_link(e, l, 0, S, st, va, le);
+            int n_used = 0, first = -1, last = -1;
+            for (int r = 0; r < nr; r++) if (va[r] == 0) { if (first < 0) first = r; last = r; n_used++; }
+            if (n_used > 1) {
+                int lambda_min = st[first], lambda_max = st[last] + le[last];
+                int st2[1024], va2[1024], le2[1024];
+                int nr2 = rle_link(e, l, lambda_min, lambda_max, st2, va2, le2);
+                long unused_spectrum_slots = 0;                 /* np.sum(1 - internal_values) */
+                for (int r = 0; r < nr2; r++) unused_spectrum_slots += 1 - va2[r];
+                if (unused_spectrum_slots > 0)
+                    cur_link_compactness = ((double)(lambda_max - lambda_min) / (double)(S - free_sum)) *
+                                           (1 / (double)unused_spectrum_slots);
+                else cur_link_compactness = 1.0;
+            } else cur_link_compactness = 1.0;
+        }
+        e->link_comp[l] = ((last_compactness * last_update) + (cur_link_compactness * time_diff)) / e->now;
+    }
+    e->link_last[l] = e->now;
+}
+
+/* rmsa_env.py:699-744 (_get_network_compactness) */
+static double network_compactness(const oenv_t *e) {
+    int S = e->c.num_slots;
+    long sum_occupied = 0, sum_unused_spectrum_blocks = 0;
+    for (int l = 0; l < e->c.num_links; l++) {
+        int st[1024], va[1024], le[1024];
+        int nr = rle_link(e, l, 0, S, st, va, le);
+        int n_used = 0, first = -1, last = -1;
+        for (int r = 0; r < nr; r++) if (va[r] == 0) { if (first < 0) first = r; last = r; n_used++; }
+        if (n_used > 1) {
+            int lambda_min = st[first], lambda_max = st[last] + le[last];
+            sum_occupied += lambda_max - lambda_min;
+            int st2[1024], va2[1024], le2[1024];
+            int nr2 = rle_link(e, l, lambda_min, lambda_max, st2, va2, le2);
+            for (int r = 0; r < nr2; r++) sum_unused_spectrum_blocks += va2[r];
+        }
+    }
+    if (sum_unused_spectrum_blocks > 0)
+        return ((double)sum_occupied / (double)e->sum_nh) * ((double)e->c.num_links / (double)sum_unused_spectrum_blocks);
+    return 1.0;
+}
+
+/* np.mean of a float64 list: numpy's pairwise summation (8 partial sums for n <= 128, recursive above) / n */
+static double np_sum(const double *a, int n) {
+    if (n < 8) { double r = 0.0; for (int i = 0; i < n; i++) r += a[i]; return r; }
+    if (n <= 128) {
+        double r[8];
+        for (int j = 0; j < 8; j++) r[j] = a[j];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8) for (int j = 0; j < 8; j++) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; i++) res += a[i];
+        return res;
+    }
+    int n2 = n / 2; n2 -= n2 % 8;
+    return np_sum(a, n2) + np_sum(a + n2, n - n2);
+}
+
+static double mean_over_edges(const oenv_t *e, const double *per_link) {
+    double tmp[4096];
+    for (int i = 0; i < e->c.num_links; i++) tmp[i] = per_link[e->t.link_order[i]];
+    return np_sum(tmp, e->c.num_links) / (double)e->c.num_links;
+}
+
+/* rmsa_env.py:364-415 (masks, allocation ids, per-link float stats) */
 static void provision(oenv_t *e, int row, int core, int initial_slot, int n) {
     for (int h = e->t.path_link_ptr[row]; h < e->t.path_link_ptr[row + 1]; h++) {
         int l = e->t.path_links[h];
         for (int s = initial_slot; s < initial_slot + n; s++) { AV(e, core, l, s) = 0; AL(e, core, l, s) = e->cur.id; }
+        if (e->c.stats && (e->c.kind == KIND_RMSA || e->c.kind == KIND_DEEPRMSA)) update_link_stats(e, l);
     }
+    e->sum_nh += (long)n * (e->t.path_link_ptr[row + 1] - e->t.path_link_ptr[row]);
     e->cur.path_row = row; e->cur.initial_slot = initial_slot; e->cur.number_slots = n; e->cur.core = core;
 }
 
@@ -274,7 +369,9 @@ static void release(oenv_t *e, const service_t *s) {
     for (int h = e->t.path_link_ptr[s->path_row]; h < e->t.path_link_ptr[s->path_row + 1]; h++) {
         int l = e->t.path_links[h];
         for (int k = s->initial_slot; k < s->initial_slot + s->number_slots; k++) { AV(e, s->core, l, k) = 1; AL(e, s->core, l, k) = -1; }
+        if (e->c.stats && (e->c.kind == KIND_RMSA || e->c.kind == KIND_DEEPRMSA)) update_link_stats(e, l);
     }
+    e->sum_nh -= (long)s->number_slots * (e->t.path_link_ptr[s->path_row + 1] - e->t.path_link_ptr[s->path_row]);
 }
 
 static void release_due(oenv_t *e) {
@@ -367,6 +464,7 @@ typedef struct {
     int32_t done;
     double reward;
     int64_t info_counters[8];   /* counters when the reference builds `info` (before _next_service) */
+    double stats[4];            /* network_compactness, its difference, avg link compactness, avg link utilisation */
 } ostep_t;
 
 void *oracle_create(const ocfg_t *cfg, const otab_t *tab) {
@@ -387,6 +485,10 @@ void *oracle_create(const ocfg_t *cfg, const otab_t *tab) {
     e->t.node_prob = dup_mem(e, tab->node_prob, sizeof(double) * N);
     e->t.bit_rates = dup_mem(e, tab->bit_rates, sizeof(int32_t) * cfg->num_bit_rates);
     e->t.bit_rate_prob = dup_mem(e, tab->bit_rate_prob, sizeof(double) * cfg->num_bit_rates);
+    e->t.link_order = dup_mem(e, tab->link_order, sizeof(int32_t) * cfg->num_links);
+    e->link_util = (double *)calloc((size_t)cfg->num_links, sizeof(double));
+    e->link_comp = (double *)calloc((size_t)cfg->num_links, sizeof(double));
+    e->link_last = (double *)calloc((size_t)cfg->num_links, sizeof(double));
     size_t cells = (size_t)cfg->num_cores * cfg->num_links * cfg->num_slots;
     e->avail = (int8_t *)malloc(cells);
     e->alloc = (int32_t *)malloc(cells * sizeof(int32_t));
@@ -407,13 +509,16 @@ void *oracle_create_shared(const ocfg_t *cfg, const otab_t *tab) {
     build_thresholds(e->t.node_prob, cfg->num_nodes, e->src_thr);
     if (cfg->num_bit_rates > 0) build_thresholds(e->t.bit_rate_prob, cfg->num_bit_rates, e->br_thr);
     e->traffic = 1;
+    e->link_util = (double *)calloc((size_t)cfg->num_links, sizeof(double));
+    e->link_comp = (double *)calloc((size_t)cfg->num_links, sizeof(double));
+    e->link_last = (double *)calloc((size_t)cfg->num_links, sizeof(double));
     return e;
 }
 
 void oracle_destroy(void *p) {
     oenv_t *e = (oenv_t *)p;
     for (int i = 0; i < e->nown; i++) free(e->own[i]);
-    free(e->avail); free(e->alloc); free(e->heap); free(e);
+    free(e->avail); free(e->alloc); free(e->heap); free(e->link_util); free(e->link_comp); free(e->link_last); free(e);
 }
 
 void oracle_set_trace(void *p, const double *arr, const double *hold, const int32_t *src, const int32_t *dst,
@@ -441,6 +546,8 @@ void oracle_reset(void *p, int full) {
     e->nheap = 0; e->now = 0.0;
     e->processed = e->accepted = 0; e->br_req = e->br_prov = 0;
     e->req_index = 0;
+    e->sum_nh = 0;
+    for (int l = 0; l < e->c.num_links; l++) { e->link_util[l] = 0.0; e->link_comp[l] = 0.0; e->link_last[l] = 0.0; }
     size_t cells = (size_t)e->c.num_cores * e->c.num_links * e->c.num_slots;
     memset(e->avail, 1, cells);
     for (size_t i = 0; i < cells; i++) e->alloc[i] = -1;
@@ -466,6 +573,7 @@ static void finish_step(oenv_t *e, ostep_t *o) {
 /* rmsa_env.py:163-282 */
 static int step_rmsa(oenv_t *e, int path, int initial_slot, ostep_t *o) {
     int rc = 0;
+    double previous_network_compactness = e->c.stats ? network_compactness(e) : 0.0;      /* rmsa_env.py:168-170 */
     e->cur.accepted = 0;
     if (path < e->c.k_paths && initial_slot < e->c.num_slots && path >= 0 && initial_slot >= 0) {
         int row = pair_row(e, e->cur.src, e->cur.dst, path);
@@ -480,6 +588,14 @@ static int step_rmsa(oenv_t *e, int path, int initial_slot, ostep_t *o) {
                 heap_push(e, e->cur.arrival + e->cur.holding, &e->cur);
             }
         }
+    }
+    o->stats[0] = o->stats[1] = o->stats[2] = o->stats[3] = 0.0;
+    if (e->c.stats) {   /* rmsa_env.py:229-264 */
+        double cur = network_compactness(e);
+        o->stats[0] = cur;
+        o->stats[1] = previous_network_compactness - cur;
+        o->stats[2] = mean_over_edges(e, e->link_comp);
+        o->stats[3] = mean_over_edges(e, e->link_util);
     }
     finish_step(e, o);
     return rc;

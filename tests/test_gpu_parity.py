@@ -328,3 +328,26 @@ def test_wide_layout_matches_oracle(kind, topo, env_args, policy, n_envs, T):
         assert np.array_equal(cnt[i], o.counters())
     assert int(env.error_flags().abs().sum()) == 0
     env.close()
+
+
+# ------------------------------------------------------------------ row f1: float statistics of info
+@pytest.mark.parametrize("name", [n for n in helpers.golden_names() if n.startswith(("rmsa", "deeprmsa"))])
+def test_info_float_statistics_bit_exact(name):
+    """network_compactness, its difference, avg_link_compactness, avg_link_utilization (rmsa_env.py:229-264):
+    float64, bit-identical to the reference on the recorded traces."""
+    g = helpers.load_golden(name)
+    meta = g["meta"]
+    n, T = meta["n_envs"], meta["T"]
+    env = make_env(meta, n, obs_dtype=torch.float64, link_stats=True)
+    env.set_trace(g["req_arrival"], g["req_holding"], g["req_src"], g["req_dst"], g["req_bit_rate"])
+    env.reset(full=True)
+    env.reset(full=False)
+    for t in range(T):
+        obs, reward, done, info = env.step(torch.as_tensor(g["actions"][:, t], device="cuda"))
+        assert np.array_equal(env.decisions.cpu().numpy()[:, 0], g["accepted"][:, t]), ("accepted", t)
+        for key in ("network_compactness", "network_compactness_difference", "avg_link_compactness", "avg_link_utilization"):
+            got = info[key].cpu().numpy()
+            assert np.array_equal(got, g["info_" + key][:, t]), (key, t, got, g["info_" + key][:, t])
+    assert np.array_equal(env.available_slots().cpu().numpy().reshape(g["final_avail"].shape), g["final_avail"])
+    assert int(env.error_flags().abs().sum()) == 0
+    env.close()

@@ -44,6 +44,11 @@ def replay(g, i, use_heuristic=False):
         if "info_bit_rate_blocking_rate" in g:
             assert (ic[4] - ic[5]) / ic[4] == g["info_bit_rate_blocking_rate"][i, t]
             assert (ic[6] - ic[7]) / ic[6] == g["info_episode_bit_rate_blocking_rate"][i, t]
+        if "info_network_compactness" in g:          # row f1: float statistics of info, bit-exact
+            assert o.stats[0] == g["info_network_compactness"][i, t], ("network_compactness", t)
+            assert o.stats[1] == g["info_network_compactness_difference"][i, t], ("compactness difference", t)
+            assert o.stats[2] == g["info_avg_link_compactness"][i, t], ("avg_link_compactness", t, o.stats[2], g["info_avg_link_compactness"][i, t])
+            assert o.stats[3] == g["info_avg_link_utilization"][i, t], ("avg_link_utilization", t)
         if i < g["avail_bits"].shape[0] and (t % 7 == 0 or t == T - 1):
             avail = e.state()[0].reshape(Cc * E, S).astype(np.uint8)
             assert np.array_equal(np.packbits(avail, axis=1, bitorder="little"), g["avail_bits"][i, t]), ("masks", t)
