@@ -156,6 +156,23 @@ int orlg_heuristic(orlg_env *env, int which, int32_t *actions_dev, orlg_stream s
 /* uniform random policy (action_space.sample() equivalent, Philox stream 2) */
 int orlg_random_actions(orlg_env *env, int32_t *actions_dev, orlg_stream stream);
 
+/* Discrete bit-rate selection (RMSA-v0, rmsa_env.py:88-110): the per-bit-rate blocking rates and `fairness` of
+ * `info` (rmsa_env.py:217-227, 268-273) as of the last orlg_step: float64 [num_envs, orlg_num_bit_rates + 1] =
+ * bit_rate_blocking_<rate> in the order of `bit_rates`, then fairness = max - min. */
+int orlg_num_bit_rates(const orlg_env *env);    /* 0 unless RMSA-v0 with discrete bit rates */
+int orlg_bit_rate_blocking(orlg_env *env, double *out_dev, orlg_stream stream);
+
+/* ---- gym wrappers of the reference, batched ---------------------------- */
+/* SimpleMatrixObservation.observation (rmsa_env.py:806-837, rmcsa_env.py:914-947) of every env:
+ * uint8 [num_envs, orlg_matrix_obs_dim] = one-hot(min(src_id, dst_id)) [nodes], one-hot(max(src_id, dst_id))
+ * [nodes], available_slots flattened as (core, link, slot), 1 = free */
+int orlg_matrix_obs_dim(const orlg_env *env);   /* 2*nodes + cores*links*slots */
+int orlg_matrix_observation(orlg_env *env, uint8_t *out_dev, orlg_stream stream);
+/* PathOnlyFirstFitAction.action (rmsa_env.py:840-874, rwa_env.py:505-536): path_actions_dev int32 [num_envs]
+ * (path index, anything else = reject) -> actions_dev int32 [num_envs, 2] = (path, first-fit slot) or (k, S).
+ * RMSA-v0 scans range(0, S - n) like the reference (never the last feasible start), RWA-v0 range(W). */
+int orlg_path_only_first_fit(orlg_env *env, const int32_t *path_actions_dev, int32_t *actions_dev, orlg_stream stream);
+
 /* ---- introspection (what heuristics / tests read from the reference env object) -------- */
 /* counters after the last step: int64 [num_envs, 8], same order as info_dev */
 int orlg_get_counters(orlg_env *env, int64_t *counters_dev, orlg_stream stream);

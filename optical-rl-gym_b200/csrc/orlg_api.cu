@@ -8,6 +8,7 @@
 
 #include "orlg_deeprmsa_fast.cuh"
 #include "orlg_step_wide.cuh"
+#include "orlg_wrappers.cuh"
 
 using namespace orlg;
 
@@ -308,6 +309,7 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     if (!rc) rc = dev_alloc(env, &p.cand, n * (size_t)p.cand_stride);
     if (!rc && wide && cfg->kind == ORLG_DEEPRMSA) rc = dev_alloc(env, &p.cand16, n * (size_t)p.cand_stride);
     if (!rc) rc = dev_alloc(env, &p.errors, n);
+    if (!rc && cfg->kind == ORLG_RMSA && t->num_bit_rates > 0) rc = dev_alloc(env, &p.br_hist, 2 * (size_t)t->num_bit_rates * n);
     if (rc) { orlg_destroy(env); return rc; }
 
     // ---- fast DeepRMSA kernel: small tables packed for shared-memory staging
@@ -569,6 +571,44 @@ int orlg_enable_stats(orlg_env *env, double *stats_dev) {
     }
     p.stats = 1;
     p.stats_out = stats_dev;
+    return ORLG_OK;
+}
+
+int orlg_num_bit_rates(const orlg_env *env) { return env->p.br_hist ? env->p.n_bit_rates : 0; }
+
+int orlg_bit_rate_blocking(orlg_env *env, double *out_dev, orlg_stream stream) {
+    if (!env || !out_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
+    if (!env->p.br_hist) return fail(ORLG_E_UNSUPPORTED, "per-bit-rate statistics exist for RMSA-v0 with bit_rate_selection='discrete'");
+    bit_rate_blocking_kernel<<<(env->p.n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->p, out_dev);
+    CUDA_OK(cudaGetLastError());
+    return ORLG_OK;
+}
+
+int orlg_matrix_obs_dim(const orlg_env *env) { return 2 * env->p.N + env->p.C * env->p.E * env->p.S; }
+
+int orlg_matrix_observation(orlg_env *env, uint8_t *out_dev, orlg_stream stream) {
+    if (!env || !out_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
+    const long long total = (long long)orlg_matrix_obs_dim(env) * env->p.n;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    matrix_observation_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(env->p, out_dev);
+    CUDA_OK(cudaGetLastError());
+    return ORLG_OK;
+}
+
+int orlg_path_only_first_fit(orlg_env *env, const int32_t *path_actions_dev, int32_t *actions_dev, orlg_stream stream) {
+    if (!env || !path_actions_dev || !actions_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
+    if (env->p.kind != ORLG_RMSA && env->p.kind != ORLG_RWA)
+        return fail(ORLG_E_UNSUPPORTED, "PathOnlyFirstFitAction exists for RMSA-v0 and RWA-v0 (the RMCSA one raises upstream)");
+    const int blocks = (env->p.n + 127) / 128;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (env->p.nwv) {
+    case 1: path_only_first_fit_kernel<1><<<blocks, 128, 0, s>>>(env->p, path_actions_dev, actions_dev); break;
+    case 2: path_only_first_fit_kernel<2><<<blocks, 128, 0, s>>>(env->p, path_actions_dev, actions_dev); break;
+    case 3: path_only_first_fit_kernel<3><<<blocks, 128, 0, s>>>(env->p, path_actions_dev, actions_dev); break;
+    default: path_only_first_fit_kernel<4><<<blocks, 128, 0, s>>>(env->p, path_actions_dev, actions_dev); break;
+    }
+    CUDA_OK(cudaGetLastError());
     return ORLG_OK;
 }
 

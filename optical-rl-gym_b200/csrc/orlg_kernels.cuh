@@ -72,7 +72,25 @@ struct Params {
     long long *sum_nh;                 // [n] sum over running services of number_slots * hops
     double *stats_out;                 // [n][4] network_compactness, its difference, avg link compactness, avg link utilisation
     const int *link_order;             // [E] link indices in topology.edges() order (np.mean over the links)
+    // ---- discrete bit-rate selection (row f4: rmsa_env.py:88-110, 217-227, 268-273, 408-415, 579-581)
+    int *br_hist;                      // [2][n_bit_rates][n] bit_rate_requested_histogram / bit_rate_provisioned_histogram
 };
+
+// position of a bit rate in the discrete list (-1: not one of them, e.g. a foreign trace)
+__device__ __forceinline__ int br_index(const Params &p, int br) {
+    for (int i = 0; i < p.n_bit_rates; i++)
+        if (p.bit_rates[i] == br) return i;
+    return -1;
+}
+__device__ __forceinline__ void br_hist_bump(const Params &p, int env, int which, int br) {
+    if (!p.br_hist) return;
+    const int i = br_index(p, br);
+    if (i >= 0) p.br_hist[((size_t)which * p.n_bit_rates + i) * p.n + env] += 1;
+}
+__device__ __forceinline__ void br_hist_clear(const Params &p, int env) {
+    if (!p.br_hist) return;
+    for (int i = 0; i < 2 * p.n_bit_rates; i++) p.br_hist[(size_t)i * p.n + env] = 0;
+}
 
 struct StepIO {
     const int *actions;
@@ -278,6 +296,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
         now = 0.0; nheap = 0; hmin = ORLG_INF; tailmin = ORLG_INF; ridx = 0; err = 0;
 #pragma unroll
         for (int q = 0; q < 8; q++) cnt[q] = 0;
+        if (KIND == ORLG_RMSA) br_hist_clear(p, env);
     }
 
     if (mode == MODE_STEP) {
@@ -363,6 +382,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
             }
             cnt[1] += 1; cnt[3] += 1;                        // services_accepted (+episode)
             if (KIND != ORLG_RWA) { cnt[5] += br; cnt[7] += br; }   // bit_rate_provisioned (+episode)
+            if (KIND == ORLG_RMSA) br_hist_bump(p, env, 1, br);     // rmsa_env.py:408-415
             d_row = row; d_start = start; d_n = n; d_core = core; d_mod = mod;
         }
         if (KIND == ORLG_RWA || KIND == ORLG_RMCSA) {         // rwa_env.py:135-136, rmcsa_env.py:292-295
@@ -419,6 +439,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
         sid = (int)cnt[2];                                    // Service(self.episode_services_processed, ...)
         if (KIND == ORLG_RMSA || KIND == ORLG_DEEPRMSA) {
             cnt[0] += 1; cnt[2] += 1; cnt[4] += br; cnt[6] += br;
+            if (KIND == ORLG_RMSA) br_hist_bump(p, env, 0, br);     // rmsa_env.py:579-581
         } else if (KIND == ORLG_RMCSA) {
             cnt[4] += br; cnt[6] += br;                       // rmcsa_env.py:730-731
         }
@@ -767,6 +788,25 @@ __global__ void export_kernel(const Params p, unsigned *masks_out, int *alloc_ou
     }
     if (sid_out) sid_out[env] = (int)p.cur_req[env].y;
     if (err_out) err_out[env] = p.errors[env];
+}
+
+// info["bit_rate_blocking_<rate>"] and info["fairness"] (rmsa_env.py:217-227, 268-273) as the reference sees them when
+// it builds `info`: the pending request (drawn after that point) is taken out of the requested histogram again.
+__global__ void bit_rate_blocking_kernel(const Params p, double *out) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.n) return;
+    const int B = p.n_bit_rates;
+    const int pending = br_index(p, (int)(p.cur_req[env].x >> 16));
+    double lo = 0.0, hi = 0.0;
+    for (int i = 0; i < B; i++) {
+        const int req = p.br_hist[(size_t)i * p.n + env] - (i == pending ? 1 : 0);
+        const int prov = p.br_hist[((size_t)B + i) * p.n + env];
+        const double b = req > 0 ? __ddiv_rn((double)(req - prov), (double)req) : 0.0;
+        out[(size_t)env * (B + 1) + i] = b;
+        lo = i == 0 ? b : fmin(lo, b);
+        hi = i == 0 ? b : fmax(hi, b);
+    }
+    out[(size_t)env * (B + 1) + B] = __dadd_rn(hi, -lo);
 }
 
 // per-device sums of the 8 counters (+ #envs with an error flag) for the cross-GPU all-reduce

@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(128) step_wide_kernel(const Params p, const St
         now = 0.0; nheap = 0; hmin = ORLG_INF; tailmin = ORLG_INF; ridx = 0; err = 0;
 #pragma unroll
         for (int q = 0; q < 8; q++) cnt[q] = 0;
+        if (KIND == ORLG_RMSA) br_hist_clear(p, env);
     }
 
     if (mode == MODE_STEP) {
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(128) step_wide_kernel(const Params p, const St
             events_push(ev, nheap, hmin, tailmin, __dadd_rn(now, hold), pack_service(row, start, n, core, sid));
             cnt[1] += 1; cnt[3] += 1;
             if (KIND != ORLG_RWA) { cnt[5] += br; cnt[7] += br; }
+            if (KIND == ORLG_RMSA) br_hist_bump(p, env, 1, br);
         }
         if (KIND == ORLG_RWA || KIND == ORLG_RMCSA) {
             cnt[0] += 1; cnt[2] += 1;
@@ -259,6 +261,7 @@ __global__ void __launch_bounds__(128) step_wide_kernel(const Params p, const St
         now = arrival; hold = holding; src = nsrc; dst = ndst; br = nbr;
         sid = (int)cnt[2];
         if (KIND == ORLG_RMSA || KIND == ORLG_DEEPRMSA) { cnt[0] += 1; cnt[2] += 1; cnt[4] += br; cnt[6] += br; }
+        if (KIND == ORLG_RMSA) br_hist_bump(p, env, 0, br);
         else if (KIND == ORLG_RMCSA) { cnt[4] += br; cnt[6] += br; }
         events_release(ev, nheap, hmin, tailmin, now, apply_payload([&](unsigned long long pl) {
             wide_path_update<NWV>(p, env, svc_row(pl), svc_core(pl), svc_start(pl), svc_slots(pl), true);

@@ -80,6 +80,11 @@ def lib():
     L.orlg_error_flags.argtypes = [vp, vp, vp]
     L.orlg_reduce_counters.argtypes = [vp, vp, vp]
     L.orlg_enable_stats.argtypes = [vp, vp]
+    L.orlg_num_bit_rates.argtypes = [vp]
+    L.orlg_bit_rate_blocking.argtypes = [vp, vp, vp]
+    L.orlg_matrix_obs_dim.argtypes = [vp]
+    L.orlg_matrix_observation.argtypes = [vp, vp, vp]
+    L.orlg_path_only_first_fit.argtypes = [vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -92,4 +97,6 @@ def check(rc):
 EXPORTED = ["orlg_create", "orlg_destroy", "orlg_last_error", "orlg_version", "orlg_action_dim", "orlg_obs_dim",
             "orlg_mask_words", "orlg_heap_capacity", "orlg_state_bytes", "orlg_set_trace", "orlg_reset", "orlg_step",
             "orlg_observation", "orlg_observation_int", "orlg_heuristic", "orlg_random_actions", "orlg_get_counters",
-            "orlg_get_requests", "orlg_export_state", "orlg_error_flags", "orlg_reduce_counters", "orlg_enable_stats"]
+            "orlg_get_requests", "orlg_export_state", "orlg_error_flags", "orlg_reduce_counters", "orlg_enable_stats",
+            "orlg_num_bit_rates", "orlg_bit_rate_blocking", "orlg_matrix_obs_dim", "orlg_matrix_observation",
+            "orlg_path_only_first_fit"]

@@ -1,0 +1,70 @@
+"""On-device MLP policy for the "PPO-policy actions" variant of the headline config.
+
+Architecture of the agent the reference trains and ships
+(examples/stable_baselines3/DeepRMSA.ipynb: ``PPO(MlpPolicy, env, policy_kwargs=dict(net_arch=5*[128]))``;
+examples/stable_baselines3/bkp/deeprmsa-ppo-trained/best_model.zip): observation 54 -> 5 x (Linear 128 + tanh)
+shared trunk -> ``action_net`` (5 logits) and ``value_net`` (1).  ``from_sb3_zip`` reads ``policy.pth`` out of
+such an archive (a plain ``state_dict``; Stable-Baselines3 itself is not needed).  The forward pass is five
+small GEMMs on whatever device the observations live on (library GEMMs: this is plumbing next to the env).
+"""
+from __future__ import annotations
+
+import io
+import zipfile
+from typing import Sequence
+
+import torch
+
+
+class MlpPolicy(torch.nn.Module):
+    def __init__(self, obs_dim: int = 54, n_actions: int = 5, net_arch: Sequence[int] = (128,) * 5):
+        super().__init__()
+        layers, d = [], obs_dim
+        for width in net_arch:
+            layers += [torch.nn.Linear(d, width), torch.nn.Tanh()]
+            d = width
+        self.shared_net = torch.nn.Sequential(*layers)
+        self.action_net = torch.nn.Linear(d, n_actions)
+        self.value_net = torch.nn.Linear(d, 1)
+
+    @classmethod
+    def from_state_dict(cls, sd) -> "MlpPolicy":
+        """``policy.pth`` of an SB3 ``ActorCriticPolicy`` with a shared trunk (keys ``mlp_extractor.shared_net.<2i>``)
+        or with separate actor/critic trunks (``mlp_extractor.policy_net`` / ``value_net``, SB3 >= 1.8: the actor's
+        trunk is kept)."""
+        trunk = "mlp_extractor.shared_net." if any(k.startswith("mlp_extractor.shared_net.") for k in sd) else "mlp_extractor.policy_net."
+        idx = sorted({int(k[len(trunk):].split(".")[0]) for k in sd if k.startswith(trunk)})
+        widths = [sd["%s%d.weight" % (trunk, i)].shape[0] for i in idx]
+        obs_dim = sd["%s%d.weight" % (trunk, idx[0])].shape[1]
+        pol = cls(obs_dim, sd["action_net.weight"].shape[0], widths)
+        mine = {}
+        for j, i in enumerate(idx):
+            mine["shared_net.%d.weight" % (2 * j)] = sd["%s%d.weight" % (trunk, i)]
+            mine["shared_net.%d.bias" % (2 * j)] = sd["%s%d.bias" % (trunk, i)]
+        for k in ("action_net.weight", "action_net.bias", "value_net.weight", "value_net.bias"):
+            mine[k] = sd[k]
+        pol.load_state_dict(mine)
+        return pol
+
+    @classmethod
+    def from_sb3_zip(cls, path, device=None) -> "MlpPolicy":
+        with zipfile.ZipFile(path) as z:
+            sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu", weights_only=True)
+        pol = cls.from_state_dict(sd)
+        return pol.to(device) if device is not None else pol
+
+    def forward(self, obs: torch.Tensor):
+        """(logits [N, n_actions], value [N]) -- observations are used as they are (SB3 ``preprocess_obs`` of a
+        Box space is a cast to float)."""
+        latent = self.shared_net(obs.to(self.action_net.weight.dtype))
+        return self.action_net(latent), self.value_net(latent).squeeze(-1)
+
+    @torch.no_grad()
+    def act(self, obs: torch.Tensor, deterministic: bool = True, generator=None) -> torch.Tensor:
+        """int32 actions [N, 1] ready for ``OpticalVecEnv.step_raw`` (``model.predict(obs, deterministic=...)``)."""
+        logits, _ = self.forward(obs)
+        if deterministic:
+            a = logits.argmax(dim=-1)
+        else:
+            a = torch.multinomial(torch.softmax(logits.float(), dim=-1), 1, generator=generator).squeeze(-1)
+        return a.to(torch.int32).unsqueeze(-1)

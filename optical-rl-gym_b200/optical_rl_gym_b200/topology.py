@@ -47,7 +47,7 @@ class TopologyTables:
     num_links: int
     k_paths: int
     node_names: Tuple[str, ...]
-    link_nodes: np.ndarray      # int32 [E,2] node indices of each link index
+    link_nodes: np.ndarray      # int32 [E,2] node indices (low, high) of each link index
     link_length: np.ndarray     # float64 [E]
     pair_first: np.ndarray      # int32 [N*N] first path row of (src,dst); -1 on the diagonal
     pair_count: np.ndarray      # int32 [N*N] number of candidate paths (<= k)
@@ -113,7 +113,7 @@ class TopologyTables:
         link_nodes = np.zeros((e, 2), np.int32)
         link_length = np.zeros(e, np.float64)
         for u, v, data in graph.edges(data=True):
-            link_nodes[data["index"]] = (nidx[u], nidx[v])
+            link_nodes[data["index"]] = (min(nidx[u], nidx[v]), max(nidx[u], nidx[v]))
             link_length[data["index"]] = float(data.get("length", 0.0))
         mods = tuple(g.get("modulations") or ())
         mod_key = [(m.name, m.spectral_efficiency) for m in mods]
@@ -157,21 +157,36 @@ class TopologyTables:
     def from_links(cls, name: str, num_nodes: int, links: Iterable[Tuple[int, int, float]], k_paths: int = 5,
                    modulations: Optional[Sequence[Tuple[str, float, int, float, float]]] = DEFAULT_MODULATIONS,
                    one_based: bool = True) -> "TopologyTables":
-        """k-shortest-path pre-processing from a plain link list (NetworkX Yen's algorithm,
-        like ``utils.get_k_shortest_paths`` / ``create_topology.py:106-137``)."""
-        import networkx as nx
-
+        """k-shortest-path pre-processing from a plain link list over nodes 1..N (or 0..N-1)."""
         off = 1 if one_based else 0
         node_names = tuple(str(i + off) for i in range(num_nodes))
+        return cls.from_named_links(name, node_names, [(str(u), str(v), l) for u, v, l in links], k_paths, modulations)
+
+    @classmethod
+    def from_named_links(cls, name: str, node_names: Sequence[str], links: Sequence[Tuple[str, str, float]],
+                         k_paths: int = 5,
+                         modulations: Optional[Sequence[Tuple[str, float, int, float, float]]] = DEFAULT_MODULATIONS,
+                         ) -> "TopologyTables":
+        """``get_topology`` (examples/create_topology.py:96-147) on a node list + link list: NetworkX Yen's
+        algorithm by length (``utils.get_k_shortest_paths``), path length as ``np.sum`` over the hops, the most
+        spectrally efficient modulation whose reach covers it (``utils.get_best_modulation_format``).  Nodes and
+        links are inserted in the given order, which is what fixes the tie-breaking between equal-length paths
+        and the ``topology.edges()`` iteration order (``link_order``)."""
+        import networkx as nx
+
+        node_names = tuple(str(x) for x in node_names)
+        nidx = {nm: i for i, nm in enumerate(node_names)}
         graph = nx.Graph()
-        for nm in node_names:            # same insertion order as graph_utils.read_txt_file
+        for nm in node_names:            # same insertion order as graph_utils.read_txt_file / read_sndlib_topology
             graph.add_node(nm)
-        links = list(links)
+        links = [(str(u), str(v), l) for u, v, l in links]
         for idx, (u, v, length) in enumerate(links):
-            graph.add_edge(str(u), str(v), index=idx, length=length)
+            if u not in nidx or v not in nidx:
+                raise ValueError("link %d joins an unknown node (%s, %s)" % (idx, u, v))
+            graph.add_edge(u, v, index=idx, length=length)
         mods = tuple(modulations or ())
         by_se = sorted(range(len(mods)), key=lambda m: mods[m][2], reverse=True)
-        n = num_nodes
+        n = len(node_names)
         pair_first = np.full(n * n, -1, np.int32)
         pair_count = np.zeros(n * n, np.int32)
         hops, length, se, mod, ptr, plinks, nodes = [], [], [], [], [0], [], []
@@ -185,20 +200,20 @@ class TopologyTables:
                     if mods:
                         best = next((m for m in by_se if plen <= mods[m][1]), None)
                         if best is None:
-                            raise ValueError("no modulation reaches a path of %s km" % plen)
+                            raise ValueError("It was not possible to find a suitable MF for a path with %s km" % plen)
                     hops.append(len(p) - 1)
                     length.append(plen)
                     se.append(int(mods[best][2]) if mods else 1)
                     mod.append(best)
                     plinks.extend(int(graph[a][b]["index"]) for a, b in zip(p[:-1], p[1:]))
-                    nodes.extend(int(x) - off for x in p)
+                    nodes.extend(nidx[x] for x in p)
                     ptr.append(len(plinks))
                 for key in (i * n + j, j * n + i):
                     pair_first[key] = first
                     pair_count[key] = len(paths)
         return cls(
             name=name, num_nodes=n, num_links=len(links), k_paths=k_paths, node_names=node_names,
-            link_nodes=np.array([(u - off, v - off) for u, v, _ in links], np.int32).reshape(-1, 2),
+            link_nodes=np.array([(min(nidx[u], nidx[v]), max(nidx[u], nidx[v])) for u, v, _ in links], np.int32).reshape(-1, 2),
             link_length=np.array([l for _, _, l in links], np.float64),
             pair_first=pair_first, pair_count=pair_count,
             path_hops=np.array(hops, np.int32), path_length=np.array(length, np.float64),
@@ -212,6 +227,141 @@ class TopologyTables:
             mod_xt=np.array([m[4] for m in mods], np.float64),
             link_order=np.array([data["index"] for _, _, data in graph.edges(data=True)], np.int32),
         )
+
+
+# ---------------------------------------------------------------------- topology files
+def read_txt_file(file) -> Tuple[Tuple[str, ...], list]:
+    """The reference's ``.txt`` format (examples/graph_utils.py:89-116): lines starting with ``#`` are comments,
+    then the node count, the link count, and one ``src dst length_km`` line per link; nodes are named "1".."N"
+    and link ``index`` is the line order.  Returns (node names, [(src, dst, length)])."""
+    with open(file, "r") as fh:
+        lines = [ln for ln in fh if not ln.startswith("#")]
+    names: Tuple[str, ...] = ()
+    links = []
+    for idx, line in enumerate(lines):
+        if idx == 0:
+            names = tuple(str(i) for i in range(1, int(line) + 1))
+        elif idx == 1:
+            int(line)                      # declared link count (the reference reads and ignores it)
+        elif len(line) > 1:
+            info = line.replace("\n", "").split(" ")
+            links.append((info[0], info[1], int(info[2])))
+    return names, links
+
+
+def _geographical_distance(latlong1, latlong2) -> float:
+    """examples/graph_utils.py:10-28 (haversine, R = 6373 km; note the reference feeds (x, y) = (lon, lat))."""
+    import math
+
+    R = 6373.0
+    lat1, lon1 = math.radians(latlong1[0]), math.radians(latlong1[1])
+    lat2, lon2 = math.radians(latlong2[0]), math.radians(latlong2[1])
+    dlon, dlat = lon2 - lon1, lat2 - lat1
+    a = math.sin(dlat / 2) ** 2 + math.cos(lat1) * math.cos(lat2) * math.sin(dlon / 2) ** 2
+    c = 2 * math.atan2(math.sqrt(a), math.sqrt(1 - a))
+    return R * c
+
+
+def read_sndlib_topology(file) -> Tuple[Tuple[str, ...], list]:
+    """SNDlib native XML (examples/graph_utils.py:31-86): nodes in document order with (x, y) coordinates, link
+    length = haversine distance (``coordinatesType="geographical"``) or the Euclidean one, rounded to 3 decimals."""
+    import math
+    import xml.dom.minidom
+
+    doc = xml.dom.minidom.parse(file).documentElement
+    ctype = doc.getElementsByTagName("nodes")[0].getAttribute("coordinatesType")
+    pos, names = {}, []
+    for node in doc.getElementsByTagName("node"):
+        x = float(node.getElementsByTagName("x")[0].childNodes[0].data)
+        y = float(node.getElementsByTagName("y")[0].childNodes[0].data)
+        names.append(node.getAttribute("id"))
+        pos[names[-1]] = (x, y)
+    links = []
+    for link in doc.getElementsByTagName("link"):
+        s = link.getElementsByTagName("source")[0].childNodes[0].data
+        t = link.getElementsByTagName("target")[0].childNodes[0].data
+        if ctype == "geographical":
+            length = np.around(_geographical_distance(pos[s], pos[t]), 3)
+        else:
+            length = np.around(math.sqrt((pos[s][0] - pos[t][0]) ** 2 + (pos[s][1] - pos[t][1]) ** 2), 3)
+        links.append((s, t, float(length)))
+    return tuple(names), links
+
+
+def get_topology(file_name, topology_name: Optional[str] = None, modulations=DEFAULT_MODULATIONS, k_paths: int = 5,
+                 cache_dir: Optional[str] = None) -> TopologyTables:
+    """``examples/create_topology.py:get_topology`` -> flat tables.  ``cache_dir`` keeps the k-shortest-path
+    result on disk (keyed by file contents, k and the modulation table): Yen's algorithm on a 100-node graph
+    takes about a minute of host time."""
+    import hashlib
+    import os
+
+    file_name = str(file_name)
+    if file_name.endswith(".xml"):
+        names, links = read_sndlib_topology(file_name)
+    elif file_name.endswith(".txt"):
+        names, links = read_txt_file(file_name)
+    else:
+        raise ValueError("Supplied topology is unknown")
+    name = topology_name or os.path.splitext(os.path.basename(file_name))[0]
+    cache = None
+    if cache_dir:
+        with open(file_name, "rb") as fh:
+            key = hashlib.sha256(fh.read() + repr((k_paths, tuple(modulations or ()))).encode()).hexdigest()[:16]
+        cache = os.path.join(cache_dir, "%s_k%d_%s.npz" % (name, k_paths, key))
+        if os.path.exists(cache):
+            return TopologyTables.load(cache)
+    tables = TopologyTables.from_named_links(name, names, links, k_paths=k_paths, modulations=modulations)
+    if cache:
+        os.makedirs(cache_dir, exist_ok=True)
+        tables.save(cache)
+    return tables
+
+
+def load_reference_pickle(file) -> TopologyTables:
+    """Un-pickles a topology written by the reference's ``create_topology.py`` (the shipped ``*.h5`` files are
+    pickles of an ``nx.Graph`` whose ``ksp`` entries are ``optical_rl_gym.utils.Path`` / ``Modulation``
+    dataclasses, utils.py:14-59).  The reference package is not needed: stand-in classes with the same module
+    path are registered for the duration of the load."""
+    import pickle
+    import sys
+    import types
+
+    stubs = {}
+    if "optical_rl_gym.utils" not in sys.modules:
+        @dataclasses.dataclass
+        class Modulation:
+            name: str
+            maximum_length: float
+            spectral_efficiency: int
+            minimum_osnr: Optional[float] = None
+            inband_xt: Optional[float] = None
+
+        @dataclasses.dataclass
+        class Path:
+            path_id: int
+            node_list: Tuple[str]
+            hops: int
+            length: float
+            best_modulation: Optional[Modulation] = None
+            current_modulation: Optional[Modulation] = None
+
+        pkg = sys.modules.get("optical_rl_gym") or types.ModuleType("optical_rl_gym")
+        utils = types.ModuleType("optical_rl_gym.utils")
+        utils.Modulation, utils.Path = Modulation, Path
+        Modulation.__module__ = Path.__module__ = "optical_rl_gym.utils"
+        stubs = {"optical_rl_gym": pkg, "optical_rl_gym.utils": utils}
+        added = [k for k in stubs if k not in sys.modules]
+        sys.modules.update({k: stubs[k] for k in added})
+    else:
+        added = []
+    try:
+        with open(file, "rb") as fh:
+            graph = pickle.load(fh)
+    finally:
+        for k in added:
+            sys.modules.pop(k, None)
+    return TopologyTables.from_graph(graph)
 
 
 def nsfnet(k_paths: int = 5) -> TopologyTables:

@@ -59,10 +59,13 @@ class StepInfo:
     _COL = {"service_blocking_rate": (0, 1), "episode_service_blocking_rate": (2, 3),
             "bit_rate_blocking_rate": (4, 5), "episode_bit_rate_blocking_rate": (6, 7)}
 
-    def __init__(self, counters: torch.Tensor, keys, stats: Optional[torch.Tensor] = None):
+    def __init__(self, counters: torch.Tensor, keys, stats: Optional[torch.Tensor] = None,
+                 bit_rate_blocking: Optional[torch.Tensor] = None, bit_rates=()):
         self.counters = counters       # int64 [N, 8]
         self.stats = stats             # float64 [N, 4] (rmsa_env.py:249-263) when link_stats=True
-        self._keys = list(keys) + (STAT_KEYS if stats is not None else [])
+        self.bit_rate_blocking = bit_rate_blocking     # float64 [N, B + 1] (rmsa_env.py:217-227, 268-273), discrete mode
+        self._br_keys = ["bit_rate_blocking_%d" % int(b) for b in bit_rates] + ["fairness"] if bit_rate_blocking is not None else []
+        self._keys = list(keys) + (STAT_KEYS if stats is not None else []) + self._br_keys
 
     def keys(self):
         return list(self._keys)
@@ -78,6 +81,8 @@ class StepInfo:
             raise KeyError(key)
         if key in STAT_KEYS:
             return self.stats[:, STAT_KEYS.index(key)]
+        if key in self._br_keys:
+            return self.bit_rate_blocking[:, self._br_keys.index(key)]
         a, b = self._COL[key]
         c = self.counters
         return (c[:, a] - c[:, b]).to(torch.float64) / c[:, a].to(torch.float64)
@@ -228,6 +233,11 @@ class OpticalVecEnv:
         if link_stats:
             self._stats = torch.zeros((n, 4), dtype=torch.float64, device=dev)
             nat.check(self._lib.orlg_enable_stats(self._h, _ptr(self._stats)))
+        # discrete bit-rate selection: per-bit-rate blocking + fairness of `info` (rmsa_env.py:217-227, 268-273)
+        self._brb = None
+        nb = self._lib.orlg_num_bit_rates(self._h)
+        if nb and collect_info:
+            self._brb = torch.zeros((n, nb + 1), dtype=torch.float64, device=dev)
         if traffic == "philox" and a.get("reset", True):
             self.reset(full=True)
 
@@ -295,7 +305,11 @@ class OpticalVecEnv:
     def step_wait(self):
         nat.check(self._lib.orlg_step(self._h, _ptr(self._actions), _ptr(self._obs), _ptr(self._reward), _ptr(self._done),
                                       _ptr(self._decision), _ptr(self._info), self._stream()))
-        info = StepInfo(self._info, self.metadata["metrics"], self._stats) if self._info is not None else None
+        info = None
+        if self._info is not None:
+            if self._brb is not None:
+                nat.check(self._lib.orlg_bit_rate_blocking(self._h, _ptr(self._brb), self._stream()))
+            info = StepInfo(self._info, self.metadata["metrics"], self._stats, self._brb, self.bit_rates)
         return self._obs, self._reward, self._done, info
 
     def step(self, actions):
@@ -326,6 +340,23 @@ class OpticalVecEnv:
         if out is None:
             out = torch.empty((self.num_envs, self.action_dim), dtype=torch.int32, device=self.device)
         nat.check(self._lib.orlg_heuristic(self._h, which, _ptr(out), self._stream()))
+        return out
+
+    def matrix_observation(self, out: Optional[torch.Tensor] = None):
+        """``SimpleMatrixObservation.observation`` of every env (rmsa_env.py:806-837, rmcsa_env.py:914-947):
+        uint8 [N, 2*nodes + cores*links*slots]."""
+        d = self._lib.orlg_matrix_obs_dim(self._h)
+        if out is None:
+            out = torch.empty((self.num_envs, d), dtype=torch.uint8, device=self.device)
+        nat.check(self._lib.orlg_matrix_observation(self._h, _ptr(out), self._stream()))
+        return out
+
+    def path_only_first_fit(self, path_actions, out: Optional[torch.Tensor] = None):
+        """``PathOnlyFirstFitAction.action`` for every env (rmsa_env.py:840-874, rwa_env.py:505-536)."""
+        pa = torch.as_tensor(path_actions, device=self.device).to(torch.int32).reshape(self.num_envs).contiguous()
+        if out is None:
+            out = torch.empty((self.num_envs, 2), dtype=torch.int32, device=self.device)
+        nat.check(self._lib.orlg_path_only_first_fit(self._h, _ptr(pa), _ptr(out), self._stream()))
         return out
 
     def sample_actions(self, out: Optional[torch.Tensor] = None):

@@ -64,6 +64,7 @@ def lib():
         L.oracle_random_action.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_get_request.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_get_counters.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_get_bit_rate_blocking.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 4
         L.oracle_error.argtypes = [C.c_void_p]
         L.oracle_error.restype = C.c_int
@@ -191,6 +192,12 @@ class OracleEnv:
         self.L.oracle_get_counters(self.h, _ptr(c))
         return c
 
+    def bit_rate_blocking(self):
+        """info["bit_rate_blocking_<rate>"] per discrete bit rate + info["fairness"] of the last step."""
+        out = np.zeros(self.cfg.num_bit_rates + 1, np.float64)
+        self.L.oracle_get_bit_rate_blocking(self.h, _ptr(out))
+        return out
+
     def state(self):
         avail = np.zeros(self.cells, np.int8)
         alloc = np.zeros(self.cells, np.int32)
@@ -213,6 +220,44 @@ class OracleEnv:
         self.L.oracle_rollout(self.h, T, policy, _ptr(actions), self.adim, _ptr(dec), _ptr(rew), _ptr(done),
                               _ptr(obs), self.obs_dim, _ptr(aout))
         return dict(decisions=dec, rewards=rew, dones=done, obs=obs, actions=aout)
+
+
+# ---------------------------------------------------------------- row f2: the reference's gym wrappers (numpy restatement)
+def simple_matrix_observation(env, num_nodes):
+    """SimpleMatrixObservation.observation (rmsa_env.py:806-837, rmcsa_env.py:914-947): float64 0/1 vector
+    one-hot(min(src_id, dst_id)) ++ one-hot(max(src_id, dst_id)) ++ available_slots.reshape(-1)."""
+    avail, _, _, _ = env.state()
+    r = env.request()
+    tau = np.zeros((2, num_nodes))
+    tau[0, min(r["src"], r["dst"])] = 1
+    tau[1, max(r["src"], r["dst"])] = 1
+    spectrum = avail.astype(np.float64)
+    if env.cfg.num_cores == 1:
+        spectrum = spectrum[0]
+    return np.concatenate((tau.reshape((1, tau.size)), spectrum.reshape((1, spectrum.size))), axis=1).reshape(-1)
+
+
+def path_only_first_fit(env, tables, action):
+    """PathOnlyFirstFitAction.action (rmsa_env.py:840-874; rwa_env.py:505-536): path index -> (path, first-fit
+    slot); RMSA tries range(0, S - n) only, RWA range(W); otherwise the reject action (k, S)."""
+    import math
+
+    k, S = tables.k_paths, env.cfg.num_slots
+    if action < k:
+        avail, _, _, _ = env.state()
+        r = env.request()
+        row = tables.rows_of(r["src"], r["dst"])[action]
+        links = tables.links_of(row)
+        if env.kind == KINDS["RWA-v0"]:
+            for w in range(S):
+                if np.all(avail[0, links, w] == 1):
+                    return (action, w)
+        else:
+            n = math.ceil(r["bit_rate"] / (int(tables.path_se[row]) * env.cfg.channel_width)) + 1
+            for s in range(0, S - n):
+                if np.all(avail[0, links, s:s + n] == 1):
+                    return (action, s)
+    return (k, S)
 
 
 def rollout_mt(env_id, tables, *, seed, env0, n_envs, steps, policy=1, with_obs=True, threads=None, **kw):

@@ -90,7 +90,17 @@ typedef struct {
     /* float statistics of row f1 (rmsa_env.py:439-543, 699-744) */
     double *link_util, *link_comp, *link_last;   /* [E] time-averaged utilisation / compactness, last update time */
     long sum_nh;                                  /* sum over running services of number_slots * hops */
+    /* discrete bit-rate selection (rmsa_env.py:88-110): bit_rate_requested_histogram / bit_rate_provisioned_histogram,
+       and what step() derives from them for `info` (rmsa_env.py:217-227, 268-273) */
+    int64_t hist_req[64], hist_prov[64];
+    double br_blocking[65];                       /* per bit rate (order of bit_rates), then fairness */
 } oenv_t;
+
+static int br_slot(const oenv_t *e, int bit_rate) {
+    for (int i = 0; i < e->c.num_bit_rates; i++)
+        if (e->t.bit_rates[i] == bit_rate) return i;
+    return -1;
+}
 
 /* ------------------------------------------------------------------ tables */
 static void *dup_mem(oenv_t *e, const void *p, size_t n) {
@@ -394,6 +404,7 @@ static void next_service(oenv_t *e) {
         e->cur = s; e->new_service = 1;
         e->processed++; e->ep_processed++;
         e->br_req += s.bit_rate; e->ep_br_req += s.bit_rate;
+        if (e->c.kind == KIND_RMSA && br_slot(e, s.bit_rate) >= 0) e->hist_req[br_slot(e, s.bit_rate)]++;   /* rmsa_env.py:579-581 */
         release_due(e);
     } else if (e->c.kind == KIND_RWA) {
         release_due(e);
@@ -546,6 +557,7 @@ void oracle_reset(void *p, int full) {
     e->nheap = 0; e->now = 0.0;
     e->processed = e->accepted = 0; e->br_req = e->br_prov = 0;
     e->req_index = 0;
+    memset(e->hist_req, 0, sizeof(e->hist_req)); memset(e->hist_prov, 0, sizeof(e->hist_prov));   /* rmsa_env.py:348-349 */
     e->sum_nh = 0;
     for (int l = 0; l < e->c.num_links; l++) { e->link_util[l] = 0.0; e->link_comp[l] = 0.0; e->link_last[l] = 0.0; }
     size_t cells = (size_t)e->c.num_cores * e->c.num_links * e->c.num_slots;
@@ -585,9 +597,21 @@ static int step_rmsa(oenv_t *e, int path, int initial_slot, ostep_t *o) {
                 e->accepted++; e->ep_accepted++;
                 e->br_prov += e->cur.bit_rate; e->ep_br_prov += e->cur.bit_rate;
                 e->cur.accepted = 1;
+                if (e->c.kind == KIND_RMSA && br_slot(e, e->cur.bit_rate) >= 0) e->hist_prov[br_slot(e, e->cur.bit_rate)]++;   /* rmsa_env.py:408-415 */
                 heap_push(e, e->cur.arrival + e->cur.holding, &e->cur);
             }
         }
+    }
+    if (e->c.kind == KIND_RMSA && e->c.num_bit_rates > 0) {      /* rmsa_env.py:217-227, 268-273 */
+        double lo = 0.0, hi = 0.0;
+        for (int i = 0; i < e->c.num_bit_rates; i++) {
+            double b = 0.0;
+            if (e->hist_req[i] > 0) b = (double)(e->hist_req[i] - e->hist_prov[i]) / (double)e->hist_req[i];
+            e->br_blocking[i] = b;
+            if (i == 0 || b < lo) lo = b;
+            if (i == 0 || b > hi) hi = b;
+        }
+        e->br_blocking[e->c.num_bit_rates] = hi - lo;
     }
     o->stats[0] = o->stats[1] = o->stats[2] = o->stats[3] = 0.0;
     if (e->c.stats) {   /* rmsa_env.py:229-264 */
@@ -836,6 +860,12 @@ void oracle_get_request(void *p, double *arrival, double *holding, int32_t *ints
     oenv_t *e = (oenv_t *)p;
     *arrival = e->cur.arrival; *holding = e->cur.holding;
     ints[0] = e->cur.src; ints[1] = e->cur.dst; ints[2] = e->cur.bit_rate; ints[3] = e->cur.id;
+}
+
+/* info["bit_rate_blocking_<rate>"] (order of bit_rates) and info["fairness"] of the last step */
+void oracle_get_bit_rate_blocking(void *p, double *out /* [num_bit_rates + 1] */) {
+    oenv_t *e = (oenv_t *)p;
+    for (int i = 0; i <= e->c.num_bit_rates; i++) out[i] = e->br_blocking[i];
 }
 
 void oracle_get_counters(void *p, int64_t *c /* [8] */) {

@@ -12,7 +12,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def golden_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not p.endswith("nsfnet_tables.npz"))
+                  if not p.endswith("nsfnet_tables.npz") and not os.path.basename(p).startswith(("wrap_", "topo_")))
 
 
 def load_golden(name):
@@ -20,6 +20,10 @@ def load_golden(name):
         g = {k: z[k] for k in z.files}
     g["meta"] = json.loads(str(g["meta"]))
     return g
+
+
+def wrapper_golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "wrap_*.npz")))
 
 
 def golden_tables():
@@ -50,6 +54,9 @@ def sim_kwargs(meta):
     if kind == "RMCSA-v0":
         kw["num_cores"] = a.get("num_spatial_resources", 7)
         kw["worst_xt"] = a.get("worst_xt", {7: -84.7, 12: -61.9, 19: -54.8}.get(kw["num_cores"]))
+    if a.get("bit_rate_selection") == "discrete":
+        kw["bit_rates"] = list(a.get("bit_rates", (10, 40, 100)))
+        kw["bit_rate_prob"] = a.get("bit_rate_probabilities")
     if a.get("node_request_probabilities") is not None:
         kw["node_prob"] = np.array(a["node_request_probabilities"], np.float64)
     return kw

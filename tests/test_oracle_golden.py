@@ -49,6 +49,11 @@ def replay(g, i, use_heuristic=False):
             assert o.stats[1] == g["info_network_compactness_difference"][i, t], ("compactness difference", t)
             assert o.stats[2] == g["info_avg_link_compactness"][i, t], ("avg_link_compactness", t, o.stats[2], g["info_avg_link_compactness"][i, t])
             assert o.stats[3] == g["info_avg_link_utilization"][i, t], ("avg_link_utilization", t)
+        if "info_fairness" in g:                     # row f4: discrete bit rates (rmsa_env.py:217-227, 268-273)
+            brb = e.bit_rate_blocking()
+            for b, rate in enumerate(helpers.sim_kwargs(meta)["bit_rates"]):
+                assert brb[b] == g["info_bit_rate_blocking_%d" % rate][i, t], ("bit_rate_blocking", rate, t)
+            assert brb[-1] == g["info_fairness"][i, t], ("fairness", t)
         if i < g["avail_bits"].shape[0] and (t % 7 == 0 or t == T - 1):
             avail = e.state()[0].reshape(Cc * E, S).astype(np.uint8)
             assert np.array_equal(np.packbits(avail, axis=1, bitorder="little"), g["avail_bits"][i, t]), ("masks", t)
