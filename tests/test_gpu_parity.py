@@ -351,3 +351,68 @@ def test_info_float_statistics_bit_exact(name):
     assert np.array_equal(env.available_slots().cpu().numpy().reshape(g["final_avail"].shape), g["final_avail"])
     assert int(env.error_flags().abs().sum()) == 0
     env.close()
+
+
+# ------------------------------------------------------------------ ragged batches and boundary sizes
+@pytest.mark.parametrize("kind,n_envs,env_args", [
+    ("DeepRMSA-v0", 1, dict(episode_length=20)),                                   # a single env
+    ("DeepRMSA-v0", 33, dict(episode_length=20)),                                  # one lane past a warp
+    ("DeepRMSA-v0", 129, dict(episode_length=25, num_spectrum_resources=128)),     # one env past a CTA; S = word boundary
+    ("DeepRMSA-v0", 31, dict(episode_length=2, j=2, num_spectrum_resources=33)),   # 1-step episodes, S just past a word
+    ("RMSA-v0", 127, dict(episode_length=30, load=400, mean_service_holding_time=25, num_spectrum_resources=128,
+                          allow_rejection=True)),
+    ("RWA-v0", 5, dict(episode_length=10, load=600, mean_service_holding_time=25, num_spectrum_resources=32)),
+    ("RMCSA-v0", 3, dict(episode_length=15, load=500, mean_service_holding_time=25, num_spectrum_resources=40,
+                         num_spatial_resources=2, worst_xt=-84.7, allow_rejection=True)),
+])
+def test_ragged_batches_and_boundary_sizes_match_oracle(kind, n_envs, env_args):
+    """Batch sizes that are not a multiple of the warp / CTA size, slot counts on and next to a 32-bit word
+    boundary, very short episodes: CUDA == oracle on Philox traffic (decisions, dones, observations, final state)."""
+    from optical_rl_gym_b200 import OpticalVecEnv
+    from oracle import oracle
+
+    tables = helpers.golden_tables()
+    seed, base, T = 13, 70, 120
+    env = OpticalVecEnv(kind, n_envs, tables, traffic="philox", record_decisions=True, obs_dtype=torch.float64,
+                        env_id_base=base, seed=seed, **env_args)
+    okw = helpers.sim_kwargs(dict(kind=kind, env_args=env_args))
+    refs, oracles = [], []
+    for i in range(n_envs):
+        o = oracle.OracleEnv(kind, tables, **okw)
+        o.set_philox(seed, base + i)
+        o.reset(full=True)
+        refs.append(o.rollout(T, policy=1, want_obs=(kind == "DeepRMSA-v0")))
+        oracles.append(o)
+    for t in range(T):
+        a = env.sample_actions()
+        assert np.array_equal(a.cpu().numpy(), np.stack([r["actions"][t] for r in refs])), ("actions", t)
+        obs, reward, done, info = env.step(a)
+        assert np.array_equal(env.decisions.cpu().numpy()[:, :4], np.stack([r["decisions"][t] for r in refs])), ("decision", t)
+        assert np.array_equal(done.cpu().numpy(), np.array([r["dones"][t] for r in refs])), ("done", t)
+        if kind == "DeepRMSA-v0":
+            assert np.array_equal(obs.cpu().numpy(), np.stack([r["obs"][t] for r in refs])), ("obs", t)
+    avail = env.available_slots().cpu().numpy()
+    cnt = env.counters().cpu().numpy()
+    for i, o in enumerate(oracles):
+        oa = o.state()[0]
+        assert np.array_equal(avail[i].reshape(oa.shape), oa), ("avail", i)
+        assert np.array_equal(cnt[i], o.counters()), ("counters", i)
+    assert int(env.error_flags().abs().sum()) == 0
+    env.close()
+
+
+def test_heap_overflow_is_flagged_not_silent():
+    """More live services than heap_capacity: the request is blocked and the env carries ORLG_ERR_HEAP_OVERFLOW."""
+    from optical_rl_gym_b200 import OpticalVecEnv, _native
+
+    env = OpticalVecEnv("RWA-v0", 8, helpers.golden_tables(), seed=2, heap_capacity=16, load=2000,
+                        mean_service_holding_time=25, episode_length=1000)
+    for _ in range(200):
+        env.step(env.heuristic("sap_ff"))
+    flags = env.error_flags().cpu().numpy()
+    assert (flags & _native.ERR_HEAP_OVERFLOW).all()
+    m, alloc, now, nheap = env.export_state(allocation=True)
+    assert int(nheap.max()) <= env.heap_capacity
+    avail = env.available_slots()
+    assert torch.equal((avail == 0), (alloc.reshape(avail.shape) >= 0))      # state stays consistent
+    env.close()
