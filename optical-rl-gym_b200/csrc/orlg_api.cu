@@ -32,6 +32,7 @@ struct orlg_env {
     int device;
     int km;                       // KM template instance (5 or 8)
     bool fast;                    // DeepRMSA fast kernel applicable (NSFNET-class: 22 links, k <= 5)
+    bool hot;                     // ... and its steady-state specialisation (deeprmsa_fast_kernel<.., HOT = true>)
     bool wide;                    // beyond 32 links / 128 slots / 8 paths: CSR link lists, multi-word masks
     size_t fast_smem;
     size_t obs_smem;
@@ -108,6 +109,12 @@ void launch_step_kind(const orlg_env *env, const StepIO &io, int mode, cudaStrea
 template <int JT, bool OBS64>
 void launch_fast(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s) {
     const int blocks = (env->p.n + FAST_THREADS - 1) / FAST_THREADS;
+    if (JT == 1 && !OBS64 && env->hot && mode == MODE_STEP && env->p.traffic == ORLG_TRAFFIC_PHILOX && io.obs && io.reward &&
+        io.done && !io.decision && !io.obs_int) {
+        if (env->p.E == 22) deeprmsa_fast_kernel<22, 5, 1, false, true><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode);
+        else deeprmsa_fast_kernel<0, 5, 1, false, true><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode);
+        return;
+    }
     if (env->p.E == 22) deeprmsa_fast_kernel<22, 5, JT, OBS64><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode);
     else deeprmsa_fast_kernel<0, 5, JT, OBS64><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode);
 }
@@ -314,6 +321,7 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
 
     // ---- fast DeepRMSA kernel: small tables packed for shared-memory staging
     env->fast = false;
+    env->hot = false;
     if (!wide && cfg->kind == ORLG_DEEPRMSA && p.k <= 5 && P <= 65535 && se_max <= 15 && !std::getenv("ORLG_FORCE_GENERIC")) {
         std::vector<unsigned char> blob;
         auto put = [&blob](const void *src, size_t bytes) {
@@ -375,7 +383,19 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
                 if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<22, 5, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
                 if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<0, 5, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
             }
+            if (ea == cudaSuccess && env->fast_smem > 48 * 1024) {
+                ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<22, 5, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
+                if (ea == cudaSuccess) ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<0, 5, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);
+            }
             if (ea != cudaSuccess) env->fast = false;
+            // steady-state specialisation: continuous bit rates below 128 Gb/s whose slot counts all fit the 4-round
+            // shift-AND, exactly KM candidate paths per pair, j = 1, 8-byte candidate cache, even observation width
+            int n_hi = 0;
+            for (int se = 1; se <= se_max; se++)
+                for (int b = 0; b <= cfg->bit_rate_hi && b <= br_max; b++)
+                    n_hi = nslots[(size_t)se * (br_max + 1) + b] > n_hi ? nslots[(size_t)se * (br_max + 1) + b] : n_hi;
+            env->hot = env->fast && J == 1 && p.k == 5 && p.cand_stride == 8 && t->num_bit_rates == 0 && cfg->bit_rate_hi < 128 &&
+                       cfg->bit_rate_lo >= 0 && n_hi <= 16 && (p.obs_dim & 1) == 0 && !std::getenv("ORLG_NO_HOT");
         }
     }
 

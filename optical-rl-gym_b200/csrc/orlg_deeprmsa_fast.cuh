@@ -114,10 +114,19 @@ __device__ unsigned long long g_warp_timeline[2 * 65536];      // per warp: glob
 #define PHASE_INIT() do { } while (0)
 #endif
 
-template <int ET, int KM, int JT, bool OBS64>
+// HOT = the instance for the steady-state rollout step (chosen by the host when it holds): mode == MODE_STEP, Philox
+// traffic with continuous bit rates < 128 Gb/s, every request fits the 4-round shift-AND (n <= 16), k == KM, j == 1,
+// float32 observation + reward + done requested, no decision / integer-observation outputs.  Same code with those
+// conditions as compile-time constants: the reset / trace / generic-feature paths disappear from the instruction stream.
+template <int ET, int KM, int JT, bool OBS64, bool HOT = false>
 __global__ void __launch_bounds__(FAST_THREADS, FAST_MIN_BLOCKS)
-deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
+deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt) {
     extern __shared__ __align__(16) unsigned char smem[];
+    const int mode = HOT ? (int)MODE_STEP : mode_rt;
+    const bool philox = HOT ? true : (p.traffic == ORLG_TRAFFIC_PHILOX);
+    const bool cand8 = HOT ? true : (p.cand_stride == 8);
+    StepIO io = io_rt;
+    if (HOT) { io.decision = nullptr; io.obs_int = nullptr; }
     const int tid = threadIdx.x;
     const int env = blockIdx.x * FAST_THREADS + tid;
     const bool live = env < p.n;
@@ -154,7 +163,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
     // rounds + the two logarithms run while the loads above are still in flight.
     uint32_t rc_[4] = {0u, 0u, 0u, 0u}, rd_[4] = {0u, 0u, 0u, 0u};
     double e_iat = 0.0, e_hold = 0.0;
-    if (p.traffic == ORLG_TRAFFIC_PHILOX && (mode == MODE_STEP || mode == MODE_FULL_RESET)) {
+    if (philox && (mode == MODE_STEP || mode == MODE_FULL_RESET)) {
         const unsigned long long gid = (unsigned long long)(p.env_id_base + e);
         const unsigned r0 = mode == MODE_FULL_RESET ? 0u : p.lockstep_ridx;
         rc_[0] = r0; rc_[2] = (uint32_t)gid; rc_[3] = 0u;
@@ -176,7 +185,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
     unsigned err = p.errors[e];
     const int act = (mode == MODE_STEP) ? io.actions[e] : -1;
     unsigned long long candw = 0;
-    if (p.cand_stride == 8) candw = *reinterpret_cast<const unsigned long long *>(p.cand + (size_t)e * 8);
+    if (cand8) candw = *reinterpret_cast<const unsigned long long *>(p.cand + (size_t)e * 8);
     const Events ev = {p.ev_time + (size_t)e * p.heap_cap, p.ev_pay + (size_t)e * p.heap_cap, p.ev_gmin + (size_t)e * p.ev_groups};
     double tailmin = p.ev_tail[e];
     if (mode == MODE_STEP && hmin <= now + 4.0 * p.mean_iat) prefetch_l2(ev.gmin);     // a release is likely: warm the directory
@@ -224,7 +233,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             if (act >= 0 && act < p.k * J) {
                 const int route = JT == 1 ? act : act / J;
                 if (route < np_a) {
-                    const unsigned st = p.cand_stride == 8 ? (unsigned)((candw >> (8 * act)) & 0xffu)
+                    const unsigned st = cand8 ? (unsigned)((candw >> (8 * act)) & 0xffu)
                                                            : (unsigned)p.cand[(size_t)e * p.cand_stride + act];
                     if (st != CAND_NONE) {
                         if (nheap + 1 > (unsigned)p.heap_cap) {
@@ -232,7 +241,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
                         } else {
                             a_row = first + route;
                             const int se = s_path_se[a_row];
-                            a_n = br < 128 ? s_nslots[se * 128 + br] : p.nslots[se * (p.br_max + 1) + br];
+                            a_n = (HOT || br < 128) ? s_nslots[se * 128 + br] : p.nslots[se * (p.br_max + 1) + br];
                             a_lm = s_path_lm[a_row];
                             a_start = (int)st;
                             const double rel = __dadd_rn(now, hold);
@@ -246,7 +255,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
                     err |= ORLG_ERR_NO_SUCH_PATH;
                 }
             }
-            if (io.reward) io.reward[env] = accepted ? 1.0f : -1.0f;
+            if (HOT || io.reward) io.reward[env] = accepted ? 1.0f : -1.0f;
             if (io.decision) {
                 int *d = io.decision + (size_t)env * 6;
                 d[0] = accepted; d[1] = d_row; d[2] = d_start; d[3] = d_n; d[4] = accepted ? 0 : -1; d[5] = -1;
@@ -262,7 +271,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
         if (mode == MODE_STEP || mode == MODE_FULL_RESET) {
             double arrival, holding;
             int nsrc, ndst, nbr;
-            if (p.traffic == ORLG_TRAFFIC_PHILOX) {
+            if (philox) {
                 const uint32_t *c = rc_, *d = rd_;
                 if (ridx != (mode == MODE_FULL_RESET ? 0u : p.lockstep_ridx)) err |= ORLG_ERR_LOCKSTEP;
                 arrival = __dadd_rn(now, e_iat);
@@ -276,7 +285,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
                 if (tt >= lo) tt += mass;
                 ndst = pick_thr_bsearch(s_node_thr, n, p.node_top_step, (unsigned)tt);
                 if (ndst == nsrc) ndst = (nsrc + 1) % n;
-                if (p.n_bit_rates > 0) nbr = p.bit_rates[pick_thr(p.br_thr, p.n_bit_rates, d[0])];
+                if (!HOT && p.n_bit_rates > 0) nbr = p.bit_rates[pick_thr(p.br_thr, p.n_bit_rates, d[0])];
                 else nbr = p.br_lo + (int)__umulhi(d[0], (unsigned)p.br_span);
             } else if ((long long)ridx < p.trace_len) {
                 const orlg_request r = p.trace[(size_t)e * p.trace_len + ridx];
@@ -328,6 +337,19 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
         if (mode == MODE_EPISODE_RESET || (mode == MODE_STEP && done && p.auto_reset)) {
             cnt[2] = 1; cnt[3] = 0; cnt[6] = br; cnt[7] = 0;      // rmsa_env.py:285-330
         }
+        if (mode != MODE_OBSERVE) {      // ---- store the scalar block (final from here on: frees its registers for phase C)
+            p.now[env] = now;
+            p.cur_hold[env] = hold;
+            p.cur_req[env] = make_uint2((unsigned)src | ((unsigned)dst << 8) | ((unsigned)br << 16), (unsigned)sid);
+#pragma unroll
+            for (int q = 0; q < 8; q++) p.counters[(size_t)q * p.n + env] = cnt[q];
+            p.req_index[env] = ridx;
+            p.nheap[env] = nheap;
+            p.heap_min[env] = hmin;
+            p.ev_tail[env] = tailmin;
+            p.errors[env] = err;
+            if (mode == MODE_STEP && (HOT || io.done)) io.done[env] = done ? 1 : 0;
+        }
         PHASE_MARK(5);               // allocation + release loop (heap pops)
 
         // ============ Phase C, part 1: free-slot mask of every candidate path of the pending request
@@ -345,8 +367,8 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             const bool have = q < npaths;
             const int row = have ? first + q : first;
             const int se = s_path_se[row];
-            ns[q] = s_nslots[se * 128 + min(br, 127)];
-            if (br >= 128) ns[q] = p.nslots[se * (p.br_max + 1) + br];
+            ns[q] = s_nslots[se * 128 + (HOT ? br : min(br, 127))];
+            if (!HOT && br >= 128) ns[q] = p.nslots[se * (p.br_max + 1) + br];
             ll[q] = s_path_ll[row];
             pm[q] = have ? s_path_lm[row] : 0u;
             hops[q] = have ? (int)(ll[q] >> 60) : 0;
@@ -399,7 +421,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
     if (live) {
         // ============ Phase C, part 2: block features (deeprmsa_env.py:60-121)
         const int W = 2 * J + 3;
-        const bool want_obs = io.obs != nullptr;
+        const bool want_obs = HOT ? true : (io.obs != nullptr);
         float *so32 = reinterpret_cast<float *>(stage) + (size_t)lane * p.obs_dim;
         double *so64 = reinterpret_cast<double *>(stage) + (size_t)lane * p.obs_dim;
         if (want_obs) {
@@ -411,7 +433,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             } else {
                 // rows are 8-byte aligned (obs_dim even) or handled element-wise
                 const int head = 1 + 2 * p.N;
-                if (JT == 1 && io.obs_int == nullptr && p.k == KM && (p.obs_dim & 1) == 0) {
+                if (HOT || (JT == 1 && io.obs_int == nullptr && p.k == KM && (p.obs_dim & 1) == 0)) {
                     // every feature entry is written below: only the head (bit rate + one-hots) needs zeros
                     float2 *r2 = reinterpret_cast<float2 *>(so32);
                     for (int q = 0; q < (head + 1) / 2; q++) r2[q] = make_float2(0.0f, 0.0f);
@@ -429,7 +451,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
         int n_max = 0;
 #pragma unroll
         for (int q = 0; q < KM; q++) n_max = max(n_max, ns[q]);
-        const bool flat = JT == 1 && !OBS64 && io.obs_int == nullptr && p.k == KM && n_max <= 16;
+        const bool flat = HOT ? true : (JT == 1 && !OBS64 && io.obs_int == nullptr && p.k == KM && n_max <= 16);
         if (flat) {
             // j = 1, float32: straight-line code, the KM paths are independent instruction streams.
             // With B = positions where a free run of >= n slots starts-or-continues (shift-AND doubling):
@@ -529,7 +551,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             }
         }
         }
-        if (p.cand_stride == 8) {
+        if (cand8) {
             *reinterpret_cast<unsigned long long *>(p.cand + (size_t)env * 8) = cand_out;
         } else {
             for (int q = npaths * J; q < p.k * J; q++) p.cand[(size_t)env * p.cand_stride + q] = (unsigned char)CAND_NONE;
@@ -538,23 +560,10 @@ deeprmsa_fast_kernel(const Params p, const StepIO io, const int mode) {
             for (int q = npaths * W; q < p.k * W; q++) io.obs_int[(size_t)env * p.k * W + q] = -1;
 
         PHASE_MARK(9);                   // block features + observation row
-        if (mode != MODE_OBSERVE) {      // ---- store the scalar block
-            p.now[env] = now;
-            p.cur_hold[env] = hold;
-            p.cur_req[env] = make_uint2((unsigned)src | ((unsigned)dst << 8) | ((unsigned)br << 16), (unsigned)sid);
-#pragma unroll
-            for (int q = 0; q < 8; q++) p.counters[(size_t)q * p.n + env] = cnt[q];
-            p.req_index[env] = ridx;
-            p.nheap[env] = nheap;
-            p.heap_min[env] = hmin;
-            p.ev_tail[env] = tailmin;
-            p.errors[env] = err;
-            if (mode == MODE_STEP && io.done) io.done[env] = done ? 1 : 0;
-        }
     }
 
     PHASE_MARK(10);         // scalar stores
-    if (io.obs != nullptr) {
+    if (HOT || io.obs != nullptr) {
         __syncwarp();
         PHASE_MARK(11);     // (warp-level sync before the tile copy)
         const int row0 = blockIdx.x * FAST_THREADS + wid * 32;          // first env of this warp

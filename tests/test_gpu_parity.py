@@ -416,3 +416,43 @@ def test_heap_overflow_is_flagged_not_silent():
     avail = env.available_slots()
     assert torch.equal((avail == 0), (alloc.reshape(avail.shape) >= 0))      # state stays consistent
     env.close()
+
+
+def test_steady_state_specialisation_matches_oracle_and_generic_instance(monkeypatch):
+    """The HOT instance of the fast kernel (what bench.py and a plain rollout run: Philox traffic, float32
+    observation, no decision output) against the oracle, and bit-for-bit against the general instance."""
+    from optical_rl_gym_b200 import OpticalVecEnv
+    from oracle import oracle
+
+    tables = helpers.golden_tables()
+    n, T, seed = 200, 300, 31
+    kw = dict(traffic="philox", seed=seed, episode_length=45)
+    hot = OpticalVecEnv("DeepRMSA-v0", n, tables, **kw)                      # collect_info on: info counters too
+    monkeypatch.setenv("ORLG_NO_HOT", "1")
+    gen = OpticalVecEnv("DeepRMSA-v0", n, tables, **kw)
+    monkeypatch.delenv("ORLG_NO_HOT")
+    refs = []
+    for i in range(n):
+        o = oracle.OracleEnv("DeepRMSA-v0", tables, num_slots=100, episode_length=45)
+        o.set_philox(seed, i)
+        o.reset(full=True)
+        refs.append((o, o.rollout(T, policy=1, want_obs=True)))
+    assert torch.equal(hot.reset(), gen.reset())
+    for t in range(T):
+        a = hot.sample_actions()
+        assert torch.equal(a, gen.sample_actions())
+        oh, rh_, dh, ih = hot.step(a)
+        og, rg, dg, ig = gen.step(a)
+        assert torch.equal(oh, og) and torch.equal(rh_, rg) and torch.equal(dh, dg), t
+        assert torch.equal(ih.counters, ig.counters), t
+        want_r = np.array([r["rewards"][t] for _, r in refs])
+        assert np.array_equal(rh_.cpu().numpy().astype(np.float64), want_r), ("reward", t)
+        assert np.array_equal(dh.cpu().numpy(), np.array([r["dones"][t] for _, r in refs])), ("done", t)
+        np.testing.assert_allclose(oh.cpu().numpy(), np.stack([r["obs"][t] for _, r in refs]), rtol=OBS_RTOL, atol=0)
+    avail = hot.available_slots().cpu().numpy()
+    cnt = hot.counters().cpu().numpy()
+    for i, (o, _) in enumerate(refs):
+        oa = o.state()[0]
+        assert np.array_equal(avail[i].reshape(oa.shape), oa) and np.array_equal(cnt[i], o.counters()), i
+    assert int(hot.error_flags().abs().sum()) == 0
+    hot.close(); gen.close()
