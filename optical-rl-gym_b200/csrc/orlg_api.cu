@@ -358,6 +358,20 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
         p.off_node_thr = put(node_thr.data(), node_thr.size() * 4);
         p.off_pos = put(pos.data(), pos.size() * 4);
         p.off_nsl = put(nsl.data(), nsl.size() * 4);
+        std::vector<float> rcp4(p.S / 2 + 2, 0.0f);               // 1 / (4 r): at most (S + 1) / 2 free runs on a path
+        for (size_t r = 1; r < rcp4.size(); r++) rcp4[r] = 1.0f / (float)(4 * r);
+        p.off_rcp4 = put(rcp4.data(), rcp4.size() * 4);
+        std::vector<unsigned> dbl(17, 0u);                          // shift-AND doubling: shifts of the 4 rounds for n <= 16
+        for (int nn = 1; nn <= 16; nn++) {
+            int len = 1;
+            for (int it = 0; it < 4; it++) {
+                int sh = len < nn - len ? len : nn - len;
+                if (sh < 0) sh = 0;
+                dbl[nn] |= (unsigned)sh << (8 * it);
+                len += sh;
+            }
+        }
+        p.off_dbl = put(dbl.data(), dbl.size() * 4);
         blob.resize((blob.size() + 15) / 16 * 16);
         if (ll_ok && blob.size() <= 24 * 1024 && blob.size() + (size_t)FAST_THREADS * 16 * 32 <= 100 * 1024) {
             std::vector<uint4> blob4(blob.size() / 16);

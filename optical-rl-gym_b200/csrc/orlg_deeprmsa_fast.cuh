@@ -33,6 +33,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// the same with the four shift amounts of n packed one per byte (table built by the host: orlg_api.cu)
+__device__ __forceinline__ Bits bits_runs_ge_sched(const Bits &a, unsigned sched) {
+    Bits b = a;
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+        b = bits_and(b, bits_shr_small(b, (int)((sched >> (8 * it)) & 0xffu)));
+    }
+    return b;
+}
 __device__ __forceinline__ Bits bits_runs_ge_flat(const Bits &a, int n) {
     // shift-AND doubling without any branch; valid for 1 <= n <= 16 (the caller takes the generic path otherwise)
     Bits b = a;
@@ -45,6 +54,20 @@ __device__ __forceinline__ Bits bits_runs_ge_flat(const Bits &a, int n) {
         len += s;
     }
     return b;
+}
+
+// bits [start, start + n) for 1 <= n <= 32, 0 <= start, start + n <= 128: one 64-bit shift placed at word start / 32
+__device__ __forceinline__ Bits bits_range_short(int start, int n) {
+    const unsigned long long m = ((1ULL << n) - 1ULL) << (start & 31);
+    const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
+    const int ws = start >> 5;
+    Bits r;
+#pragma unroll
+    for (int i = 0; i < NW; i++) r.w[i] = (i == ws) ? lo : ((i == ws + 1) ? hi : 0u);
+    return r;
+}
+__device__ __forceinline__ Bits bits_range_auto(int start, int n) {
+    return (n <= 32) ? bits_range_short(start, n) : bits_range(start, start + n);
 }
 
 // mask of bits >= start (0 <= start <= 128)
@@ -199,6 +222,8 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt) {
     const unsigned *s_node_thr = reinterpret_cast<const unsigned *>(smem + p.off_node_thr);
     const float *s_pos = reinterpret_cast<const float *>(smem + p.off_pos);     // (2v - S) / S
     const float *s_nsl = reinterpret_cast<const float *>(smem + p.off_nsl);     // (2n - 11) / 7, n < 32
+    const float *s_rcp4 = reinterpret_cast<const float *>(smem + p.off_rcp4);   // 1 / (4 r), r <= (S + 1) / 2 free runs
+    const unsigned *s_dbl = reinterpret_cast<const unsigned *>(smem + p.off_dbl);   // shift-AND doubling schedule of n <= 16
 
     PHASE_MARK(0);               // issue of the async copies + scalar loads
     cp_async_wait<1>();          // tables landed (this thread's part) ...
@@ -306,7 +331,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt) {
         PHASE_MARK(4);               // wait for masks
 
         if (accepted) {              // _provision_path: clear [start, start+n) on the path's links
-            const Bits rm = bits_range(a_start, a_start + a_n);
+            const Bits rm = HOT ? bits_range_short(a_start, a_n) : bits_range_auto(a_start, a_n);
             unsigned m = a_lm;
             while (m) {
                 const int l = __ffs(m) - 1;
@@ -321,7 +346,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt) {
             events_release(ev, nheap, hmin, tailmin, now, apply_payload([&](unsigned long long pl) {     // rmsa_env.py:591-597
                 const unsigned lm = s_path_lm[svc_row(pl)];
                 const int rs = svc_start(pl);
-                const Bits rm = bits_range(rs, rs + svc_slots(pl));
+                const Bits rm = HOT ? bits_range_short(rs, svc_slots(pl)) : bits_range_auto(rs, svc_slots(pl));
                 unsigned m = lm;
                 while (m) {
                     const int l = __ffs(m) - 1;
@@ -383,9 +408,8 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt) {
                 const uint4 v = sm[l * 32];
 #pragma unroll
                 for (int q = 0; q < KM; q++) {
-                    const unsigned keep = ((pm[q] >> l) & 1u) - 1u;          // on the path: 0, else all ones
-                    A[q].w[0] &= v.x | keep; A[q].w[1] &= v.y | keep;
-                    A[q].w[2] &= v.z | keep; A[q].w[3] &= v.w | keep;
+                    // predicated AND (LOP3 with a predicate output + 4 predicated LOP3): 5 instructions per (link, path)
+                    if (pm[q] & (1u << l)) { A[q].w[0] &= v.x; A[q].w[1] &= v.y; A[q].w[2] &= v.z; A[q].w[3] &= v.w; }
                 }
             }
         } else {
@@ -460,7 +484,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt) {
 #pragma unroll
             for (int q = 0; q < KM; q++) {
                 const int n = ns[q];
-                const Bits B = bits_runs_ge_flat(A[q], n);
+                const Bits B = bits_runs_ge_sched(A[q], s_dbl[n]);
                 const int st = bits_ffs_flat(B);
                 const int fe = bits_ffs_flat(bits_andnot(B, bits_shr1(B)));
                 const int len = fe - st + n;
@@ -475,7 +499,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt) {
                     so32[ob + 1] = blk ? (float)(len - 8) * 0.125f : -1.0f;
                     so32[ob + 2] = have ? s_nsl[n] : -1.0f;                 // n <= 16 here
                     so32[ob + 3] = have ? s_pos[total] : -1.0f;
-                    so32[ob + 4] = runs > 0 ? __fdividef((float)(total - 4 * runs), (float)(4 * runs)) : -1.0f;   // <= 2 ulp
+                    so32[ob + 4] = runs > 0 ? (float)(total - 4 * runs) * s_rcp4[runs] : -1.0f;   // x * fl(1/y): <= 1.5 ulp
                 }
             }
         } else {
@@ -583,6 +607,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt) {
                     const int nv = total_el >> 2;
                     const float4 *s4 = reinterpret_cast<const float4 *>(s);
                     float4 *g4 = reinterpret_cast<float4 *>(g);
+#pragma unroll 4
                     for (int q = lane; q < nv; q += 32) g4[q] = s4[q];
                     done_el = nv << 2;
                 }
