@@ -588,30 +588,35 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt) {
 
     PHASE_MARK(10);         // scalar stores
     if (HOT || io.obs != nullptr) {
+        // The warp's 32 rows are one contiguous run of the [N, obs_dim] tensor: a single bulk (TMA) store from shared
+        // memory, issued by one lane (generic-proxy writes -> fence.proxy.async by every writer -> warp sync -> store).
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         PHASE_MARK(11);     // (warp-level sync before the tile copy)
         const int row0 = blockIdx.x * FAST_THREADS + wid * 32;          // first env of this warp
         const int rows = min(32, p.n - row0);
         if (rows > 0) {
-            const size_t tile0 = (size_t)row0 * p.obs_dim;
-            const int total_el = rows * p.obs_dim;
-            if (OBS64) {
-                const double *s = reinterpret_cast<const double *>(stage);
-                double *g = reinterpret_cast<double *>(io.obs) + tile0;
-                for (int q = lane; q < total_el; q += 32) g[q] = s[q];
-            } else {
-                const float *s = reinterpret_cast<const float *>(stage);
-                float *g = reinterpret_cast<float *>(io.obs) + tile0;
-                int done_el = 0;
-                if ((reinterpret_cast<size_t>(g) & 15) == 0) {
-                    const int nv = total_el >> 2;
-                    const float4 *s4 = reinterpret_cast<const float4 *>(s);
-                    float4 *g4 = reinterpret_cast<float4 *>(g);
-#pragma unroll 4
-                    for (int q = lane; q < nv; q += 32) g4[q] = s4[q];
-                    done_el = nv << 2;
+            const size_t esz = OBS64 ? 8 : 4;
+            unsigned char *g = reinterpret_cast<unsigned char *>(io.obs) + (size_t)row0 * p.obs_dim * esz;
+            const unsigned bytes = (unsigned)(rows * p.obs_dim * esz);
+            if ((reinterpret_cast<size_t>(g) & 15) == 0 && (bytes & 15u) == 0) {
+                if (lane == 0) {
+                    const unsigned ssrc = (unsigned)__cvta_generic_to_shared(stage);
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(ssrc), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory must outlive the read
                 }
-                for (int q = done_el + lane; q < total_el; q += 32) g[q] = s[q];
+            } else {                 // ragged tail or unaligned view: element loop
+                const int total_el = rows * p.obs_dim;
+                if (OBS64) {
+                    const double *sv = reinterpret_cast<const double *>(stage);
+                    double *gv = reinterpret_cast<double *>(g);
+                    for (int q = lane; q < total_el; q += 32) gv[q] = sv[q];
+                } else {
+                    const float *sv = reinterpret_cast<const float *>(stage);
+                    float *gv = reinterpret_cast<float *>(g);
+                    for (int q = lane; q < total_el; q += 32) gv[q] = sv[q];
+                }
             }
         }
     }
