@@ -33,6 +33,7 @@ struct orlg_env {
     int km;                       // KM template instance (5 or 8)
     bool fast;                    // DeepRMSA fast kernel applicable (NSFNET-class: 22 links, k <= 5)
     bool hot;                     // ... and its steady-state specialisation (deeprmsa_fast_kernel<.., HOT = true>)
+    CUtensorMap mask_map;         // TMA view of the mask tensor: [C*E rows][n x 16 bytes], box = E rows x 512 bytes
     bool wide;                    // beyond 32 links / 128 slots / 8 paths: CSR link lists, multi-word masks
     size_t fast_smem;
     size_t obs_smem;
@@ -98,6 +99,26 @@ double reach_km(double osnr, double inband_xt_raw, int se, int bit_rate, double 
     return lmax_snr < lmax_xt ? lmax_snr : lmax_xt;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency)
+bool encode_mask_map(orlg_env *env) {
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess)
+        return false;
+    const Params &p = env->p;
+    const cuuint64_t gdim[2] = {(cuuint64_t)p.n * 4, (cuuint64_t)p.C * p.E};        // uint32 elements per row, rows
+    const cuuint64_t gstride[1] = {(cuuint64_t)p.n * 16};                           // bytes between rows
+    const cuuint32_t box[2] = {128, (cuuint32_t)p.E};                               // 32 envs x 16 B, all links
+    const cuuint32_t estr[2] = {1, 1};
+    return reinterpret_cast<encode_fn>(fn)(&env->mask_map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, p.masks, gdim, gstride, box, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int KIND>
 void launch_step_kind(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s) {
     const int blocks = (env->p.n + STEP_THREADS - 1) / STEP_THREADS;
@@ -111,12 +132,12 @@ void launch_fast(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s
     const int blocks = (env->p.n + FAST_THREADS - 1) / FAST_THREADS;
     if (JT == 1 && !OBS64 && env->hot && mode == MODE_STEP && env->p.traffic == ORLG_TRAFFIC_PHILOX && io.obs && io.reward &&
         io.done && !io.decision && !io.obs_int) {
-        if (env->p.E == 22) deeprmsa_fast_kernel<22, 5, 1, false, true><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode);
-        else deeprmsa_fast_kernel<0, 5, 1, false, true><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode);
+        if (env->p.E == 22) deeprmsa_fast_kernel<22, 5, 1, false, true><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode, env->mask_map);
+        else deeprmsa_fast_kernel<0, 5, 1, false, true><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode, env->mask_map);
         return;
     }
-    if (env->p.E == 22) deeprmsa_fast_kernel<22, 5, JT, OBS64><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode);
-    else deeprmsa_fast_kernel<0, 5, JT, OBS64><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode);
+    if (env->p.E == 22) deeprmsa_fast_kernel<22, 5, JT, OBS64><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode, env->mask_map);
+    else deeprmsa_fast_kernel<0, 5, JT, OBS64><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode, env->mask_map);
 }
 
 template <int KIND>
@@ -372,7 +393,7 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
             }
         }
         p.off_dbl = put(dbl.data(), dbl.size() * 4);
-        blob.resize((blob.size() + 15) / 16 * 16);
+        blob.resize((blob.size() + 127) / 128 * 128);          // the warp areas behind it are TMA destinations (128-byte aligned)
         if (ll_ok && blob.size() <= 24 * 1024 && blob.size() + (size_t)FAST_THREADS * 16 * 32 <= 100 * 1024) {
             std::vector<uint4> blob4(blob.size() / 16);
             std::memcpy(blob4.data(), blob.data(), blob.size());
@@ -383,7 +404,7 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
             size_t per_thread = (size_t)p.obs_dim * (p.obs_f64 ? 8 : 4);      // observation tile overlays the mask area
             if (per_thread < (size_t)p.E * 16) per_thread = (size_t)p.E * 16;
             p.warp_area_bytes = (int)((per_thread * 32 + 127) / 128 * 128);
-            env->fast_smem = blob.size() + (size_t)(FAST_THREADS / 32) * p.warp_area_bytes;
+            env->fast_smem = blob.size() + (size_t)(FAST_THREADS / 32) * p.warp_area_bytes + 8 * (FAST_THREADS / 32);   // + per-warp mbarriers
             p.node_top_step = 1;
             while (p.node_top_step * 2 <= p.N - 1) p.node_top_step *= 2;
             cudaError_t ea = cudaSuccess;
@@ -409,7 +430,8 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
                 for (int b = 0; b <= cfg->bit_rate_hi && b <= br_max; b++)
                     n_hi = nslots[(size_t)se * (br_max + 1) + b] > n_hi ? nslots[(size_t)se * (br_max + 1) + b] : n_hi;
             env->hot = env->fast && J == 1 && p.k == 5 && p.cand_stride == 8 && t->num_bit_rates == 0 && cfg->bit_rate_hi < 128 &&
-                       cfg->bit_rate_lo >= 0 && n_hi <= 16 && (p.obs_dim & 1) == 0 && !std::getenv("ORLG_NO_HOT");
+                       cfg->bit_rate_lo >= 0 && n_hi <= 16 && (p.obs_dim & 1) == 0 && p.E <= 256 && !std::getenv("ORLG_NO_HOT");
+            if (env->hot && !encode_mask_map(env)) env->hot = false;
         }
     }
 

@@ -12,6 +12,7 @@
 //   * the observation tile of the CTA overlays the mask area once the masks are dead and is written
 //     to HBM with full-line stores.
 #pragma once
+#include <cuda.h>          // CUtensorMap (type only: the encoder is fetched with cudaGetDriverEntryPoint)
 #include "orlg_kernels.cuh"
 
 namespace orlg {
@@ -141,9 +142,33 @@ __device__ unsigned long long g_warp_timeline[2 * 65536];      // per warp: glob
 // traffic with continuous bit rates < 128 Gb/s, every request fits the 4-round shift-AND (n <= 16), k == KM, j == 1,
 // float32 observation + reward + done requested, no decision / integer-observation outputs.  Same code with those
 // conditions as compile-time constants: the reset / trace / generic-feature paths disappear from the instruction stream.
+// ---- TMA: the warp's [E links] x [32 envs x 16 B] tile of the mask tensor arrives with ONE cp.async.bulk.tensor.2d,
+// completion on a per-warp mbarrier (HOT instance; the general instance keeps per-thread cp.async)
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok = 0, spins = 0;
+    while (!ok) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 22)) asm volatile("trap;");      // a copy that never lands must fail loudly, not hang
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, int x, int y, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(tmap), "r"(x), "r"(y),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
 template <int ET, int KM, int JT, bool OBS64, bool HOT = false>
 __global__ void __launch_bounds__(FAST_THREADS, FAST_MIN_BLOCKS)
-deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt) {
+deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt, const __grid_constant__ CUtensorMap mask_map) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int mode = HOT ? (int)MODE_STEP : mode_rt;
     const bool philox = HOT ? true : (p.traffic == ORLG_TRAFFIC_PHILOX);
@@ -162,6 +187,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt) {
     const int lane = tid & 31, wid = tid >> 5;
     unsigned char *warp_area = smem + p.tab_vec * 16 + (size_t)wid * p.warp_area_bytes;
     uint4 *sm = reinterpret_cast<uint4 *>(warp_area) + lane;                   // this thread's masks: sm[l * 32]
+    unsigned long long *mask_bar = reinterpret_cast<unsigned long long *>(smem + p.tab_vec * 16 + (size_t)(FAST_THREADS / 32) * p.warp_area_bytes) + wid;
     PHASE_INIT();
 
     // ---------------- stage 0: asynchronous copies (group 0 = tables, group 1 = this env's link masks)
@@ -169,7 +195,13 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt) {
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         for (int i = tid; i < p.tab_vec; i += FAST_THREADS) cp_async16(dst + i, p.tab_blob + i);
         cp_async_commit();
-        if (mode != MODE_FULL_RESET) {
+        if (HOT) {
+            if (lane == 0) {
+                mbar_init(mask_bar, 1);
+                mbar_expect_tx(mask_bar, (unsigned)(E * 32 * 16));
+                tma_load_2d(warp_area, &mask_map, (blockIdx.x * FAST_THREADS + wid * 32) * 4, 0, mask_bar);
+            }
+        } else if (mode != MODE_FULL_RESET) {
             const uint4 *mr = p.masks + e;
             unsigned sdst = (unsigned)__cvta_generic_to_shared(sm);
             for (int l = 0; l < E; l++) {
@@ -327,7 +359,8 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt) {
         }
 
         PHASE_MARK(3);               // phase B: traffic draw
-        cp_async_wait<0>();          // this thread's masks are in shared memory
+        if (HOT) mbar_wait(mask_bar, 0);       // the warp's tile has landed (TMA)
+        else cp_async_wait<0>();               // this thread's masks are in shared memory
         PHASE_MARK(4);               // wait for masks
 
         if (accepted) {              // _provision_path: clear [start, start+n) on the path's links
