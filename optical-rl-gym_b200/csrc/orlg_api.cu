@@ -404,7 +404,7 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
             size_t per_thread = (size_t)p.obs_dim * (p.obs_f64 ? 8 : 4);      // observation tile overlays the mask area
             if (per_thread < (size_t)p.E * 16) per_thread = (size_t)p.E * 16;
             p.warp_area_bytes = (int)((per_thread * 32 + 127) / 128 * 128);
-            env->fast_smem = blob.size() + (size_t)(FAST_THREADS / 32) * p.warp_area_bytes + 8 * (FAST_THREADS / 32);   // + per-warp mbarriers
+            env->fast_smem = blob.size() + (size_t)(FAST_THREADS / 32) * p.warp_area_bytes + 8 * (FAST_THREADS / 32 + 1);   // + per-warp mbarriers + the table barrier
             p.node_top_step = 1;
             while (p.node_top_step * 2 <= p.N - 1) p.node_top_step *= 2;
             cudaError_t ea = cudaSuccess;

@@ -188,12 +188,23 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt, cons
     unsigned char *warp_area = smem + p.tab_vec * 16 + (size_t)wid * p.warp_area_bytes;
     uint4 *sm = reinterpret_cast<uint4 *>(warp_area) + lane;                   // this thread's masks: sm[l * 32]
     unsigned long long *mask_bar = reinterpret_cast<unsigned long long *>(smem + p.tab_vec * 16 + (size_t)(FAST_THREADS / 32) * p.warp_area_bytes) + wid;
+    unsigned long long *tab_bar = reinterpret_cast<unsigned long long *>(smem + p.tab_vec * 16 + (size_t)(FAST_THREADS / 32) * p.warp_area_bytes) + FAST_THREADS / 32;
     PHASE_INIT();
 
     // ---------------- stage 0: asynchronous copies (group 0 = tables, group 1 = this env's link masks)
     {
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
-        for (int i = tid; i < p.tab_vec; i += FAST_THREADS) cp_async16(dst + i, p.tab_blob + i);
+        if (HOT) {                   // one bulk copy for the whole table blob, completion on the CTA's mbarrier
+            if (tid == 0) {
+                mbar_init(tab_bar, 1);
+                mbar_expect_tx(tab_bar, (unsigned)p.tab_vec * 16u);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(p.tab_blob), "r"((unsigned)p.tab_vec * 16u),
+                               "r"((unsigned)__cvta_generic_to_shared(tab_bar)) : "memory");
+            }
+        } else {
+            for (int i = tid; i < p.tab_vec; i += FAST_THREADS) cp_async16(dst + i, p.tab_blob + i);
+        }
         cp_async_commit();
         if (HOT) {
             if (lane == 0) {
@@ -258,8 +269,13 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt, cons
     const unsigned *s_dbl = reinterpret_cast<const unsigned *>(smem + p.off_dbl);   // shift-AND doubling schedule of n <= 16
 
     PHASE_MARK(0);               // issue of the async copies + scalar loads
-    cp_async_wait<1>();          // tables landed (this thread's part) ...
-    __syncthreads();             // ... and everybody else's
+    if (HOT) {
+        __syncthreads();         // the barrier initialised by thread 0 is visible ...
+        mbar_wait(tab_bar, 0);   // ... and the tables have landed
+    } else {
+        cp_async_wait<1>();      // tables landed (this thread's part) ...
+        __syncthreads();         // ... and everybody else's
+    }
     PHASE_MARK(1);               // wait for tables (first round trip)
 
     int src = rq.x & 0xff, dst = (rq.x >> 8) & 0xff, br = (int)(rq.x >> 16), sid = (int)rq.y;
@@ -372,6 +388,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt, cons
                 uint4 v = sm[l * 32];
                 v.x &= ~rm.w[0]; v.y &= ~rm.w[1]; v.z &= ~rm.w[2]; v.w &= ~rm.w[3];
                 sm[l * 32] = v;
+                if (HOT) p.masks[(size_t)l * p.n + env] = v;       // write-through: no dirty-link pass later
             }
             dirty |= a_lm;
         }
@@ -387,6 +404,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt, cons
                     uint4 v = sm[l * 32];
                     v.x |= rm.w[0]; v.y |= rm.w[1]; v.z |= rm.w[2]; v.w |= rm.w[3];
                     sm[l * 32] = v;
+                    if (HOT) p.masks[(size_t)l * p.n + env] = v;
                 }
                 dirty |= lm;
             }));
@@ -459,7 +477,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt, cons
             }
         }
         PHASE_MARK(6);               // candidate-path AND
-        {   // write back the links this step touched
+        if (!HOT) {   // write back the links this step touched
             uint4 *mw = p.masks + env;
             unsigned m = dirty;
             while (m) {
