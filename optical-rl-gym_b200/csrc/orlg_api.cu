@@ -127,13 +127,31 @@ void launch_step_kind(const orlg_env *env, const StepIO &io, int mode, cudaStrea
     else step_kernel<KIND, KMAX><<<blocks, STEP_THREADS, smem, s>>>(env->p, io, mode);
 }
 
+// launch configuration with the programmatic-stream-serialization attribute (griddepcontrol in the kernels)
+cudaLaunchAttribute g_pdl_attr[1];
+cudaLaunchConfig_t pdl_config(int blocks, int threads, size_t smem, cudaStream_t s) {
+    static const bool off = std::getenv("ORLG_NO_PDL") != nullptr;
+    g_pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    g_pdl_attr[0].val.programmaticStreamSerializationAllowed = off ? 0 : 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cfg.attrs = g_pdl_attr;
+    cfg.numAttrs = 1;
+    return cfg;
+}
+
 template <int JT, bool OBS64>
 void launch_fast(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s) {
     const int blocks = (env->p.n + FAST_THREADS - 1) / FAST_THREADS;
     if (JT == 1 && !OBS64 && env->hot && mode == MODE_STEP && env->p.traffic == ORLG_TRAFFIC_PHILOX && io.obs && io.reward &&
         io.done && !io.decision && !io.obs_int) {
-        if (env->p.E == 22) deeprmsa_fast_kernel<22, 5, 1, false, true><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode, env->mask_map);
-        else deeprmsa_fast_kernel<0, 5, 1, false, true><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode, env->mask_map);
+        // programmatic dependent launch: the prologue overlaps the tail of the preceding kernel of the stream
+        cudaLaunchConfig_t cfg = pdl_config(blocks, FAST_THREADS, env->fast_smem, s);
+        if (env->p.E == 22) cudaLaunchKernelEx(&cfg, deeprmsa_fast_kernel<22, 5, 1, false, true>, env->p, io, mode, env->mask_map);
+        else cudaLaunchKernelEx(&cfg, deeprmsa_fast_kernel<0, 5, 1, false, true>, env->p, io, mode, env->mask_map);
         return;
     }
     if (env->p.E == 22) deeprmsa_fast_kernel<22, 5, JT, OBS64><<<blocks, FAST_THREADS, env->fast_smem, s>>>(env->p, io, mode, env->mask_map);
@@ -550,8 +568,9 @@ int orlg_heuristic(orlg_env *env, int which, int32_t *actions_dev, orlg_stream s
 int orlg_random_actions(orlg_env *env, int32_t *actions_dev, orlg_stream stream) {
     if (!env || !actions_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
     const int threads = 256, blocks = (env->p.n + threads - 1) / threads;
-    random_action_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->p, actions_dev);
-    CUDA_OK(cudaGetLastError());
+    cudaLaunchConfig_t cfg = pdl_config(blocks, threads, 0, (cudaStream_t)stream);
+    int *actions = actions_dev;
+    CUDA_OK(cudaLaunchKernelEx(&cfg, random_action_kernel, env->p, actions));
     return ORLG_OK;
 }
 

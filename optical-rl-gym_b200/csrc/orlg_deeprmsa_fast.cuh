@@ -188,6 +188,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt, cons
     unsigned char *warp_area = smem + p.tab_vec * 16 + (size_t)wid * p.warp_area_bytes;
     uint4 *sm = reinterpret_cast<uint4 *>(warp_area) + lane;                   // this thread's masks: sm[l * 32]
     unsigned long long *mask_bar = reinterpret_cast<unsigned long long *>(smem + p.tab_vec * 16 + (size_t)(FAST_THREADS / 32) * p.warp_area_bytes) + wid;
+    if (HOT) pdl_launch_dependents();      // the next kernel in the stream may be scheduled as soon as SMs drain
     unsigned long long *tab_bar = reinterpret_cast<unsigned long long *>(smem + p.tab_vec * 16 + (size_t)(FAST_THREADS / 32) * p.warp_area_bytes) + FAST_THREADS / 32;
     PHASE_INIT();
 
@@ -207,11 +208,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt, cons
         }
         cp_async_commit();
         if (HOT) {
-            if (lane == 0) {
-                mbar_init(mask_bar, 1);
-                mbar_expect_tx(mask_bar, (unsigned)(E * 32 * 16));
-                tma_load_2d(warp_area, &mask_map, (blockIdx.x * FAST_THREADS + wid * 32) * 4, 0, mask_bar);
-            }
+            if (lane == 0) mbar_init(mask_bar, 1);      // the tile itself is requested after the dependency wait below
         } else if (mode != MODE_FULL_RESET) {
             const uint4 *mr = p.masks + e;
             unsigned sdst = (unsigned)__cvta_generic_to_shared(sm);
@@ -238,6 +235,15 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt, cons
         philox4x32_10(rd_, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
         e_iat = __dmul_rn(neg_log_u32(rc_[0]), p.mean_iat);
         e_hold = __dmul_rn(neg_log_u32(rc_[1]), p.mean_holding);
+    }
+    if (HOT) {
+        // Everything above is independent of the previous kernels in the stream (tables, Philox, logarithms): with a
+        // programmatic dependent launch it runs while they drain.  State and actions are only touched from here on.
+        pdl_wait();
+        if (lane == 0) {
+            mbar_expect_tx(mask_bar, (unsigned)(E * 32 * 16));
+            tma_load_2d(warp_area, &mask_map, (blockIdx.x * FAST_THREADS + wid * 32) * 4, 0, mask_bar);
+        }
     }
     double now = p.now[e];
     double hold = p.cur_hold[e];

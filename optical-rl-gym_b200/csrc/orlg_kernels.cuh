@@ -719,7 +719,15 @@ __global__ void heuristic_kernel(const Params p, const int which, int *actions) 
 }
 
 // uniform random policy: Philox stream 2, counter = requests generated so far (DESIGN.md "Traffic")
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream drains; it must not touch the predecessor's outputs before
+// pdl_wait().  Both are no-ops for an ordinary launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __global__ void random_action_kernel(const Params p, int *actions) {
+    pdl_launch_dependents();
+    pdl_wait();                      // req_index is written by the preceding step kernel
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.n) return;
     unsigned long long gid = (unsigned long long)(p.env_id_base + env);
