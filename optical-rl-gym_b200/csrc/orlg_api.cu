@@ -128,9 +128,9 @@ void launch_step_kind(const orlg_env *env, const StepIO &io, int mode, cudaStrea
 }
 
 // launch configuration with the programmatic-stream-serialization attribute (griddepcontrol in the kernels)
-cudaLaunchAttribute g_pdl_attr[1];
 cudaLaunchConfig_t pdl_config(int blocks, int threads, size_t smem, cudaStream_t s) {
     static const bool off = std::getenv("ORLG_NO_PDL") != nullptr;
+    static thread_local cudaLaunchAttribute g_pdl_attr[1];          // one host thread per handle (orlg.h)
     g_pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     g_pdl_attr[0].val.programmaticStreamSerializationAllowed = off ? 0 : 1;
     cudaLaunchConfig_t cfg = {};

@@ -306,6 +306,7 @@ def get_topology(file_name, topology_name: Optional[str] = None, modulations=DEF
     name = topology_name or os.path.splitext(os.path.basename(file_name))[0]
     cache = None
     if cache_dir:
+        cache_dir = os.path.expanduser(str(cache_dir))
         with open(file_name, "rb") as fh:
             key = hashlib.sha256(fh.read() + repr((k_paths, tuple(modulations or ()))).encode()).hexdigest()[:16]
         cache = os.path.join(cache_dir, "%s_k%d_%s.npz" % (name, k_paths, key))
