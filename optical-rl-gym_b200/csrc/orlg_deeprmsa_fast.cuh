@@ -220,6 +220,18 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt, cons
         }
         cp_async_commit();
     }
+    const unsigned short *s_pair_first = reinterpret_cast<const unsigned short *>(smem + p.off_pair_first);
+    const unsigned char *s_pair_count = smem + p.off_pair_count;
+    const unsigned *s_path_lm = reinterpret_cast<const unsigned *>(smem + p.off_path_lm);
+    const unsigned char *s_path_se = smem + p.off_path_se;
+    const unsigned long long *s_path_ll = reinterpret_cast<const unsigned long long *>(smem + p.off_path_ll);   // packed hop lists
+    const unsigned char *s_nslots = smem + p.off_nslots;              // [se][128]
+    const unsigned *s_node_thr = reinterpret_cast<const unsigned *>(smem + p.off_node_thr);
+    const float *s_pos = reinterpret_cast<const float *>(smem + p.off_pos);     // (2v - S) / S
+    const float *s_nsl = reinterpret_cast<const float *>(smem + p.off_nsl);     // (2n - 11) / 7, n < 32
+    const float *s_rcp4 = reinterpret_cast<const float *>(smem + p.off_rcp4);   // 1 / (4 r), r <= (S + 1) / 2 free runs
+    const unsigned *s_dbl = reinterpret_cast<const unsigned *>(smem + p.off_dbl);   // shift-AND doubling schedule of n <= 16
+
     // ---------------- stage 1: the scalar block
     // The traffic draw of _next_service needs only (seed, global env id, request index).  All envs of a
     // handle are reset and stepped together, so the request index is a launch parameter and the Philox
@@ -236,9 +248,41 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt, cons
         e_iat = __dmul_rn(neg_log_u32(rc_[0]), p.mean_iat);
         e_hold = __dmul_rn(neg_log_u32(rc_[1]), p.mean_holding);
     }
+    // HOT: the rest of the draw (source, destination, bit rate) and the candidate-path tables of the NEXT request
+    // also depend on nothing but the tables and the Philox words: done here, ahead of the dependency wait.
+    int p_src = 0, p_dst = 1, p_br = 0, p_first = 0, p_npaths = 0;
+    unsigned p_pm[KM];
+    int p_ns[KM];
+#pragma unroll
+    for (int q = 0; q < KM; q++) { p_pm[q] = 0u; p_ns[q] = 1; }
     if (HOT) {
-        // Everything above is independent of the previous kernels in the stream (tables, Philox, logarithms): with a
-        // programmatic dependent launch it runs while they drain.  State and actions are only touched from here on.
+        __syncthreads();             // the table barrier initialised by thread 0 is visible ...
+        mbar_wait(tab_bar, 0);       // ... and the tables have landed
+        const int n = p.N;
+        p_src = pick_thr_bsearch(s_node_thr, n, p.node_top_step, rc_[2]);
+        const unsigned lo = p_src ? s_node_thr[p_src - 1] : 0u;
+        const unsigned long long hi = (p_src == n - 1) ? 4294967296ULL : (unsigned long long)s_node_thr[p_src];
+        const unsigned long long mass = hi - lo;
+        unsigned long long tt = ((unsigned long long)rc_[3] * (4294967296ULL - mass)) >> 32;
+        if (tt >= lo) tt += mass;
+        p_dst = pick_thr_bsearch(s_node_thr, n, p.node_top_step, (unsigned)tt);
+        if (p_dst == p_src) p_dst = (p_src + 1) % n;
+        p_br = p.br_lo + (int)__umulhi(rd_[0], (unsigned)p.br_span);
+        const int pair = p_src * p.N + p_dst;
+        p_first = s_pair_first[pair];
+        p_npaths = min((int)s_pair_count[pair], KM);
+#pragma unroll
+        for (int q = 0; q < KM; q++) {
+            const bool have = q < p_npaths;
+            const int row = have ? p_first + q : p_first;
+            p_ns[q] = s_nslots[s_path_se[row] * 128 + p_br];
+            p_pm[q] = have ? s_path_lm[row] : 0u;
+        }
+    }
+    if (HOT) {
+        // Everything above is independent of the previous kernels in the stream (tables, Philox, logarithms, the
+        // next request): with a programmatic dependent launch it runs while they drain.  State and actions are only
+        // touched from here on.
         pdl_wait();
         if (lane == 0) {
             mbar_expect_tx(mask_bar, (unsigned)(E * 32 * 16));
@@ -262,23 +306,8 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt, cons
     double tailmin = p.ev_tail[e];
     if (mode == MODE_STEP && hmin <= now + 4.0 * p.mean_iat) prefetch_l2(ev.gmin);     // a release is likely: warm the directory
 
-    const unsigned short *s_pair_first = reinterpret_cast<const unsigned short *>(smem + p.off_pair_first);
-    const unsigned char *s_pair_count = smem + p.off_pair_count;
-    const unsigned *s_path_lm = reinterpret_cast<const unsigned *>(smem + p.off_path_lm);
-    const unsigned char *s_path_se = smem + p.off_path_se;
-    const unsigned long long *s_path_ll = reinterpret_cast<const unsigned long long *>(smem + p.off_path_ll);   // packed hop lists
-    const unsigned char *s_nslots = smem + p.off_nslots;              // [se][128]
-    const unsigned *s_node_thr = reinterpret_cast<const unsigned *>(smem + p.off_node_thr);
-    const float *s_pos = reinterpret_cast<const float *>(smem + p.off_pos);     // (2v - S) / S
-    const float *s_nsl = reinterpret_cast<const float *>(smem + p.off_nsl);     // (2n - 11) / 7, n < 32
-    const float *s_rcp4 = reinterpret_cast<const float *>(smem + p.off_rcp4);   // 1 / (4 r), r <= (S + 1) / 2 free runs
-    const unsigned *s_dbl = reinterpret_cast<const unsigned *>(smem + p.off_dbl);   // shift-AND doubling schedule of n <= 16
-
     PHASE_MARK(0);               // issue of the async copies + scalar loads
-    if (HOT) {
-        __syncthreads();         // the barrier initialised by thread 0 is visible ...
-        mbar_wait(tab_bar, 0);   // ... and the tables have landed
-    } else {
+    if (!HOT) {                  // (HOT waited for its tables in the prologue)
         cp_async_wait<1>();      // tables landed (this thread's part) ...
         __syncthreads();         // ... and everybody else's
     }
@@ -350,7 +379,12 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt, cons
         if (mode == MODE_STEP || mode == MODE_FULL_RESET) {
             double arrival, holding;
             int nsrc, ndst, nbr;
-            if (philox) {
+            if (HOT) {
+                if (ridx != p.lockstep_ridx) err |= ORLG_ERR_LOCKSTEP;
+                arrival = __dadd_rn(now, e_iat);
+                holding = e_hold;
+                nsrc = p_src; ndst = p_dst; nbr = p_br;
+            } else if (philox) {
                 const uint32_t *c = rc_, *d = rd_;
                 if (ridx != (mode == MODE_FULL_RESET ? 0u : p.lockstep_ridx)) err |= ORLG_ERR_LOCKSTEP;
                 arrival = __dadd_rn(now, e_iat);
@@ -437,7 +471,7 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt, cons
         // ============ Phase C, part 1: free-slot mask of every candidate path of the pending request
         const int pair = src * p.N + dst;
         const int first = s_pair_first[pair];
-        npaths = min((int)s_pair_count[pair], KM);
+        npaths = HOT ? p_npaths : min((int)s_pair_count[pair], KM);
         // get_available_slots (rmsa_env.py:638-649): every candidate path walks its packed hop list
         // (5 bits per link, hop count in the top 4 bits); the KM paths advance in lockstep so that the
         // LDS -> AND chains of different paths overlap.
@@ -448,11 +482,16 @@ deeprmsa_fast_kernel(const Params p, const StepIO io_rt, const int mode_rt, cons
         for (int q = 0; q < KM; q++) {
             const bool have = q < npaths;
             const int row = have ? first + q : first;
-            const int se = s_path_se[row];
-            ns[q] = s_nslots[se * 128 + (HOT ? br : min(br, 127))];
-            if (!HOT && br >= 128) ns[q] = p.nslots[se * (p.br_max + 1) + br];
+            if (HOT) {
+                ns[q] = p_ns[q];
+                pm[q] = p_pm[q];
+            } else {
+                const int se = s_path_se[row];
+                ns[q] = s_nslots[se * 128 + min(br, 127)];
+                if (br >= 128) ns[q] = p.nslots[se * (p.br_max + 1) + br];
+                pm[q] = have ? s_path_lm[row] : 0u;
+            }
             ll[q] = s_path_ll[row];
-            pm[q] = have ? s_path_lm[row] : 0u;
             hops[q] = have ? (int)(ll[q] >> 60) : 0;
             mh = max(mh, hops[q]);
             A[q] = have ? bits_ones() : Bits{{0u, 0u, 0u, 0u}};
