@@ -127,6 +127,7 @@ class OpticalVecEnv:
         t = self.tables
         self.num_envs = int(num_envs)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.metadata = {"metrics": METRICS[env_id]}
         self.k_paths = t.k_paths
         self.num_spectrum_resources = int(a["num_spectrum_resources"])
@@ -226,6 +227,7 @@ class OpticalVecEnv:
         self._done = torch.zeros(n, dtype=torch.uint8, device=dev)
         self._info = torch.zeros((n, 8), dtype=torch.int64, device=dev) if collect_info else None
         self._decision = torch.zeros((n, 6), dtype=torch.int32, device=dev) if record_decisions else None
+        self._out_ptrs = (_ptr(self._obs), _ptr(self._reward), _ptr(self._done), _ptr(self._decision), _ptr(self._info))
         self._actions = None
         self._trace = None
         # float statistics of info (network / link compactness, utilisation): opt-in, uses the generic kernel
@@ -243,7 +245,12 @@ class OpticalVecEnv:
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        # raw handle of torch's current stream on this device (the private accessor is several times cheaper than
+        # building a Stream object per call; the rollout loop issues two launches per ~20 us)
+        try:
+            return C.c_void_p(torch._C._cuda_getCurrentRawStream(self._dev_index))
+        except AttributeError:      # pragma: no cover - older / newer torch without the accessor
+            return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def close(self):
         if not getattr(self, "_closed", True) and self._h:
@@ -318,8 +325,9 @@ class OpticalVecEnv:
 
     def step_raw(self, actions_i32: torch.Tensor):
         """Hot-loop variant: ``actions_i32`` must already be a contiguous int32 CUDA tensor ``[N, action_dim]``."""
-        nat.check(self._lib.orlg_step(self._h, _ptr(actions_i32), _ptr(self._obs), _ptr(self._reward), _ptr(self._done),
-                                      _ptr(self._decision), _ptr(self._info), self._stream()))
+        rc = self._lib.orlg_step(self._h, C.c_void_p(actions_i32.data_ptr()), *self._out_ptrs, self._stream())
+        if rc:
+            nat.check(rc)
         return self._obs, self._reward, self._done
 
     def observation(self):
@@ -363,7 +371,9 @@ class OpticalVecEnv:
         """Uniform random policy (``action_space.sample()`` per env) from Philox stream 2."""
         if out is None:
             out = torch.empty((self.num_envs, self.action_dim), dtype=torch.int32, device=self.device)
-        nat.check(self._lib.orlg_random_actions(self._h, _ptr(out), self._stream()))
+        rc = self._lib.orlg_random_actions(self._h, C.c_void_p(out.data_ptr()), self._stream())
+        if rc:
+            nat.check(rc)
         return out
 
     # ------------------------------------------------------------------ introspection
