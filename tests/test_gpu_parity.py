@@ -461,40 +461,49 @@ def test_steady_state_specialisation_matches_oracle_and_generic_instance(monkeyp
 def test_interleaved_handles_and_side_streams_keep_stream_order():
     """The rollout kernels are launched with the programmatic-stream-serialization attribute (their prologue may run
     under the previous kernel's tail).  Whatever precedes them in the stream -- another handle's kernels, torch
-    kernels, copies -- and whichever stream is current, results must equal a plain one-handle run."""
+    kernels -- and whichever stream is current, results must equal a plain one-handle-at-a-time run."""
     from optical_rl_gym_b200 import OpticalVecEnv
 
     tables = helpers.golden_tables()
     kw = dict(traffic="philox", episode_length=30)
-    ref = [OpticalVecEnv("DeepRMSA-v0", 96, tables, seed=s, **kw) for s in (1, 2)]
-    out_ref = [[], []]
-    for t in range(120):
-        for i, e in enumerate(ref):
-            o, r, d, _ = e.step(e.sample_actions())
-            out_ref[i].append((o.clone(), r.clone(), d.clone()))
+    T = 120
+
+    def snap(out):
+        return tuple(x.clone() for x in out[:3])
+
+    # reference: each handle alone, synchronised after every step; handle 0 takes one extra step whenever t % 7 == 0
+    want = [[], []]
+    for i, seed in enumerate((1, 2)):
+        e = OpticalVecEnv("DeepRMSA-v0", 96, tables, seed=seed, **kw)
+        for t in range(T):
+            want[i].append(snap(e.step(e.sample_actions())))
+            torch.cuda.synchronize()
+            if i == 0 and t % 7 == 0:
+                want[i].append(snap(e.step(e.sample_actions())))
+                torch.cuda.synchronize()
+        assert int(e.error_flags().abs().sum()) == 0
+        e.close()
     a, b = [OpticalVecEnv("DeepRMSA-v0", 96, tables, seed=s, **kw) for s in (1, 2)]
     side = torch.cuda.Stream()
     junk = torch.zeros(1 << 20, device="cuda")
-    for t in range(120):
+    got = [[], []]
+    for t in range(T):
         aa = a.sample_actions()
         ab = b.sample_actions()                     # b's action kernel directly behind a's
-        oa, ra, da, _ = a.step(aa)
+        got[0].append(snap(a.step(aa)))
         junk.add_(1.0)                              # a torch kernel between the two step kernels
-        ob, rb, db, _ = b.step(ab)
-        got = ((oa, ra, da), (ob, rb, db))
-        for i in range(2):
-            for x, y in zip(got[i], out_ref[i][t]):
-                assert torch.equal(x, y), (t, i)
-        if t % 7 == 0:                              # switch the current stream: order is per stream, so hand over with events
+        got[1].append(snap(b.step(ab)))
+        if t % 7 == 0:                              # another current stream: order is per stream, hand over with events
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                aa = a.sample_actions()
-                oa, ra, da, _ = a.step(aa)
-                keep = (oa.clone(), ra.clone(), da.clone())
+                got[0].append(snap(a.step(a.sample_actions())))
             torch.cuda.current_stream().wait_stream(side)
-            o, r, d, _ = ref[0].step(ref[0].sample_actions())
-            for x, y in zip(keep, (o, r, d)):
-                assert torch.equal(x, y), ("side stream", t)
-    for e in ref + [a, b]:
+    torch.cuda.synchronize()
+    for i in range(2):
+        assert len(got[i]) == len(want[i])
+        for t, (g, w) in enumerate(zip(got[i], want[i])):
+            for x, y in zip(g, w):
+                assert torch.equal(x, y), (i, t)
+    for e in (a, b):
         assert int(e.error_flags().abs().sum()) == 0
         e.close()
