@@ -288,6 +288,14 @@ class OracleVec:
         self.L.oracle_get_counters(self.L.oracle_vec_env(self.h, int(i)), _ptr(c))
         return c
 
+    def state(self, i):
+        """(available_slots int8 [C,E,S], spectrum_slots_allocation int32 [C,E,S], current_time, len(_events)) of env i."""
+        cells = (self.cfg.num_cores, self.cfg.num_links, self.cfg.num_slots)
+        avail, alloc = np.zeros(cells, np.int8), np.zeros(cells, np.int32)
+        now, nheap = C.c_double(), C.c_int32()
+        self.L.oracle_get_state(self.L.oracle_vec_env(self.h, int(i)), _ptr(avail), _ptr(alloc), C.byref(now), C.byref(nheap))
+        return avail, alloc, now.value, nheap.value
+
     def close(self):
         if self.h:
             self.L.oracle_vec_destroy(self.h)

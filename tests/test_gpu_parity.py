@@ -507,3 +507,35 @@ def test_interleaved_handles_and_side_streams_keep_stream_order():
     for e in (a, b):
         assert int(e.error_flags().abs().sum()) == 0
         e.close()
+
+
+def test_config1_full_size_rmsa_4096_envs_sap_ff_matches_oracle():
+    """BASELINE.json configs[1] at its full size: RMSA-v0 on NSFNET (100 slots, 250 Erlang, k = 5), 4096 batched envs,
+    device shortest-available-path first-fit actions, 1000 steps: every env's counters, link masks, allocation, clock and
+    number of live services equal the oracle's (all host threads), bit for bit."""
+    from optical_rl_gym_b200 import OpticalVecEnv
+    from oracle import oracle
+
+    tables = helpers.golden_tables()
+    n, T, seed = 4096, 1000, 17
+    args = dict(episode_length=200, load=250, mean_service_holding_time=25, allow_rejection=True)
+    env = OpticalVecEnv("RMSA-v0", n, tables, traffic="philox", seed=seed, **args)
+    vec = oracle.OracleVec("RMSA-v0", tables, n, seed=seed, **helpers.sim_kwargs(dict(kind="RMSA-v0", env_args=args)))
+    accepted_ref = vec.run(T, policy=10 + helpers.HEURISTIC_ID["sap_ff"], with_obs=False)
+    acc = torch.zeros((), dtype=torch.int64, device="cuda")
+    for t in range(T):
+        obs, reward, done, info = env.step(env.heuristic("sap_ff"))
+        acc += (reward > 0).sum()
+    assert int(acc) == accepted_ref
+    cnt = env.counters().cpu().numpy()
+    m, alloc, now, nheap = env.export_state(allocation=True)
+    avail = env.available_slots().cpu().numpy()
+    alloc, now, nheap = alloc.cpu().numpy(), now.cpu().numpy(), nheap.cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(cnt[i], vec.counters(i)), ("counters", i)
+        oa, oal, onow, onh = vec.state(i)
+        assert np.array_equal(avail[i].reshape(oa.shape), oa), ("masks", i)
+        assert np.array_equal(alloc[i], oal), ("allocation", i)
+        assert now[i] == onow and nheap[i] == onh, ("clock / live services", i)
+    assert int(env.error_flags().abs().sum()) == 0
+    env.close(); vec.close()
