@@ -539,3 +539,39 @@ def test_config1_full_size_rmsa_4096_envs_sap_ff_matches_oracle():
         assert now[i] == onow and nheap[i] == onh, ("clock / live services", i)
     assert int(env.error_flags().abs().sum()) == 0
     env.close(); vec.close()
+
+
+def test_long_run_at_baseline_size_matches_oracle():
+    """65536 envs x 2000 steps through the rollout path (HOT kernel instance, dependent launches), then invariants over
+    all envs and a bit-for-bit comparison of ~100 sampled envs with the oracle replaying the same Philox streams."""
+    from optical_rl_gym_b200 import OpticalVecEnv
+    from oracle import oracle
+
+    tables = helpers.golden_tables()
+    n, T, seed = 65536, 2000, 99
+    env = OpticalVecEnv("DeepRMSA-v0", n, tables, seed=seed, episode_length=777)
+    a = torch.empty((n, 1), dtype=torch.int32, device="cuda")
+    for t in range(T):
+        env.sample_actions(out=a)
+        env.step_raw(a)
+    assert int(env.error_flags().abs().sum()) == 0
+    cnt = env.counters().cpu().numpy()
+    assert (cnt[:, 0] == T + 1).all()
+    m, alloc, now, nheap = env.export_state(allocation=True)
+    avail = env.available_slots()
+    assert torch.equal((avail == 0), (alloc.reshape(avail.shape) >= 0))       # busy slots == slots of live services
+    avail = avail.cpu().numpy()
+    obs = env.observation().cpu().numpy()
+    rng = np.random.default_rng(0)
+    for i in sorted(set([0, 1, 31, 32, 127, 128, n - 1] + rng.integers(0, n, 96).tolist())):
+        o = oracle.OracleEnv("DeepRMSA-v0", tables, num_slots=100, episode_length=777)
+        o.set_philox(seed, i)
+        o.reset(full=True)
+        o.rollout(T, policy=1)
+        oa, oal, onow, onh = o.state()
+        assert np.array_equal(avail[i].reshape(oa.shape), oa), ("masks", i)
+        assert np.array_equal(alloc[i].cpu().numpy(), oal), ("allocation", i)
+        assert now[i].item() == onow and nheap[i].item() == onh, ("clock / live services", i)
+        assert np.array_equal(cnt[i], o.counters()), ("counters", i)
+        np.testing.assert_allclose(obs[i], o.observation(), rtol=OBS_RTOL, atol=0)
+    env.close()
