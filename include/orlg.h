@@ -112,6 +112,9 @@ int orlg_heap_capacity(const orlg_env *env);
 int64_t orlg_state_bytes(const orlg_env *env);
 
 /* ---- traffic -------------------------------------------------------------------------- */
+/* env.seed(seed) (optical_network_env.py:205-210): new key of the counter-based request stream from the next
+ * request on; the state of the environments is not touched (like the reference, which only replaces its rng). */
+int orlg_seed(orlg_env *env, uint64_t seed);
 /* Replay mode: trace_dev[e * trace_len + i] is the i-th request of env e since the last full
  * reset.  The buffer must stay valid while the handle steps. */
 int orlg_set_trace(orlg_env *env, const orlg_request *trace_dev, int64_t trace_len);

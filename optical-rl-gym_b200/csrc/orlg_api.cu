@@ -476,6 +476,13 @@ int orlg_mask_words(const orlg_env *env) { return NW * env->p.nwv; }
 int orlg_heap_capacity(const orlg_env *env) { return env->p.heap_cap; }
 int64_t orlg_state_bytes(const orlg_env *env) { return env->state_bytes; }
 
+int orlg_seed(orlg_env *env, uint64_t seed) {
+    if (!env) return fail(ORLG_E_INVALID, "null handle");
+    env->p.seed = seed;           // a launch parameter: takes effect with the next kernel
+    env->cfg.seed = seed;
+    return ORLG_OK;
+}
+
 int orlg_set_trace(orlg_env *env, const orlg_request *trace_dev, int64_t trace_len) {
     if (!env || (trace_len > 0 && !trace_dev)) return fail(ORLG_E_INVALID, "null trace");
     if (trace_len >= (1LL << 32)) return fail(ORLG_E_UNSUPPORTED, "trace too long");

@@ -68,6 +68,7 @@ def lib():
     L.orlg_state_bytes.argtypes = [vp]
     L.orlg_state_bytes.restype = i64
     L.orlg_set_trace.argtypes = [vp, vp, i64]
+    L.orlg_seed.argtypes = [vp, C.c_uint64]
     L.orlg_reset.argtypes = [vp, i32, vp, vp]
     L.orlg_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.orlg_observation.argtypes = [vp, vp, vp]
@@ -95,7 +96,7 @@ def check(rc):
 
 
 EXPORTED = ["orlg_create", "orlg_destroy", "orlg_last_error", "orlg_version", "orlg_action_dim", "orlg_obs_dim",
-            "orlg_mask_words", "orlg_heap_capacity", "orlg_state_bytes", "orlg_set_trace", "orlg_reset", "orlg_step",
+            "orlg_mask_words", "orlg_heap_capacity", "orlg_state_bytes", "orlg_seed", "orlg_set_trace", "orlg_reset", "orlg_step",
             "orlg_observation", "orlg_observation_int", "orlg_heuristic", "orlg_random_actions", "orlg_get_counters",
             "orlg_get_requests", "orlg_export_state", "orlg_error_flags", "orlg_reduce_counters", "orlg_enable_stats",
             "orlg_num_bit_rates", "orlg_bit_rate_blocking", "orlg_matrix_obs_dim", "orlg_matrix_observation",

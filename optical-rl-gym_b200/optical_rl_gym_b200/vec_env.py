@@ -264,7 +264,12 @@ class OpticalVecEnv:
             pass
 
     def seed(self, seed=None):
-        raise NotImplementedError("the Philox key is fixed at construction (seed=...); build a new env to reseed")
+        """``env.seed(seed)`` for every env (optical_network_env.py:205-210; VecEnv.seed): the counter-based request
+        stream continues under the new key from the next request on (env i keeps its own sub-stream: the key is
+        shared, the global env id is part of the counter); state is untouched.  Returns the seed per env."""
+        self.rand_seed = 41 if seed is None else int(seed)
+        nat.check(self._lib.orlg_seed(self._h, self.rand_seed))
+        return [self.rand_seed] * self.num_envs
 
     def get_attr(self, name, indices=None):
         value = getattr(self, name)

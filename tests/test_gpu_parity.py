@@ -575,3 +575,34 @@ def test_long_run_at_baseline_size_matches_oracle():
         assert np.array_equal(cnt[i], o.counters()), ("counters", i)
         np.testing.assert_allclose(obs[i], o.observation(), rtol=OBS_RTOL, atol=0)
     env.close()
+
+
+def test_reseeding_mid_run_matches_oracle():
+    """VecEnv.seed(s): the Philox key changes from the next request on, state untouched (the reference's env.seed only
+    replaces the rng, optical_network_env.py:205-210)."""
+    from optical_rl_gym_b200 import OpticalVecEnv
+    from oracle import oracle
+
+    tables = helpers.golden_tables()
+    n, T = 48, 150
+    env = OpticalVecEnv("DeepRMSA-v0", n, tables, seed=5, episode_length=40, obs_dtype=torch.float64)
+    orc = []
+    for i in range(n):
+        o = oracle.OracleEnv("DeepRMSA-v0", tables, num_slots=100, episode_length=40)
+        o.set_philox(5, i)
+        o.reset(full=True)
+        orc.append(o)
+    for phase, seed in enumerate((None, 1234, 7)):
+        if seed is not None:
+            assert env.seed(seed) == [seed] * n
+            for i, o in enumerate(orc):
+                o.set_philox(seed, i)
+        refs = [o.rollout(T, policy=1, want_obs=True) for o in orc]
+        for t in range(T):
+            a = env.sample_actions()
+            assert np.array_equal(a.cpu().numpy(), np.stack([r["actions"][t] for r in refs])), (phase, t)
+            obs, reward, done, info = env.step(a)
+            assert np.array_equal(obs.cpu().numpy(), np.stack([r["obs"][t] for r in refs])), (phase, t)
+            assert np.array_equal(done.cpu().numpy(), np.array([r["dones"][t] for r in refs])), (phase, t)
+    assert int(env.error_flags().abs().sum()) == 0
+    env.close()
