@@ -73,7 +73,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.002)
+            time.sleep(0.01)
 
     def __enter__(self):
         if self.nv is not None:
