@@ -1,4 +1,8 @@
-import sys, time, os
+#!/usr/bin/env python
+"""Host-side issue rate of the rollout loop (two launches per step) against the GPU time per step:
+    python tools/host_issue_probe.py      (on a B200)"""
+import sys
+import time
 sys.path.insert(0, "optical-rl-gym_b200")
 import torch
 from optical_rl_gym_b200 import OpticalVecEnv, nsfnet
