@@ -139,6 +139,19 @@ int orlg_reset(orlg_env *env, int full, void *obs_dev, orlg_stream stream);
 int orlg_step(orlg_env *env, const int32_t *actions_dev, void *obs_dev, float *reward_dev, uint8_t *done_dev,
               int32_t *decision_dev, int64_t *info_dev, orlg_stream stream);
 
+/* T consecutive steps in ONE call: T iterations of { action = policy(env); obs, reward, done, _ = env.step(action) }
+ * (the rollout loop of examples/stable_baselines3/DeepRMSA.ipynb / utils.py:103-141 evaluate_heuristic), every step's
+ * results kept:
+ *   policy        ORLG_POLICY_RANDOM (orlg_random_actions) or an ORLG_HEUR_* id (orlg_heuristic)
+ *   obs_dev       [steps, num_envs, obs_dim]  (NULL: skip)      reward_dev  f32 [steps, num_envs]  (NULL: skip)
+ *   done_dev      u8 [steps, num_envs]        (NULL: skip)      actions_dev int32 [steps, num_envs, action_dim] (NULL: skip)
+ * Identical results to the step-by-step calls.  For DeepRMSA-v0 on NSFNET-class topologies with Philox traffic and
+ * float32 observations the T steps run inside one persistent kernel (state stays on chip); every other configuration
+ * issues the per-step kernels. */
+enum { ORLG_POLICY_RANDOM = -1 };
+int orlg_rollout(orlg_env *env, int steps, int policy, void *obs_dev, float *reward_dev, uint8_t *done_dev,
+                 int32_t *actions_dev, orlg_stream stream);
+
 /* Float statistics of `info` (rmsa_env.py:229-264, 439-543, 699-744; RMSA-v0 / DeepRMSA-v0, <= 32 links,
  * <= 128 slots): after this call every orlg_step also writes, per env, float64
  *   stats_dev[env][0..3] = network_compactness, network_compactness_difference,

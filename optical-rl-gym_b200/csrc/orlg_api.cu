@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "orlg_deeprmsa_fast.cuh"
+#include "orlg_rollout.cuh"
 #include "orlg_step_wide.cuh"
 #include "orlg_wrappers.cuh"
 
@@ -39,9 +40,24 @@ struct orlg_env {
     size_t obs_smem;
     int64_t state_bytes;
     std::vector<void *> allocs;
+    // T-steps-per-launch rollout path (orlg_rollout.cuh): window / scratch buffers, allocated by the first call
+    double *ro_sc_t = nullptr;
+    unsigned long long *ro_sc_p = nullptr;
+    WinEntry *ro_win = nullptr;
+    int *ro_actions = nullptr;    // [n, action_dim] scratch of the generic (kernel-per-step) rollout
 };
 
 namespace {
+
+// every entry point runs on the handle's device whatever the caller's current device is (and puts it back)
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
 
 template <typename T>
 int dev_alloc(orlg_env *env, T **out, size_t count, bool zero = true) {
@@ -208,6 +224,50 @@ int launch_step(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s)
     return ORLG_OK;
 }
 
+// shared-memory plan of the rollout kernel: as many warps per CTA as cover the batch in one wave (<= 14), each with
+// its mask tile + side buffer, plus a pool of observation tiles
+bool rollout_plan(const orlg_env *env, int *wpc_out, RolloutArgs *ra, size_t *smem_out) {
+    const Params &p = env->p;
+    const int warps = (p.n + 31) / 32;
+    int wpc = (warps + 147) / 148;
+    if (wpc > RO_MAX_THREADS / 32) wpc = RO_MAX_THREADS / 32;
+    if (wpc < 1) wpc = 1;
+    if (const char *v = std::getenv("ORLG_RO_WARPS")) { int w = std::atoi(v); if (w >= 1 && w <= RO_MAX_THREADS / 32) wpc = w; }
+    const int tile = (32 * p.obs_dim * 4 + 127) / 128 * 128;
+    const int warp_bytes = p.E * 512 + RO_SIDE * 512;
+    const size_t budget = 227 * 1024;
+    for (; wpc >= 1; wpc--) {
+        const size_t fixed = (size_t)p.tab_vec * 16 + (size_t)wpc * warp_bytes + 16;
+        if (fixed + tile > budget) continue;
+        int tiles = (int)((budget - fixed) / tile);
+        if (tiles > wpc) tiles = wpc;
+        if (tiles > 32) tiles = 32;
+        if (const char *v = std::getenv("ORLG_RO_TILES")) { int w = std::atoi(v); if (w >= 1 && w <= tiles) tiles = w; }
+        ra->pool_tiles = tiles; ra->tile_bytes = tile; ra->warp_bytes = warp_bytes;
+        *wpc_out = wpc;
+        *smem_out = fixed + (size_t)tiles * tile;
+        return true;
+    }
+    return false;
+}
+
+template <int ET>
+cudaError_t launch_rollout(const orlg_env *env, const RolloutArgs &ra, int policy, int wpc, size_t smem, cudaStream_t s) {
+    const int threads = wpc * 32, blocks = (env->p.n + threads - 1) / threads;
+    cudaLaunchConfig_t cfg = pdl_config(blocks, threads, smem, s);
+    cudaError_t e;
+#define ORLG_RO_LAUNCH(POL)                                                                                          \
+    do {                                                                                                             \
+        e = cudaFuncSetAttribute(deeprmsa_rollout_kernel<ET, POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, deeprmsa_rollout_kernel<ET, POL>, env->p, ra);            \
+    } while (0)
+    if (policy == ORLG_POLICY_RANDOM) ORLG_RO_LAUNCH(RO_POLICY_RANDOM);
+    else if (policy == ORLG_HEUR_SP_FF) ORLG_RO_LAUNCH(RO_POLICY_SP_FF);
+    else ORLG_RO_LAUNCH(RO_POLICY_SAP_FF);
+#undef ORLG_RO_LAUNCH
+    return e;
+}
+
 }  // namespace
 
 extern "C" {
@@ -236,7 +296,9 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
         return fail(ORLG_E_INVALID, "bit_rate_higher_bound < bit_rate_lower_bound");
     if (cfg->kind == ORLG_RMCSA && t->num_mods < 1) return fail(ORLG_E_INVALID, "RMCSA needs a modulation table");
 
-    CUDA_OK(cudaSetDevice(device));
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) return fail(ORLG_E_CUDA, "no such CUDA device");
+    DeviceGuard guard(device);
     orlg_env *env = new orlg_env();
     env->cfg = *cfg;
     env->device = device;
@@ -300,12 +362,26 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     for (int m = 0; m < t->num_mods; m++) { mod_se[m] = (unsigned char)t->mod_se[m]; se_max = t->mod_se[m] > se_max ? t->mod_se[m] : se_max; }
     // get_number_slots (rmsa_env.py:610-621): ceil(bit_rate / (SE * channel_width)) + 1, same float expression
     std::vector<unsigned char> nslots((size_t)(se_max + 1) * (br_max + 1), 1);
+    bool slots_unrepresentable = false;
     for (int se = 1; se <= se_max; se++)
         for (int b = 0; b <= br_max; b++) {
             int n = (int)std::ceil((double)b / ((double)se * cfg->channel_width)) + 1;
-            if (n > 200) n = 200;      // > S anyway: can never fit
+            if (n > 200) {             // 8-bit table entry / payload field; harmless only while 200 slots can never fit
+                const bool configured = t->num_bit_rates > 0 ? false : (b >= cfg->bit_rate_lo && b <= cfg->bit_rate_hi);
+                if (n <= p.S && configured) slots_unrepresentable = true;
+                n = 200;
+            }
             nslots[(size_t)se * (br_max + 1) + b] = (unsigned char)n;
         }
+    for (int i = 0; i < t->num_bit_rates; i++)
+        for (int se = 1; se <= se_max; se++) {
+            const int n = (int)std::ceil((double)t->bit_rates[i] / ((double)se * cfg->channel_width)) + 1;
+            if (n > 200 && n <= p.S) slots_unrepresentable = true;
+        }
+    if (slots_unrepresentable && cfg->kind != ORLG_RWA) {
+        delete env;
+        return fail(ORLG_E_UNSUPPORTED, "a request of this configuration may need 201.." + std::to_string(p.S) + " slots: at most 200 slots per service are representable");
+    }
     std::vector<double> reach((size_t)(t->num_mods > 0 ? t->num_mods : 1) * (br_max + 1), 0.0);
     if (cfg->kind == ORLG_RMCSA)
         for (int m = 0; m < t->num_mods; m++)
@@ -464,7 +540,7 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
 
 int orlg_destroy(orlg_env *env) {
     if (!env) return ORLG_OK;
-    cudaSetDevice(env->device);
+    DeviceGuard guard(env->device);
     for (void *ptr : env->allocs) cudaFree(ptr);
     delete env;
     return ORLG_OK;
@@ -494,6 +570,7 @@ int orlg_set_trace(orlg_env *env, const orlg_request *trace_dev, int64_t trace_l
 
 int orlg_reset(orlg_env *env, int full, void *obs_dev, orlg_stream stream) {
     if (!env) return fail(ORLG_E_INVALID, "null handle");
+    DeviceGuard guard(env->device);
     if (env->p.traffic == ORLG_TRAFFIC_TRACE && env->p.trace == nullptr) return fail(ORLG_E_INVALID, "trace traffic selected but orlg_set_trace was not called");
     StepIO io;
     std::memset(&io, 0, sizeof(io));
@@ -510,6 +587,7 @@ int orlg_reset(orlg_env *env, int full, void *obs_dev, orlg_stream stream) {
 int orlg_step(orlg_env *env, const int32_t *actions_dev, void *obs_dev, float *reward_dev, uint8_t *done_dev,
               int32_t *decision_dev, int64_t *info_dev, orlg_stream stream) {
     if (!env || !actions_dev) return fail(ORLG_E_INVALID, "null handle or actions");
+    DeviceGuard guard(env->device);
     StepIO io;
     io.actions = actions_dev;
     io.obs = env->p.obs_dim ? obs_dev : nullptr;
@@ -525,6 +603,7 @@ int orlg_step(orlg_env *env, const int32_t *actions_dev, void *obs_dev, float *r
 
 int orlg_observation(orlg_env *env, void *obs_dev, orlg_stream stream) {
     if (!env || !obs_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
+    DeviceGuard guard(env->device);
     if (!env->p.obs_dim) return fail(ORLG_E_UNSUPPORTED, "this env kind has a dict observation (no tensor)");
     StepIO io;
     std::memset(&io, 0, sizeof(io));
@@ -534,6 +613,7 @@ int orlg_observation(orlg_env *env, void *obs_dev, orlg_stream stream) {
 
 int orlg_observation_int(orlg_env *env, int32_t *out_dev, orlg_stream stream) {
     if (!env || !out_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
+    DeviceGuard guard(env->device);
     if (!env->p.obs_dim) return fail(ORLG_E_UNSUPPORTED, "this env kind has a dict observation (no tensor)");
     StepIO io;
     std::memset(&io, 0, sizeof(io));
@@ -543,6 +623,7 @@ int orlg_observation_int(orlg_env *env, int32_t *out_dev, orlg_stream stream) {
 
 int orlg_heuristic(orlg_env *env, int which, int32_t *actions_dev, orlg_stream stream) {
     if (!env || !actions_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
+    DeviceGuard guard(env->device);
     if (which < 0 || which > ORLG_HEUR_SAP_LF) return fail(ORLG_E_INVALID, "unknown heuristic");
     const int threads = 128, blocks = (env->p.n + threads - 1) / threads;
     cudaStream_t s = (cudaStream_t)stream;
@@ -574,6 +655,7 @@ int orlg_heuristic(orlg_env *env, int which, int32_t *actions_dev, orlg_stream s
 
 int orlg_random_actions(orlg_env *env, int32_t *actions_dev, orlg_stream stream) {
     if (!env || !actions_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
+    DeviceGuard guard(env->device);
     const int threads = 256, blocks = (env->p.n + threads - 1) / threads;
     cudaLaunchConfig_t cfg = pdl_config(blocks, threads, 0, (cudaStream_t)stream);
     int *actions = actions_dev;
@@ -584,6 +666,7 @@ int orlg_random_actions(orlg_env *env, int32_t *actions_dev, orlg_stream stream)
 static int run_export(orlg_env *env, uint32_t *masks, int32_t *alloc, double *now, int32_t *nheap, int64_t *counters,
                       orlg_request *req, int32_t *sid, uint32_t *err, orlg_stream stream) {
     if (!env) return fail(ORLG_E_INVALID, "null handle");
+    DeviceGuard guard(env->device);
     const int threads = 128, blocks = (env->p.n + threads - 1) / threads;
     if (env->wide && (masks || alloc)) {
         export_wide_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->p, masks, alloc);
@@ -639,6 +722,7 @@ int orlg_debug_warp_timeline(unsigned long long *out, int n_warps) {
 
 int orlg_enable_stats(orlg_env *env, double *stats_dev) {
     if (!env) return fail(ORLG_E_INVALID, "null handle");
+    DeviceGuard guard(env->device);
     Params &p = env->p;
     if (!stats_dev) { p.stats = 0; p.stats_out = nullptr; return ORLG_OK; }
     if (p.kind != ORLG_RMSA && p.kind != ORLG_DEEPRMSA) return fail(ORLG_E_UNSUPPORTED, "info has float statistics for RMSA-v0 / DeepRMSA-v0 only");
@@ -660,6 +744,7 @@ int orlg_num_bit_rates(const orlg_env *env) { return env->p.br_hist ? env->p.n_b
 
 int orlg_bit_rate_blocking(orlg_env *env, double *out_dev, orlg_stream stream) {
     if (!env || !out_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
+    DeviceGuard guard(env->device);
     if (!env->p.br_hist) return fail(ORLG_E_UNSUPPORTED, "per-bit-rate statistics exist for RMSA-v0 with bit_rate_selection='discrete'");
     bit_rate_blocking_kernel<<<(env->p.n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->p, out_dev);
     CUDA_OK(cudaGetLastError());
@@ -670,6 +755,7 @@ int orlg_matrix_obs_dim(const orlg_env *env) { return 2 * env->p.N + env->p.C * 
 
 int orlg_matrix_observation(orlg_env *env, uint8_t *out_dev, orlg_stream stream) {
     if (!env || !out_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
+    DeviceGuard guard(env->device);
     const long long total = (long long)orlg_matrix_obs_dim(env) * env->p.n;
     long long blocks = (total + 255) / 256;
     if (blocks > 148LL * 32) blocks = 148LL * 32;
@@ -680,6 +766,7 @@ int orlg_matrix_observation(orlg_env *env, uint8_t *out_dev, orlg_stream stream)
 
 int orlg_path_only_first_fit(orlg_env *env, const int32_t *path_actions_dev, int32_t *actions_dev, orlg_stream stream) {
     if (!env || !path_actions_dev || !actions_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
+    DeviceGuard guard(env->device);
     if (env->p.kind != ORLG_RMSA && env->p.kind != ORLG_RWA)
         return fail(ORLG_E_UNSUPPORTED, "PathOnlyFirstFitAction exists for RMSA-v0 and RWA-v0 (the RMCSA one raises upstream)");
     const int blocks = (env->p.n + 127) / 128;
@@ -694,8 +781,64 @@ int orlg_path_only_first_fit(orlg_env *env, const int32_t *path_actions_dev, int
     return ORLG_OK;
 }
 
+int orlg_rollout(orlg_env *env, int steps, int policy, void *obs_dev, float *reward_dev, uint8_t *done_dev,
+                 int32_t *actions_dev, orlg_stream stream) {
+    if (!env) return fail(ORLG_E_INVALID, "null handle");
+    DeviceGuard guard(env->device);
+    if (steps < 0) return fail(ORLG_E_INVALID, "steps must be >= 0");
+    if (policy != ORLG_POLICY_RANDOM && (policy < 0 || policy > ORLG_HEUR_SAP_LF)) return fail(ORLG_E_INVALID, "unknown policy");
+    if (steps == 0) return ORLG_OK;
+    Params &p = env->p;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool persistent = env->hot && !p.stats && p.traffic == ORLG_TRAFFIC_PHILOX && !p.obs_f64 &&
+                            (policy == ORLG_POLICY_RANDOM || policy == ORLG_HEUR_SP_FF || policy == ORLG_HEUR_SAP_FF) &&
+                            !std::getenv("ORLG_NO_ROLLOUT_KERNEL");
+    RolloutArgs ra;
+    std::memset(&ra, 0, sizeof(ra));
+    int wpc = 0;
+    size_t smem = 0;
+    if (persistent && rollout_plan(env, &wpc, &ra, &smem)) {
+        if (!env->ro_win) {
+            const size_t n = (size_t)p.n;
+            int rc = dev_alloc(env, &env->ro_sc_t, n * RO_WCAP, false);
+            if (!rc) rc = dev_alloc(env, &env->ro_sc_p, n * RO_WCAP, false);
+            if (!rc) rc = dev_alloc(env, &env->ro_win, n * RO_WCAP, false);
+            if (rc) return rc;
+        }
+        double span_steps = 40.0;
+        if (const char *v = std::getenv("ORLG_RO_SPAN")) { double w = std::atof(v); if (w > 0) span_steps = w; }
+        ra.T = steps;
+        ra.span = span_steps * p.mean_iat;
+        ra.obs = reinterpret_cast<float *>(obs_dev);
+        ra.reward = reward_dev; ra.done = done_dev; ra.actions = actions_dev;
+        ra.sc_t = env->ro_sc_t; ra.sc_p = env->ro_sc_p; ra.win = env->ro_win;
+        cudaError_t e = p.E == 22 ? launch_rollout<22>(env, ra, policy, wpc, smem, s) : launch_rollout<0>(env, ra, policy, wpc, smem, s);
+        if (e != cudaSuccess) return fail(ORLG_E_CUDA, std::string("rollout launch: ") + cudaGetErrorString(e));
+        p.lockstep_ridx += (unsigned)steps;
+        return ORLG_OK;
+    }
+    // generic: the same T steps as separate policy + step launches
+    const int adim = orlg_action_dim(env);
+    if (!actions_dev && !env->ro_actions) {
+        int rc = dev_alloc(env, &env->ro_actions, (size_t)p.n * adim, false);
+        if (rc) return rc;
+    }
+    const size_t obs_row = (size_t)p.obs_dim * (p.obs_f64 ? 8 : 4);
+    for (int t = 0; t < steps; t++) {
+        int32_t *a = actions_dev ? actions_dev + (size_t)t * p.n * adim : env->ro_actions;
+        int rc = policy == ORLG_POLICY_RANDOM ? orlg_random_actions(env, a, stream) : orlg_heuristic(env, policy, a, stream);
+        if (rc) return rc;
+        rc = orlg_step(env, a, (obs_dev && p.obs_dim) ? reinterpret_cast<unsigned char *>(obs_dev) + (size_t)t * p.n * obs_row : nullptr,
+                       reward_dev ? reward_dev + (size_t)t * p.n : nullptr, done_dev ? done_dev + (size_t)t * p.n : nullptr,
+                       nullptr, nullptr, stream);
+        if (rc) return rc;
+    }
+    return ORLG_OK;
+}
+
 int orlg_reduce_counters(orlg_env *env, int64_t *sums_dev, orlg_stream stream) {
     if (!env || !sums_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
+    DeviceGuard guard(env->device);
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_OK(cudaMemsetAsync(sums_dev, 0, 9 * sizeof(int64_t), s));
     int blocks = (env->p.n + 255) / 256;

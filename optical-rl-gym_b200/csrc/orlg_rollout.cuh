@@ -1,0 +1,509 @@
+// orlg_rollout.cuh -- T environment steps per launch for DeepRMSA (the headline rollout path).
+//
+// Same semantics as T iterations of { action = policy(env); obs, reward, done = env.step(action) } through
+// orlg_random_actions / orlg_heuristic + orlg_step (deeprmsa_env.py:48-124 on top of rmsa_env.py:163-282,
+// 545-597), with every step's action / reward / done / float32 observation written to [T, N, ...] buffers.
+// What changes is where the state lives while the T steps run:
+//   * a warp owns 32 consecutive envs for the whole launch: their link masks ([link][lane] uint4, E x 512 B)
+//     stay in shared memory and the scalar block (clock, pending request, counters, cached block starts)
+//     stays in registers; HBM sees them once at entry and once at exit;
+//   * the release-event table (orlg_device.cuh) is consulted through a per-env WINDOW: every ~span steps the
+//     thread streams its table once, moves the services that expire before a horizon into a small list sorted
+//     by release time (HBM / L2, 16-byte entries) and compacts the rest in place.  A step then only compares
+//     the list head (two registers) with the clock: the directory -> group -> payload fetch chain of the
+//     per-step kernel is gone.  Services accepted with a release time inside the horizon wait in a 3-entry
+//     side buffer in shared memory.  The exact minimum of what is left in the table gates the next rebuild,
+//     so the scheme is exact whatever the horizon (which only tunes how often the table is streamed);
+//     rebuilds are taken by the whole warp together (ballot), thread-per-env, no cross-lane traffic;
+//   * the 32 observation rows of a warp are assembled in a shared-memory tile taken from a small per-CTA
+//     pool and leave as ONE bulk (TMA) store per step; the topology tables arrive by one bulk copy per CTA;
+//   * at exit the window / side entries go back to the table and its directory is rebuilt, so that every
+//     other entry point of the library (per-step kernels, export, heuristics) sees the canonical state.
+// Release order inside a step is irrelevant (masks only); what must be exact is WHICH
+// services are due, and that is decided on the float64 times.
+#pragma once
+#include "orlg_deeprmsa_fast.cuh"
+
+namespace orlg {
+
+constexpr int RO_WCAP = 64;            // window entries per env
+constexpr int RO_SIDE = 3;             // side-buffer entries per env (shared memory)
+constexpr int RO_MAX_THREADS = 448;    // 14 warps x 148 SMs >= 65536 envs in one wave
+enum { RO_POLICY_RANDOM = 0, RO_POLICY_SP_FF = 1, RO_POLICY_SAP_FF = 2 };
+
+struct __align__(16) WinEntry {
+    double t;
+    unsigned long long p;
+};
+
+struct RolloutArgs {
+    int T;                       // steps per launch
+    int pool_tiles;              // observation tiles shared by the CTA's warps
+    int tile_bytes;              // 32 rows x obs_dim floats, rounded up to 128 bytes
+    int warp_bytes;              // per-warp shared memory: E x 512 (masks) + RO_SIDE x 512 (side buffer)
+    double span;                 // window horizon (time units ahead of the clock)
+    float *obs;                  // [T][n][obs_dim]   (NULL: skip)
+    float *reward;               // [T][n]            (NULL: skip)
+    unsigned char *done;         // [T][n]            (NULL: skip)
+    int *actions;                // [T][n]            (NULL: skip)
+    double *sc_t;                // [n][RO_WCAP] scratch: candidate times
+    unsigned long long *sc_p;    // [n][RO_WCAP] scratch: candidate payloads
+    WinEntry *win;               // [n][RO_WCAP] the sorted window
+};
+
+// apply a release / an allocation to the path's links in the warp's shared-memory mask tile
+template <bool SET>
+__device__ __forceinline__ void ro_path_update(uint4 *sm, unsigned lm, const Bits &rm) {
+    while (lm) {
+        const int l = __ffs(lm) - 1;
+        lm &= lm - 1;
+        uint4 v = sm[l * 32];
+        if (SET) { v.x |= rm.w[0]; v.y |= rm.w[1]; v.z |= rm.w[2]; v.w |= rm.w[3]; }
+        else { v.x &= ~rm.w[0]; v.y &= ~rm.w[1]; v.z &= ~rm.w[2]; v.w &= ~rm.w[3]; }
+        sm[l * 32] = v;
+    }
+}
+
+// Thread-per-env window rebuild.  On entry: table = slots [0, n) (unsorted, +INF above), window = win[wh, wn)
+// (sorted), side = up to RO_SIDE entries.  Everything goes back to the table, then one streaming pass moves the
+// entries with time < h to the scratch list and compacts the others in place (forward, stable), and the scratch
+// list is rank-sorted into the window.  Leaves tmin = exact minimum of the table.
+__device__ __forceinline__ void ro_rebuild(double *__restrict__ ev_t, unsigned long long *__restrict__ ev_p,
+                                           double *__restrict__ sc_t, unsigned long long *__restrict__ sc_p,
+                                           WinEntry *__restrict__ win, double *side_t, unsigned long long *side_p,
+                                           unsigned &n, unsigned &wh, unsigned &wn, double &tmin, double &side_min,
+                                           const double h) {
+    for (unsigned j = wh; j < wn; j++) {                // leftover window entries
+        const WinEntry w = win[j];
+        ev_t[n] = w.t; ev_p[n] = w.p; n++;
+    }
+#pragma unroll
+    for (int s = 0; s < RO_SIDE; s++) {                 // side buffer
+        const double t = side_t[s * 32];
+        if (t < ORLG_INF) { ev_t[n] = t; ev_p[n] = side_p[s * 32]; n++; side_t[s * 32] = ORLG_INF; }
+    }
+    side_min = ORLG_INF;
+    unsigned k = 0, c = 0;
+    double mn = ORLG_INF;
+    for (unsigned s0 = 0; s0 < n; s0 += 4) {            // n <= heap_cap (multiple of 16): the vector loads stay inside the table
+        const double2 ta = *reinterpret_cast<const double2 *>(ev_t + s0);
+        const double2 tb = *reinterpret_cast<const double2 *>(ev_t + s0 + 2);
+        const ulonglong2 pa = *reinterpret_cast<const ulonglong2 *>(ev_p + s0);
+        const ulonglong2 pb = *reinterpret_cast<const ulonglong2 *>(ev_p + s0 + 2);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const double t = i == 0 ? ta.x : (i == 1 ? ta.y : (i == 2 ? tb.x : tb.y));
+            const unsigned long long pl = i == 0 ? pa.x : (i == 1 ? pa.y : (i == 2 ? pb.x : pb.y));
+            if (s0 + i < n) {
+                if (t < h && c < (unsigned)RO_WCAP) {
+                    sc_t[c] = t; sc_p[c] = pl; c++;
+                } else {
+                    if (k != s0 + i) { ev_t[k] = t; ev_p[k] = pl; }
+                    k++;
+                    mn = dmin(mn, t);
+                }
+            }
+        }
+    }
+    for (unsigned s = k; s < n; s++) ev_t[s] = ORLG_INF;    // "every slot >= n holds +INF"
+    n = k;
+    tmin = mn;
+    for (unsigned j = 0; j < c; j++) {                  // rank sort (c is ~10: quadratic is fine)
+        const double tj = sc_t[j];
+        unsigned rank = 0;
+        for (unsigned q = 0; q < c; q++) {
+            const double tq = sc_t[q];
+            rank += (tq < tj || (tq == tj && q < j)) ? 1u : 0u;
+        }
+        WinEntry w;
+        w.t = tj; w.p = sc_p[j];
+        win[rank] = w;
+    }
+    wh = 0; wn = c;
+}
+
+template <int ET, int POLICY>
+__global__ void __launch_bounds__(RO_MAX_THREADS, 1)
+deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
+    constexpr int KM = 5;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int wpc = blockDim.x >> 5;
+    const int env = blockIdx.x * blockDim.x + tid;
+    const bool live = env < p.n;
+    const int e = live ? env : p.n - 1;
+    const int E = ET > 0 ? ET : p.E;
+    unsigned char *warp_area = smem + p.tab_vec * 16 + (size_t)wid * ra.warp_bytes;
+    uint4 *sm = reinterpret_cast<uint4 *>(warp_area) + lane;                                   // masks: sm[l * 32]
+    double *side_t = reinterpret_cast<double *>(warp_area + (size_t)E * 512) + lane;           // side_t[s * 32]
+    unsigned long long *side_p = reinterpret_cast<unsigned long long *>(warp_area + (size_t)E * 512 + RO_SIDE * 256) + lane;
+    unsigned char *pool = smem + p.tab_vec * 16 + (size_t)wpc * ra.warp_bytes;
+    unsigned long long *tab_bar = reinterpret_cast<unsigned long long *>(pool + (size_t)ra.pool_tiles * ra.tile_bytes);
+    unsigned *pool_free = reinterpret_cast<unsigned *>(tab_bar + 1);
+
+    pdl_launch_dependents();
+    // ---------------- tables: one bulk copy per CTA
+    if (tid == 0) {
+        mbar_init(tab_bar, 1);
+        mbar_expect_tx(tab_bar, (unsigned)p.tab_vec * 16u);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(p.tab_blob), "r"((unsigned)p.tab_vec * 16u),
+                       "r"((unsigned)__cvta_generic_to_shared(tab_bar)) : "memory");
+        *pool_free = ra.pool_tiles >= 32 ? 0xFFFFFFFFu : ((1u << ra.pool_tiles) - 1u);
+    }
+    const unsigned short *s_pair_first = reinterpret_cast<const unsigned short *>(smem + p.off_pair_first);
+    const unsigned char *s_pair_count = smem + p.off_pair_count;
+    const unsigned *s_path_lm = reinterpret_cast<const unsigned *>(smem + p.off_path_lm);
+    const unsigned char *s_path_se = smem + p.off_path_se;
+    const unsigned char *s_nslots = smem + p.off_nslots;
+    const unsigned *s_node_thr = reinterpret_cast<const unsigned *>(smem + p.off_node_thr);
+    const float *s_pos = reinterpret_cast<const float *>(smem + p.off_pos);
+    const float *s_nsl = reinterpret_cast<const float *>(smem + p.off_nsl);
+    const float *s_rcp4 = reinterpret_cast<const float *>(smem + p.off_rcp4);
+    const unsigned *s_dbl = reinterpret_cast<const unsigned *>(smem + p.off_dbl);
+    pdl_wait();                      // state is touched from here on
+
+    // ---------------- state in: masks -> shared memory (cp.async, coalesced 512 B per link and warp), scalars -> registers
+    {
+        const uint4 *mr = p.masks + e;
+        unsigned sdst = (unsigned)__cvta_generic_to_shared(sm);
+        for (int l = 0; l < E; l++) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(mr) : "memory");
+            sdst += 32 * 16;
+            mr += p.n;
+        }
+        cp_async_commit();
+    }
+    double now = p.now[e];
+    double hold = p.cur_hold[e];
+    const uint2 rq0 = p.cur_req[e];
+    int src = rq0.x & 0xff, dst = (rq0.x >> 8) & 0xff, br = (int)(rq0.x >> 16), sid = (int)rq0.y;
+    int ep_proc = (int)p.counters[(size_t)2 * p.n + e], ep_acc = (int)p.counters[(size_t)3 * p.n + e];
+    int ep_req = (int)p.counters[(size_t)6 * p.n + e], ep_prov = (int)p.counters[(size_t)7 * p.n + e];
+    int d_proc = 0, d_acc = 0, d_req = 0, d_prov = 0;        // deltas of the four running totals over this launch
+    unsigned ridx = p.req_index[e];
+    unsigned nlive = p.nheap[e];                              // live services = table + window + side
+    unsigned n_tab = nlive;
+    unsigned err = p.errors[e];
+    unsigned long long candw = *reinterpret_cast<const unsigned long long *>(p.cand + (size_t)e * 8);
+    double *const ev_t = p.ev_time + (size_t)e * p.heap_cap;
+    unsigned long long *const ev_p = p.ev_pay + (size_t)e * p.heap_cap;
+    double *const sc_t = ra.sc_t + (size_t)e * RO_WCAP;
+    unsigned long long *const sc_p = ra.sc_p + (size_t)e * RO_WCAP;
+    WinEntry *const win = ra.win + (size_t)e * RO_WCAP;
+#pragma unroll
+    for (int s = 0; s < RO_SIDE; s++) side_t[s * 32] = ORLG_INF;
+    if (ridx != p.lockstep_ridx) err |= ORLG_ERR_LOCKSTEP;
+    unsigned wh = 0, wn = 0;
+    double tmin_tab = ORLG_INF, side_min = ORLG_INF, hzn = now + ra.span;
+    WinEntry head;
+    head.t = ORLG_INF; head.p = 0;
+    if (live) {
+        ro_rebuild(ev_t, ev_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn);
+        if (wn) head = win[0];
+    }
+    cp_async_wait<0>();
+    __syncthreads();                 // pool word + table barrier initialised by thread 0 ...
+    mbar_wait(tab_bar, 0);           // ... and the tables have landed
+    if (blockIdx.x * blockDim.x + wid * 32 >= p.n) return;              // a warp without environments (no CTA-wide barrier below)
+    int npaths_cur = min((int)s_pair_count[src * p.N + dst], KM);       // candidate paths of the pending request
+
+    const unsigned long long gid = (unsigned long long)(p.env_id_base + e);
+    const unsigned k0 = (unsigned)p.seed, k1 = (unsigned)(p.seed >> 32);
+    const unsigned n_act = (unsigned)(p.k) + (p.allow_rejection ? 1u : 0u);     // j = 1
+
+    for (int t = 0; t < ra.T; t++) {
+        bool done = false;
+        int npaths = 0;
+        unsigned pm[KM];
+        int ns[KM];
+        if (live) {
+            // ---- the next request (rmsa_env.py:545-561): a pure function of (seed, global env id, request index)
+            uint32_t rc_[4] = {ridx, 0u, (uint32_t)gid, 0u}, rd_[4] = {ridx, 0u, (uint32_t)gid, 1u};
+            philox4x32_10(rc_, k0, k1);
+            philox4x32_10(rd_, k0, k1);
+            const double e_iat = __dmul_rn(neg_log_u32(rc_[0]), p.mean_iat);
+            const double e_hold = __dmul_rn(neg_log_u32(rc_[1]), p.mean_holding);
+            const int nn = p.N;
+            const int p_src = pick_thr_bsearch(s_node_thr, nn, p.node_top_step, rc_[2]);
+            const unsigned lo = p_src ? s_node_thr[p_src - 1] : 0u;
+            const unsigned long long hi = (p_src == nn - 1) ? 4294967296ULL : (unsigned long long)s_node_thr[p_src];
+            const unsigned long long mass = hi - lo;
+            unsigned long long tt = ((unsigned long long)rc_[3] * (4294967296ULL - mass)) >> 32;
+            if (tt >= lo) tt += mass;
+            int p_dst = pick_thr_bsearch(s_node_thr, nn, p.node_top_step, (unsigned)tt);
+            if (p_dst == p_src) p_dst = (p_src + 1) % nn;
+            const int p_br = p.br_lo + (int)__umulhi(rd_[0], (unsigned)p.br_span);
+            const int npair = p_src * p.N + p_dst;
+            const int p_first = s_pair_first[npair];
+            npaths = min((int)s_pair_count[npair], KM);
+#pragma unroll
+            for (int q = 0; q < KM; q++) {
+                const bool have = q < npaths;
+                const int row = have ? p_first + q : p_first;
+                ns[q] = s_nslots[s_path_se[row] * 128 + p_br];
+                pm[q] = have ? s_path_lm[row] : 0u;
+            }
+
+            // ---- the policy's action on the pending request
+            int act;
+            if (POLICY == RO_POLICY_RANDOM) {                    // orlg_random_actions: Philox stream 2, same counter
+                uint32_t ra_[4] = {ridx, 0u, (uint32_t)gid, 2u};
+                philox4x32_10(ra_, k0, k1);
+                act = (int)__umulhi(ra_[0], n_act);
+            } else if (POLICY == RO_POLICY_SP_FF) {              // deeprmsa_env.py:135-143
+                act = (!p.allow_rejection || (candw & 0xffu) != CAND_NONE) ? 0 : p.k;
+            } else {                                             // deeprmsa_env.py:146-155
+                act = p.k;
+                for (int q = npaths_cur - 1; q >= 0; q--)
+                    if (((candw >> (8 * q)) & 0xffu) != CAND_NONE) act = q;
+            }
+            if (ra.actions) ra.actions[(size_t)t * p.n + env] = act;
+
+            // ---- Phase A (deeprmsa_env.py:48-58 -> rmsa_env.py:163-209): the cached block start decides
+            bool accepted = false;
+            if (act >= 0 && act < p.k) {
+                const int pair = src * p.N + dst;
+                if (act < (int)s_pair_count[pair]) {
+                    const unsigned st = (unsigned)((candw >> (8 * act)) & 0xffu);
+                    if (st != CAND_NONE) {
+                        if (nlive + 1 > (unsigned)p.heap_cap) {
+                            err |= ORLG_ERR_HEAP_OVERFLOW;
+                        } else {
+                            const int a_row = s_pair_first[pair] + act;
+                            const int a_n = s_nslots[s_path_se[a_row] * 128 + br];
+                            const unsigned a_lm = s_path_lm[a_row];
+                            ro_path_update<false>(sm, a_lm, bits_range_short((int)st, a_n));      // _provision_path
+                            const double rel = __dadd_rn(now, hold);
+                            const unsigned long long pl = pack_service(a_row, (int)st, a_n, 0, sid);
+                            bool in_side = false;
+                            if (rel < hzn) {                     // expires inside the window: side buffer
+#pragma unroll
+                                for (int s = 0; s < RO_SIDE; s++) {
+                                    if (!in_side && !(side_t[s * 32] < ORLG_INF)) {
+                                        side_t[s * 32] = rel; side_p[s * 32] = pl; in_side = true;
+                                    }
+                                }
+                                if (in_side) side_min = dmin(side_min, rel);
+                            }
+                            if (!in_side) {                      // table push: two stores
+                                ev_t[n_tab] = rel; ev_p[n_tab] = pl; n_tab++;
+                                tmin_tab = dmin(tmin_tab, rel);
+                            }
+                            nlive++;
+                            d_acc += 1; ep_acc += 1; d_prov += br; ep_prov += br;
+                            accepted = true;
+                        }
+                    }
+                } else {
+                    err |= ORLG_ERR_NO_SUCH_PATH;
+                }
+            }
+            if (ra.reward) ra.reward[(size_t)t * p.n + env] = accepted ? 1.0f : -1.0f;
+
+            // ---- Phase B: _next_service (rmsa_env.py:545-597)
+            now = __dadd_rn(now, e_iat);
+            hold = e_hold; src = p_src; dst = p_dst; br = p_br;
+            ridx++;
+            sid = ep_proc;
+            d_proc += 1; ep_proc += 1; d_req += br; ep_req += br;
+            npaths_cur = npaths;
+            while (head.t <= now) {                              // sorted window: the head is the earliest
+                const int rs = svc_start(head.p);
+                ro_path_update<true>(sm, s_path_lm[svc_row(head.p)], bits_range_short(rs, svc_slots(head.p)));
+                nlive--; wh++;
+                if (wh < wn) head = win[wh]; else head.t = ORLG_INF;
+            }
+            if (side_min <= now) {
+                double m2 = ORLG_INF;
+#pragma unroll
+                for (int s = 0; s < RO_SIDE; s++) {
+                    const double ts = side_t[s * 32];
+                    if (ts <= now) {
+                        const unsigned long long pl = side_p[s * 32];
+                        const int rs = svc_start(pl);
+                        ro_path_update<true>(sm, s_path_lm[svc_row(pl)], bits_range_short(rs, svc_slots(pl)));
+                        side_t[s * 32] = ORLG_INF;
+                        nlive--;
+                    } else {
+                        m2 = dmin(m2, ts);
+                    }
+                }
+                side_min = m2;
+            }
+        }
+        // ---- a table entry is due somewhere in the warp: every lane re-centres its window (rare: ~1 step in 30)
+        if (__any_sync(0xffffffffu, live && tmin_tab <= now)) {
+            if (live) {
+                hzn = now + ra.span;
+                ro_rebuild(ev_t, ev_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn);
+                if (wn) head = win[0]; else head.t = ORLG_INF;
+                while (head.t <= now) {
+                    const int rs = svc_start(head.p);
+                    ro_path_update<true>(sm, s_path_lm[svc_row(head.p)], bits_range_short(rs, svc_slots(head.p)));
+                    nlive--; wh++;
+                    if (wh < wn) head = win[wh]; else head.t = ORLG_INF;
+                }
+            }
+        }
+        if (live) {
+            done = (ep_proc == p.episode_length);
+            if (done && p.auto_reset) { ep_proc = 1; ep_acc = 0; ep_req = br; ep_prov = 0; }      // rmsa_env.py:285-330
+            if (ra.done) ra.done[(size_t)t * p.n + env] = done ? 1 : 0;
+        }
+
+        // ---- an observation tile from the CTA's pool
+        unsigned tile = 0;
+        if (ra.obs) {
+            if (lane == 0) {
+                unsigned got = 0;
+                while (!got) {
+                    const unsigned f = *reinterpret_cast<volatile unsigned *>(pool_free);
+                    if (f) {
+                        const unsigned bit = f & (0u - f);
+                        if (atomicAnd(pool_free, ~bit) & bit) got = bit;
+                    } else {
+                        __nanosleep(40);
+                    }
+                }
+                tile = (unsigned)__ffs(got) - 1u;
+            }
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+        }
+        unsigned char *stage = pool + (size_t)tile * ra.tile_bytes;
+
+        if (live) {
+            // ---- Phase C (deeprmsa_env.py:60-121): free-slot mask of every candidate path, then the block features
+            Bits A[KM];
+#pragma unroll
+            for (int q = 0; q < KM; q++) A[q] = (q < npaths) ? bits_ones() : Bits{{0u, 0u, 0u, 0u}};
+            if (ET > 0) {
+#pragma unroll
+                for (int l = 0; l < (ET > 0 ? ET : 1); l++) {
+                    const uint4 v = sm[l * 32];
+#pragma unroll
+                    for (int q = 0; q < KM; q++)
+                        if (pm[q] & (1u << l)) { A[q].w[0] &= v.x; A[q].w[1] &= v.y; A[q].w[2] &= v.z; A[q].w[3] &= v.w; }
+                }
+            } else {
+                unsigned un = 0;
+#pragma unroll
+                for (int q = 0; q < KM; q++) un |= pm[q];
+                while (un) {
+                    const int l = __ffs(un) - 1;
+                    un &= un - 1;
+                    const uint4 v = sm[l * 32];
+#pragma unroll
+                    for (int q = 0; q < KM; q++)
+                        if (pm[q] & (1u << l)) { A[q].w[0] &= v.x; A[q].w[1] &= v.y; A[q].w[2] &= v.z; A[q].w[3] &= v.w; }
+                }
+            }
+            float *so32 = reinterpret_cast<float *>(stage) + (size_t)lane * p.obs_dim;
+            const bool want_obs = ra.obs != nullptr;
+            if (want_obs) {
+                const int head_n = 1 + 2 * p.N;
+                float2 *r2 = reinterpret_cast<float2 *>(so32);
+                for (int q = 0; q < (head_n + 1) / 2; q++) r2[q] = make_float2(0.0f, 0.0f);
+                so32[0] = __fdiv_rn((float)br, 100.0f);
+                so32[1 + min(src, dst)] = 1.0f; so32[1 + p.N + max(src, dst)] = 1.0f;
+            }
+            unsigned long long cand_out = 0xFFFFFFFFFFFFFFFFULL;
+#pragma unroll
+            for (int q = 0; q < KM; q++) {
+                const int n = ns[q];
+                const Bits B = bits_runs_ge_sched(A[q], s_dbl[n]);
+                const int st = bits_ffs_flat(B);
+                const int fe = bits_ffs_flat(bits_andnot(B, bits_shr1(B)));
+                const int len = fe - st + n;
+                const int total = bits_popc(A[q]);
+                const int runs = bits_popc(bits_andnot(A[q], bits_shl1(A[q])));
+                const bool have = q < npaths;
+                const bool blk = st >= 0;
+                cand_out = blk ? ((cand_out & ~(0xFFULL << (8 * q))) | ((unsigned long long)st << (8 * q))) : cand_out;
+                if (want_obs) {
+                    const int ob = 1 + 2 * p.N + q * 5;
+                    so32[ob] = blk ? s_pos[max(st, 0)] : -1.0f;
+                    so32[ob + 1] = blk ? (float)(len - 8) * 0.125f : -1.0f;
+                    so32[ob + 2] = have ? s_nsl[n] : -1.0f;
+                    so32[ob + 3] = have ? s_pos[total] : -1.0f;
+                    so32[ob + 4] = runs > 0 ? (float)(total - 4 * runs) * s_rcp4[runs] : -1.0f;
+                }
+            }
+            candw = cand_out;
+        }
+        if (ra.obs) {
+            // the warp's 32 rows = one contiguous run of obs[t]: a single bulk store, then the tile goes back to the pool
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            const int row0 = blockIdx.x * blockDim.x + wid * 32;
+            const int rows = min(32, p.n - row0);
+            if (rows > 0) {
+                float *g = ra.obs + ((size_t)t * p.n + row0) * p.obs_dim;
+                const unsigned bytes = (unsigned)(rows * p.obs_dim * 4);
+                if ((reinterpret_cast<size_t>(g) & 15) == 0 && (bytes & 15u) == 0) {
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     ::"l"(g), "r"((unsigned)__cvta_generic_to_shared(stage)), "r"(bytes) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                } else {
+                    const float *sv = reinterpret_cast<const float *>(stage);
+                    for (int q = lane; q < rows * p.obs_dim; q += 32) g[q] = sv[q];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) atomicOr(pool_free, 1u << tile);
+        }
+    }
+
+    // ---------------- state out: canonical form (orlg_device.cuh) for every other entry point
+    if (live) {
+        for (unsigned j = wh; j < wn; j++) {
+            const WinEntry w = win[j];
+            ev_t[n_tab] = w.t; ev_p[n_tab] = w.p; n_tab++;
+        }
+#pragma unroll
+        for (int s = 0; s < RO_SIDE; s++) {
+            const double ts = side_t[s * 32];
+            if (ts < ORLG_INF) { ev_t[n_tab] = ts; ev_p[n_tab] = side_p[s * 32]; n_tab++; }
+        }
+        if (n_tab != nlive) err |= ORLG_ERR_LOCKSTEP;            // internal consistency (never expected)
+        // directory: float lower bound per FULL group below the tail group, +INF from the tail group on
+        float *gmin = p.ev_gmin + (size_t)e * p.ev_groups;
+        const int tail_g = n_tab ? (int)((n_tab - 1) / EV_GROUP) : 0;
+        double all_min = ORLG_INF, tail_min = ORLG_INF;
+        for (int g = 0; g <= tail_g && n_tab; g++) {
+            double m = ORLG_INF;
+#pragma unroll
+            for (int q = 0; q < EV_GROUP / 2; q++) {
+                const double2 v = *reinterpret_cast<const double2 *>(ev_t + g * EV_GROUP + 2 * q);      // slots >= n hold +INF
+                m = dmin(m, dmin(v.x, v.y));
+            }
+            if (g < tail_g) gmin[g] = lower_f32(m); else tail_min = m;
+            all_min = dmin(all_min, g < tail_g ? (double)lower_f32(m) : m);
+        }
+        for (int g = tail_g; g < p.ev_groups; g++) gmin[g] = ORLG_INF_F;
+        uint4 *mw = p.masks + env;
+        for (int l = 0; l < E; l++) mw[(size_t)l * p.n] = sm[l * 32];
+        p.now[env] = now;
+        p.cur_hold[env] = hold;
+        p.cur_req[env] = make_uint2((unsigned)src | ((unsigned)dst << 8) | ((unsigned)br << 16), (unsigned)sid);
+        p.counters[(size_t)0 * p.n + env] += d_proc;
+        p.counters[(size_t)1 * p.n + env] += d_acc;
+        p.counters[(size_t)2 * p.n + env] = ep_proc;
+        p.counters[(size_t)3 * p.n + env] = ep_acc;
+        p.counters[(size_t)4 * p.n + env] += d_req;
+        p.counters[(size_t)5 * p.n + env] += d_prov;
+        p.counters[(size_t)6 * p.n + env] = ep_req;
+        p.counters[(size_t)7 * p.n + env] = ep_prov;
+        p.req_index[env] = ridx;
+        p.nheap[env] = n_tab;
+        p.heap_min[env] = all_min;
+        p.ev_tail[env] = tail_min;
+        p.errors[env] = err;
+        *reinterpret_cast<unsigned long long *>(p.cand + (size_t)env * 8) = candw;
+    }
+}
+
+}  // namespace orlg

@@ -128,6 +128,7 @@ class OpticalVecEnv:
         self.num_envs = int(num_envs)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", self._dev_index)       # always an indexed device: buffers, stream and handle agree
         self.metadata = {"metrics": METRICS[env_id]}
         self.k_paths = t.k_paths
         self.num_spectrum_resources = int(a["num_spectrum_resources"])
@@ -200,7 +201,7 @@ class OpticalVecEnv:
         self._h = C.c_void_p()
         self._closed = False
         with torch.cuda.device(self.device):
-            nat.check(self._lib.orlg_create(C.byref(cfg), C.byref(tab), self.device.index or 0, C.byref(self._h)))
+            nat.check(self._lib.orlg_create(C.byref(cfg), C.byref(tab), self._dev_index, C.byref(self._h)))
         self.action_dim = self._lib.orlg_action_dim(self._h)
         self.obs_dim = self._lib.orlg_obs_dim(self._h)
         self.mask_words = self._lib.orlg_mask_words(self._h)
@@ -334,6 +335,29 @@ class OpticalVecEnv:
         if rc:
             nat.check(rc)
         return self._obs, self._reward, self._done
+
+    def rollout(self, steps: int, policy="random", *, obs=None, reward=None, done=None, actions=None,
+                want_obs: bool = True, want_actions: bool = True):
+        """``steps`` iterations of ``a = policy(env); env.step(a)`` in ONE native call (``orlg_rollout``), every step's
+        results kept: returns ``(obs [T, N, obs_dim] | None, reward [T, N], done [T, N], actions [T, N, action_dim] | None)``.
+        ``policy``: "random" (:meth:`sample_actions`) or a heuristic name (:meth:`heuristic`).  Identical to the
+        step-by-step loop; DeepRMSA-v0 with Philox traffic and float32 observations runs as one persistent kernel."""
+        T, n, dev = int(steps), self.num_envs, self.device
+        pol = -1 if policy in ("random", None) else (nat.HEURISTICS[policy] if isinstance(policy, str) else int(policy))
+        if obs is None and want_obs and self.obs_dim:
+            obs = torch.empty((T, n, self.obs_dim), dtype=self.obs_dtype, device=dev)
+        if reward is None:
+            reward = torch.empty((T, n), dtype=torch.float32, device=dev)
+        if done is None:
+            done = torch.empty((T, n), dtype=torch.uint8, device=dev)
+        if actions is None and want_actions:
+            actions = torch.empty((T, n, self.action_dim), dtype=torch.int32, device=dev)
+        for tns, shape in ((obs, (T, n, self.obs_dim)), (reward, (T, n)), (done, (T, n)), (actions, (T, n, self.action_dim))):
+            if tns is not None:
+                assert tuple(tns.shape) == shape and tns.is_contiguous() and tns.device == dev, (tuple(tns.shape), shape)
+        with torch.cuda.device(self._dev_index):
+            nat.check(self._lib.orlg_rollout(self._h, T, pol, _ptr(obs), _ptr(reward), _ptr(done), _ptr(actions), self._stream()))
+        return obs, reward, done, actions
 
     def observation(self):
         if not self.obs_dim:

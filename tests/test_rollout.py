@@ -1,0 +1,182 @@
+"""GPU parity of the T-steps-per-launch rollout path (orlg_rollout / OpticalVecEnv.rollout):
+bit-for-bit against the step-by-step path on a twin handle, and against the CPU oracle replaying the
+same Philox streams.  The persistent kernel keeps masks / scalars on chip and consults the release-event
+table through a sorted window, so the cases below force every window regime: frequent rebuilds (tiny
+horizon), side-buffer and window-capacity overflow (huge horizon), tile-pool contention, ragged batches,
+and launch boundaries interleaved with ordinary per-step calls (the state must be canonical there)."""
+import numpy as np
+import pytest
+
+import helpers
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+OBS_RTOL = 1e-6      # north_star tolerance for float32 observations
+
+
+def _oracles(kind, tables, n, seed, base=0, **okw):
+    from oracle import oracle
+
+    out = []
+    for i in range(n):
+        o = oracle.OracleEnv(kind, tables, **okw)
+        o.set_philox(seed, base + i)
+        o.reset(full=True)
+        out.append(o)
+    return out
+
+
+def _final_state_equal(a, b):
+    ma, ala, nowa, nha = a.export_state(allocation=True)
+    mb, alb, nowb, nhb = b.export_state(allocation=True)
+    assert torch.equal(ma, mb), "masks"
+    assert torch.equal(ala, alb), "allocation"
+    assert torch.equal(nowa, nowb) and torch.equal(nha, nhb), "clock / live services"
+    assert torch.equal(a.counters(), b.counters()), "counters"
+    ra, sa = a.current_requests()
+    rb, sb = b.current_requests()
+    assert np.array_equal(ra, rb) and np.array_equal(sa, sb), "pending request"
+    assert int(a.error_flags().abs().sum()) == 0 and int(b.error_flags().abs().sum()) == 0
+
+
+@pytest.mark.parametrize("policy,span,warps,tiles", [
+    ("random", None, None, None),          # defaults
+    ("random", "2", None, None),           # horizon of 2 steps: a rebuild almost every step
+    ("random", "100000", None, None),      # horizon beyond every release: window capacity + side buffer overflow paths
+    ("sap", "7", "14", "1"),               # 14 warps share ONE observation tile
+    ("sp", None, "3", "2"),
+])
+def test_rollout_matches_step_path_and_oracle(monkeypatch, policy, span, warps, tiles):
+    from optical_rl_gym_b200 import OpticalVecEnv
+
+    for k, v in (("ORLG_RO_SPAN", span), ("ORLG_RO_WARPS", warps), ("ORLG_RO_TILES", tiles)):
+        if v is not None:
+            monkeypatch.setenv(k, v)
+    tables = helpers.golden_tables()
+    n, seed = 1000 if warps == "14" else 200, 17
+    kw = dict(traffic="philox", seed=seed, episode_length=45, allow_rejection=(policy != "random"))
+    ro = OpticalVecEnv("DeepRMSA-v0", n, tables, **kw)
+    st = OpticalVecEnv("DeepRMSA-v0", n, tables, **kw)
+    pol_id = {"random": 1, "sp": 10, "sap": 11}[policy]
+    n_or = 64
+    orc = _oracles("DeepRMSA-v0", tables, n_or, seed, num_slots=100, episode_length=45, allow_rejection=(policy != "random"))
+
+    def step_path(T):
+        obs, rew, done, act = [], [], [], []
+        for _ in range(T):
+            a = st.sample_actions() if policy == "random" else st.heuristic(policy)
+            o, r, d, _ = st.step(a)
+            obs.append(o.clone()); rew.append(r.clone()); done.append(d.clone()); act.append(a.clone())
+        return torch.stack(obs), torch.stack(rew), torch.stack(done), torch.stack(act)
+
+    for T in (1, 7, 64, 3, 150):
+        o1, r1, d1, a1 = ro.rollout(T, policy)
+        o2, r2, d2, a2 = step_path(T)
+        assert torch.equal(a1, a2), ("actions", T)
+        assert torch.equal(r1, r2) and torch.equal(d1, d2), ("reward / done", T)
+        assert torch.equal(o1, o2), ("observations", T)
+        refs = [o.rollout(T, policy=pol_id, want_obs=True) for o in orc]
+        assert np.array_equal(a1[:, :n_or].cpu().numpy(), np.stack([r["actions"] for r in refs], 1)), ("oracle actions", T)
+        assert np.array_equal(r1[:, :n_or].cpu().numpy().astype(np.float64), np.stack([r["rewards"] for r in refs], 1)), T
+        assert np.array_equal(d1[:, :n_or].cpu().numpy(), np.stack([r["dones"] for r in refs], 1)), T
+        np.testing.assert_allclose(o1[:, :n_or].cpu().numpy(), np.stack([r["obs"] for r in refs], 1), rtol=OBS_RTOL, atol=0)
+        _final_state_equal(ro, st)
+        # a few ordinary steps on both handles between the launches: the rollout left canonical state behind
+        for _ in range(5):
+            a = ro.sample_actions()
+            assert torch.equal(a, st.sample_actions())
+            x, y = ro.step(a), st.step(a)
+            assert torch.equal(x[0], y[0]) and torch.equal(x[1], y[1]) and torch.equal(x[2], y[2])
+        for o in orc:
+            o.rollout(5, policy=1)
+    avail = ro.available_slots().cpu().numpy()
+    for i, o in enumerate(orc):
+        oa, oal, onow, onh = o.state()
+        assert np.array_equal(avail[i].reshape(oa.shape), oa), ("oracle masks", i)
+        assert np.array_equal(ro.counters()[i].cpu().numpy(), o.counters()), ("oracle counters", i)
+    ro.close(); st.close()
+
+
+def test_rollout_without_outputs_and_partial_outputs():
+    from optical_rl_gym_b200 import OpticalVecEnv
+
+    tables = helpers.golden_tables()
+    kw = dict(traffic="philox", seed=3, episode_length=30)
+    a = OpticalVecEnv("DeepRMSA-v0", 97, tables, **kw)
+    b = OpticalVecEnv("DeepRMSA-v0", 97, tables, **kw)
+    o, r, d, act = a.rollout(80)
+    o2, r2, d2, act2 = b.rollout(80, want_obs=False, want_actions=False)
+    assert o2 is None and act2 is None
+    assert torch.equal(r, r2) and torch.equal(d, d2)
+    _final_state_equal(a, b)
+    assert torch.equal(a.observation(), b.observation())
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("kind,env_args,policy", [
+    ("RMSA-v0", dict(episode_length=50, load=250, mean_service_holding_time=25, allow_rejection=True), "sap_ff"),
+    ("RWA-v0", dict(episode_length=64, load=450, mean_service_holding_time=25), "random"),
+    ("DeepRMSA-v0", dict(episode_length=40, j=2), "sap"),          # j = 2: outside the persistent kernel's limits
+])
+def test_generic_rollout_equals_step_loop(kind, env_args, policy):
+    from optical_rl_gym_b200 import OpticalVecEnv
+
+    tables = helpers.golden_tables()
+    kw = dict(traffic="philox", seed=9, **env_args)
+    ro = OpticalVecEnv(kind, 80, tables, **kw)
+    st = OpticalVecEnv(kind, 80, tables, **kw)
+    T = 60
+    o1, r1, d1, a1 = ro.rollout(T, policy)
+    for t in range(T):
+        a = st.sample_actions() if policy == "random" else st.heuristic(policy)
+        o, r, d, _ = st.step(a)
+        assert torch.equal(a1[t], a) and torch.equal(r1[t], r) and torch.equal(d1[t], d), t
+        if o is not None:
+            assert torch.equal(o1[t], o), t
+    _final_state_equal(ro, st)
+    ro.close(); st.close()
+
+
+def test_rollout_full_size_65536_envs_invariants_and_sampled_oracle():
+    """BASELINE configs[2] size through the persistent kernel: conservation invariants over all envs, ~100 sampled
+    envs bit-for-bit against the oracle (masks, allocation, clock, live services, counters), observations within 1e-6."""
+    from optical_rl_gym_b200 import OpticalVecEnv
+    from oracle import oracle
+
+    tables = helpers.golden_tables()
+    n, seed, T = 65536, 21, 1200
+    env = OpticalVecEnv("DeepRMSA-v0", n, tables, seed=seed, episode_length=333)
+    acc = torch.zeros(n, dtype=torch.int64, device="cuda")
+    ndone = torch.zeros(n, dtype=torch.int64, device="cuda")
+    last_obs = None
+    for chunk in (100, 500, 37, 563):
+        o, r, d, a = env.rollout(chunk)
+        acc += (r > 0).sum(0)
+        ndone += d.sum(0)
+        last_obs = o[-1]
+    assert int(env.error_flags().abs().sum()) == 0
+    cnt = env.counters()
+    assert torch.all(cnt[:, 0] == T + 1) and torch.all(cnt[:, 1] == acc)
+    assert torch.all(ndone == T // 332)
+    m, alloc, now, nheap = env.export_state(allocation=True)
+    avail = env.available_slots()
+    assert torch.equal((avail == 0), (alloc.reshape(avail.shape) >= 0))          # busy slots == slots of live services
+    assert torch.equal(last_obs, env.observation())
+    rate = float(acc.sum()) / (n * T)
+    assert 0.3 < rate < 0.4, rate
+    avail = avail.cpu().numpy()
+    cnt = cnt.cpu().numpy()
+    rng = np.random.default_rng(1)
+    for i in sorted(set([0, 1, 31, 32, 447, 448, n - 1] + rng.integers(0, n, 96).tolist())):
+        o = oracle.OracleEnv("DeepRMSA-v0", tables, num_slots=100, episode_length=333)
+        o.set_philox(seed, i)
+        o.reset(full=True)
+        o.rollout(T, policy=1)
+        oa, oal, onow, onh = o.state()
+        assert np.array_equal(avail[i].reshape(oa.shape), oa), ("masks", i)
+        assert np.array_equal(alloc[i].cpu().numpy(), oal), ("allocation", i)
+        assert now[i].item() == onow and nheap[i].item() == onh, ("clock / live services", i)
+        assert np.array_equal(cnt[i], o.counters()), ("counters", i)
+        np.testing.assert_allclose(last_obs[i].cpu().numpy(), o.observation(), rtol=OBS_RTOL, atol=0)
+    env.close()
