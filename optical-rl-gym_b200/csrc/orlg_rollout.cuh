@@ -31,6 +31,22 @@ constexpr int RO_SIDE = 3;             // side-buffer entries per env (shared me
 constexpr int RO_MAX_THREADS = 448;    // 14 warps x 148 SMs >= 65536 envs in one wave
 enum { RO_POLICY_RANDOM = 0, RO_POLICY_SP_FF = 1, RO_POLICY_SAP_FF = 2 };
 
+// optional cycle accounting per warp (instrumented builds: -DORLG_PHASE_TIMING, tools/rollout_phases.py)
+#ifdef ORLG_PHASE_TIMING
+#define RPH_INIT() long long rph_t_ = clock64()
+#define RPH_MARK(k)                                                                                      \
+    do {                                                                                                 \
+        long long rph_n_ = clock64();                                                                    \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase_cycles[k], (unsigned long long)(rph_n_ - rph_t_)); \
+        rph_t_ = rph_n_;                                                                                 \
+    } while (0)
+#define RPH_COUNT(k) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase_cycles[k], 1ULL); } while (0)
+#else
+#define RPH_INIT() do { } while (0)
+#define RPH_MARK(k) do { } while (0)
+#define RPH_COUNT(k) do { } while (0)
+#endif
+
 struct __align__(16) WinEntry {
     double t;
     unsigned long long p;
@@ -142,6 +158,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     unsigned *pool_free = reinterpret_cast<unsigned *>(tab_bar + 1);
 
     pdl_launch_dependents();
+    RPH_INIT();
     // ---------------- tables: one bulk copy per CTA
     if (tid == 0) {
         mbar_init(tab_bar, 1);
@@ -212,6 +229,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     const unsigned k0 = (unsigned)p.seed, k1 = (unsigned)(p.seed >> 32);
     const unsigned n_act = (unsigned)(p.k) + (p.allow_rejection ? 1u : 0u);     // j = 1
 
+    RPH_MARK(8);                     // entry: state in + first window build
     for (int t = 0; t < ra.T; t++) {
         bool done = false;
         int npaths = 0;
@@ -245,6 +263,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                 pm[q] = have ? s_path_lm[row] : 0u;
             }
 
+            RPH_MARK(0);             // request draw
             // ---- the policy's action on the pending request
             int act;
             if (POLICY == RO_POLICY_RANDOM) {                    // orlg_random_actions: Philox stream 2, same counter
@@ -301,6 +320,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             }
             if (ra.reward) ra.reward[(size_t)t * p.n + env] = accepted ? 1.0f : -1.0f;
 
+            RPH_MARK(1);             // action + phase A
             // ---- Phase B: _next_service (rmsa_env.py:545-597)
             now = __dadd_rn(now, e_iat);
             hold = e_hold; src = p_src; dst = p_dst; br = p_br;
@@ -332,8 +352,10 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                 side_min = m2;
             }
         }
+        RPH_MARK(2);                 // phase B + window / side releases
         // ---- a table entry is due somewhere in the warp: every lane re-centres its window (rare: ~1 step in 30)
         if (__any_sync(0xffffffffu, live && tmin_tab <= now)) {
+            RPH_COUNT(15);
             if (live) {
                 hzn = now + ra.span;
                 ro_rebuild(ev_t, ev_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn);
@@ -346,6 +368,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                 }
             }
         }
+        RPH_MARK(3);                 // rebuild
         if (live) {
             done = (ep_proc == p.episode_length);
             if (done && p.auto_reset) { ep_proc = 1; ep_acc = 0; ep_req = br; ep_prov = 0; }      // rmsa_env.py:285-330
@@ -371,6 +394,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             tile = __shfl_sync(0xffffffffu, tile, 0);
         }
         unsigned char *stage = pool + (size_t)tile * ra.tile_bytes;
+        RPH_MARK(4);                 // done + tile acquisition
 
         if (live) {
             // ---- Phase C (deeprmsa_env.py:60-121): free-slot mask of every candidate path, then the block features
@@ -398,6 +422,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                         if (pm[q] & (1u << l)) { A[q].w[0] &= v.x; A[q].w[1] &= v.y; A[q].w[2] &= v.z; A[q].w[3] &= v.w; }
                 }
             }
+            RPH_MARK(5);             // candidate-path AND
             float *so32 = reinterpret_cast<float *>(stage) + (size_t)lane * p.obs_dim;
             const bool want_obs = ra.obs != nullptr;
             if (want_obs) {
@@ -431,6 +456,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             }
             candw = cand_out;
         }
+        RPH_MARK(6);                 // features + observation row
         if (ra.obs) {
             // the warp's 32 rows = one contiguous run of obs[t]: a single bulk store, then the tile goes back to the pool
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -455,6 +481,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             __syncwarp();
             if (lane == 0) atomicOr(pool_free, 1u << tile);
         }
+        RPH_MARK(7);                 // tile store + release
     }
 
     // ---------------- state out: canonical form (orlg_device.cuh) for every other entry point
@@ -504,6 +531,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
         p.errors[env] = err;
         *reinterpret_cast<unsigned long long *>(p.cand + (size_t)env * 8) = candw;
     }
+    RPH_MARK(9);                     // exit: canonical state out
 }
 
 }  // namespace orlg
