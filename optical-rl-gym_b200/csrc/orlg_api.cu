@@ -41,8 +41,6 @@ struct orlg_env {
     int64_t state_bytes;
     std::vector<void *> allocs;
     // T-steps-per-launch rollout path (orlg_rollout.cuh): window / scratch buffers, allocated by the first call
-    double *ro_sc_t = nullptr;
-    unsigned long long *ro_sc_p = nullptr;
     WinEntry *ro_win = nullptr;
     int *ro_actions = nullptr;    // [n, action_dim] scratch of the generic (kernel-per-step) rollout
 };
@@ -800,9 +798,7 @@ int orlg_rollout(orlg_env *env, int steps, int policy, void *obs_dev, float *rew
     if (persistent && rollout_plan(env, &wpc, &ra, &smem)) {
         if (!env->ro_win) {
             const size_t n = (size_t)p.n;
-            int rc = dev_alloc(env, &env->ro_sc_t, n * RO_WCAP, false);
-            if (!rc) rc = dev_alloc(env, &env->ro_sc_p, n * RO_WCAP, false);
-            if (!rc) rc = dev_alloc(env, &env->ro_win, n * RO_WCAP, false);
+            int rc = dev_alloc(env, &env->ro_win, n * RO_WCAP, false);
             if (rc) return rc;
         }
         double span_steps = 40.0;
@@ -811,7 +807,7 @@ int orlg_rollout(orlg_env *env, int steps, int policy, void *obs_dev, float *rew
         ra.span = span_steps * p.mean_iat;
         ra.obs = reinterpret_cast<float *>(obs_dev);
         ra.reward = reward_dev; ra.done = done_dev; ra.actions = actions_dev;
-        ra.sc_t = env->ro_sc_t; ra.sc_p = env->ro_sc_p; ra.win = env->ro_win;
+        ra.win = env->ro_win;
         cudaError_t e = p.E == 22 ? launch_rollout<22>(env, ra, policy, wpc, smem, s) : launch_rollout<0>(env, ra, policy, wpc, smem, s);
         if (e != cudaSuccess) return fail(ORLG_E_CUDA, std::string("rollout launch: ") + cudaGetErrorString(e));
         p.lockstep_ridx += (unsigned)steps;

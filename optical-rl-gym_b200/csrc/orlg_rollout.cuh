@@ -8,15 +8,17 @@
 //     stay in shared memory and the scalar block (clock, pending request, counters, cached block starts)
 //     stays in registers; HBM sees them once at entry and once at exit;
 //   * the release-event table (orlg_device.cuh) is consulted through a per-env WINDOW: every ~span steps the
-//     thread streams its table once, moves the services that expire before a horizon into a small list sorted
-//     by release time (HBM / L2, 16-byte entries) and compacts the rest in place.  A step then only compares
-//     the list head (two registers) with the clock: the directory -> group -> payload fetch chain of the
-//     per-step kernel is gone.  Services accepted with a release time inside the horizon wait in a 3-entry
-//     side buffer in shared memory.  The exact minimum of what is left in the table gates the next rebuild,
-//     so the scheme is exact whatever the horizon (which only tunes how often the table is streamed);
-//     rebuilds are taken by the whole warp together (ballot), thread-per-env, no cross-lane traffic;
+//     warp streams the tables of its 32 envs (one env at a time, all lanes: coalesced 256-byte loads, ballot /
+//     popc compaction), moves the services that expire before a horizon into a small list sorted by release
+//     time (HBM / L2, 16-byte entries) and compacts the rest in place.  A step then only compares the list
+//     head (registers; the following entry is fetched one pop ahead) with the clock: the directory -> group ->
+//     payload fetch chain of the per-step kernel is gone.  Services accepted with a release time inside the
+//     horizon wait in a 3-entry side buffer in shared memory.  The exact minimum of what is left in the table
+//     gates the next rebuild, so the scheme is exact whatever the horizon (which only tunes how often the
+//     tables are streamed);
 //   * the 32 observation rows of a warp are assembled in a shared-memory tile taken from a small per-CTA
-//     pool and leave as ONE bulk (TMA) store per step; the topology tables arrive by one bulk copy per CTA;
+//     pool (held only while the rows are written and copied out with coalesced 16-byte stores); the topology
+//     tables arrive by one bulk (TMA) copy per CTA;
 //   * at exit the window / side entries go back to the table and its directory is rebuilt, so that every
 //     other entry point of the library (per-step kernels, export, heuristics) sees the canonical state.
 // Release order inside a step is irrelevant (masks only); what must be exact is WHICH
@@ -62,8 +64,6 @@ struct RolloutArgs {
     float *reward;               // [T][n]            (NULL: skip)
     unsigned char *done;         // [T][n]            (NULL: skip)
     int *actions;                // [T][n]            (NULL: skip)
-    double *sc_t;                // [n][RO_WCAP] scratch: candidate times
-    unsigned long long *sc_p;    // [n][RO_WCAP] scratch: candidate payloads
     WinEntry *win;               // [n][RO_WCAP] the sorted window
 };
 
@@ -80,62 +80,142 @@ __device__ __forceinline__ void ro_path_update(uint4 *sm, unsigned lm, const Bit
     }
 }
 
-// Thread-per-env window rebuild.  On entry: table = slots [0, n) (unsorted, +INF above), window = win[wh, wn)
-// (sorted), side = up to RO_SIDE entries.  Everything goes back to the table, then one streaming pass moves the
-// entries with time < h to the scratch list and compacts the others in place (forward, stable), and the scratch
-// list is rank-sorted into the window.  Leaves tmin = exact minimum of the table.
-__device__ __forceinline__ void ro_rebuild(double *__restrict__ ev_t, unsigned long long *__restrict__ ev_p,
-                                           double *__restrict__ sc_t, unsigned long long *__restrict__ sc_p,
-                                           WinEntry *__restrict__ win, double *side_t, unsigned long long *side_p,
-                                           unsigned &n, unsigned &wh, unsigned &wn, double &tmin, double &side_min,
-                                           const double h) {
-    for (unsigned j = wh; j < wn; j++) {                // leftover window entries
-        const WinEntry w = win[j];
-        ev_t[n] = w.t; ev_p[n] = w.p; n++;
-    }
-#pragma unroll
-    for (int s = 0; s < RO_SIDE; s++) {                 // side buffer
-        const double t = side_t[s * 32];
-        if (t < ORLG_INF) { ev_t[n] = t; ev_p[n] = side_p[s * 32]; n++; side_t[s * 32] = ORLG_INF; }
-    }
-    side_min = ORLG_INF;
-    unsigned k = 0, c = 0;
-    double mn = ORLG_INF;
-    for (unsigned s0 = 0; s0 < n; s0 += 4) {            // n <= heap_cap (multiple of 16): the vector loads stay inside the table
-        const double2 ta = *reinterpret_cast<const double2 *>(ev_t + s0);
-        const double2 tb = *reinterpret_cast<const double2 *>(ev_t + s0 + 2);
-        const ulonglong2 pa = *reinterpret_cast<const ulonglong2 *>(ev_p + s0);
-        const ulonglong2 pb = *reinterpret_cast<const ulonglong2 *>(ev_p + s0 + 2);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const double t = i == 0 ? ta.x : (i == 1 ? ta.y : (i == 2 ? tb.x : tb.y));
-            const unsigned long long pl = i == 0 ? pa.x : (i == 1 ? pa.y : (i == 2 ? pb.x : pb.y));
-            if (s0 + i < n) {
-                if (t < h && c < (unsigned)RO_WCAP) {
-                    sc_t[c] = t; sc_p[c] = pl; c++;
-                } else {
-                    if (k != s0 + i) { ev_t[k] = t; ev_p[k] = pl; }
-                    k++;
-                    mn = dmin(mn, t);
-                }
+__device__ __forceinline__ WinEntry win_load(const WinEntry *w) {       // L2 (the window is rewritten by other lanes)
+    const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(w));
+    WinEntry e;
+    e.t = __hiloint2double((int)v.y, (int)v.x);
+    e.p = (unsigned long long)v.z | ((unsigned long long)v.w << 32);
+    return e;
+}
+
+// one observation tile out of the CTA's pool (lane 0 spins on the free mask; the index is broadcast)
+__device__ __forceinline__ unsigned ro_tile_acquire(unsigned *pool_free, int lane) {
+    unsigned tile = 0;
+    if (lane == 0) {
+        unsigned got = 0;
+        while (!got) {
+            const unsigned f = *reinterpret_cast<volatile unsigned *>(pool_free);
+            if (f) {
+                const unsigned bit = f & (0u - f);
+                if (atomicAnd(pool_free, ~bit) & bit) got = bit;
+            } else {
+                __nanosleep(32);
             }
         }
+        tile = (unsigned)__ffs(got) - 1u;
     }
-    for (unsigned s = k; s < n; s++) ev_t[s] = ORLG_INF;    // "every slot >= n holds +INF"
-    n = k;
-    tmin = mn;
-    for (unsigned j = 0; j < c; j++) {                  // rank sort (c is ~10: quadratic is fine)
-        const double tj = sc_t[j];
-        unsigned rank = 0;
-        for (unsigned q = 0; q < c; q++) {
-            const double tq = sc_t[q];
-            rank += (tq < tj || (tq == tj && q < j)) ? 1u : 0u;
+    return __shfl_sync(0xffffffffu, tile, 0);
+}
+__device__ __forceinline__ void ro_tile_release(unsigned *pool_free, unsigned tile, int lane) {
+    __syncwarp();
+    if (lane == 0) atomicOr(pool_free, 1u << tile);
+}
+
+__device__ __forceinline__ double warp_min_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = dmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Warp-cooperative window rebuild: for each of the warp's `nvalid` envs in turn, all 32 lanes
+//   * append the env's leftover window entries and its side-buffer entries to its table (coalesced),
+//   * stream the table once: entries with time <= h (at most RO_WCAP of them) go to the scratch list `ct` / `cp`
+//     (shared memory), the others are compacted in place (forward, stable; ballot + popc positions),
+//   * rank-sort the scratch list by time into the env's window in HBM,
+// and the env's owner lane takes the new table size, the exact minimum of the table and the first two window entries.
+// Lane i owns env env0 + i; `hzn` is each lane's NEW horizon.  If more than RO_WCAP entries lie below the horizon the
+// rest stays in the table (the caller retries with a shorter horizon while a table entry is still due).
+__device__ __forceinline__ void ro_rebuild_warp(const Params &p, const RolloutArgs &ra, const int env0, const int nvalid, const int lane,
+                                                unsigned char *scratch, double *side_t0, unsigned long long *side_p0,
+                                                unsigned &n_tab, unsigned &wh, unsigned &wn, double &tmin_tab, double &side_min,
+                                                const double hzn, WinEntry &head, WinEntry &nxt) {
+    double *ct = reinterpret_cast<double *>(scratch);                              // [RO_WCAP]
+    unsigned long long *cp = reinterpret_cast<unsigned long long *>(scratch + RO_WCAP * 8);   // [RO_WCAP]
+    WinEntry *first2 = reinterpret_cast<WinEntry *>(scratch + RO_WCAP * 16);       // ranks 0 and 1
+    const unsigned lt = (1u << lane) - 1u;
+    __syncwarp();
+    for (int i = 0; i < nvalid; i++) {
+        unsigned n_i = __shfl_sync(0xffffffffu, n_tab, i);
+        const unsigned wh_i = __shfl_sync(0xffffffffu, wh, i), wn_i = __shfl_sync(0xffffffffu, wn, i);
+        const double h_i = __shfl_sync(0xffffffffu, hzn, i);
+        double *ev_t = p.ev_time + (size_t)(env0 + i) * p.heap_cap;
+        unsigned long long *ev_p = p.ev_pay + (size_t)(env0 + i) * p.heap_cap;
+        WinEntry *win = ra.win + (size_t)(env0 + i) * RO_WCAP;
+        if (i + 1 < nvalid) {            // warm L2 with the next env's table while this one is processed
+            const unsigned n_n = __shfl_sync(0xffffffffu, n_tab, i + 1);
+            for (unsigned off = lane * 16; off < n_n; off += 512) {
+                prefetch_l2(ev_t + p.heap_cap + off);
+                prefetch_l2(ev_p + p.heap_cap + off);
+            }
         }
-        WinEntry w;
-        w.t = tj; w.p = sc_p[j];
-        win[rank] = w;
+        for (unsigned j = wh_i + lane; j < wn_i; j += 32) {           // leftover window entries -> table
+            const WinEntry w = win_load(win + j);
+            ev_t[n_i + j - wh_i] = w.t; ev_p[n_i + j - wh_i] = w.p;
+        }
+        n_i += wn_i - wh_i;
+        {                                                             // side buffer -> table
+            double ts = ORLG_INF;
+            if (lane < RO_SIDE) ts = side_t0[lane * 32 + i];
+            const bool v = ts < ORLG_INF;
+            const unsigned m = __ballot_sync(0xffffffffu, v);
+            if (v) {
+                const unsigned pos = n_i + __popc(m & lt);
+                ev_t[pos] = ts; ev_p[pos] = side_p0[lane * 32 + i];
+                side_t0[lane * 32 + i] = ORLG_INF;
+            }
+            n_i += __popc(m);
+        }
+        __syncwarp();                                                 // the appended entries are read back below (L2)
+        unsigned k = 0, cnt = 0;
+        double mn = ORLG_INF;
+        for (unsigned c0 = 0; c0 < n_i; c0 += 32) {
+            const unsigned s = c0 + lane;
+            const bool in = s < n_i;
+            const double t = in ? __ldcg(ev_t + s) : ORLG_INF;
+            const unsigned long long pl = in ? __ldcg(ev_p + s) : 0ULL;
+            const bool sel = in && t <= h_i;
+            const unsigned msel = __ballot_sync(0xffffffffu, sel);
+            const unsigned r_sel = __popc(msel & lt);
+            const bool take = sel && (cnt + r_sel < (unsigned)RO_WCAP);     // window full: the rest stays in the table
+            const bool keep = in && !take;
+            const unsigned mtake = __ballot_sync(0xffffffffu, take), mkeep = __ballot_sync(0xffffffffu, keep);
+            if (take) { ct[cnt + r_sel] = t; cp[cnt + r_sel] = pl; }
+            if (keep) {
+                const unsigned idx = k + __popc(mkeep & lt);
+                if (idx != s) { ev_t[idx] = t; ev_p[idx] = pl; }
+                mn = dmin(mn, t);
+            }
+            cnt += __popc(mtake); k += __popc(mkeep);
+        }
+        for (unsigned s = k + lane; s < n_i; s += 32) ev_t[s] = ORLG_INF;       // "every slot >= n holds +INF"
+        mn = warp_min_f64(mn);
+        __syncwarp();
+        for (unsigned j = lane; j < cnt; j += 32) {                  // rank sort (cnt ~ 15)
+            const double tj = ct[j];
+            unsigned rank = 0;
+            for (unsigned q = 0; q < cnt; q++) {
+                const double tq = ct[q];
+                rank += (tq < tj || (tq == tj && q < j)) ? 1u : 0u;
+            }
+            WinEntry w;
+            w.t = tj; w.p = cp[j];
+            win[rank] = w;
+            if (rank < 2) first2[rank] = w;
+        }
+        __syncwarp();
+        if (lane == i) {
+            n_tab = k; wh = 0; wn = cnt; tmin_tab = mn; side_min = ORLG_INF;
+            head.t = ORLG_INF; nxt.t = ORLG_INF;
+            if (cnt > 0) head = first2[0];
+            if (cnt > 1) nxt = first2[1];
+        }
+        __syncwarp();
     }
-    wh = 0; wn = c;
+}
+
+// packed integer pre-image of one path's features: start (7, 127 = no block) | length (7) | total free (7) | free runs (6) | slots (5)
+__device__ __forceinline__ unsigned feat_pack(int st, int len, int total, int runs, int n) {
+    return (unsigned)(st < 0 ? 127 : st) | ((unsigned)(len & 127) << 7) | ((unsigned)total << 14) | ((unsigned)runs << 21) | ((unsigned)n << 27);
 }
 
 template <int ET, int POLICY>
@@ -145,14 +225,18 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int wpc = blockDim.x >> 5;
-    const int env = blockIdx.x * blockDim.x + tid;
+    const int env0 = blockIdx.x * blockDim.x + wid * 32;           // first env of this warp
+    const int env = env0 + lane;
     const bool live = env < p.n;
+    const int nvalid = min(32, p.n - env0);
     const int e = live ? env : p.n - 1;
     const int E = ET > 0 ? ET : p.E;
     unsigned char *warp_area = smem + p.tab_vec * 16 + (size_t)wid * ra.warp_bytes;
     uint4 *sm = reinterpret_cast<uint4 *>(warp_area) + lane;                                   // masks: sm[l * 32]
-    double *side_t = reinterpret_cast<double *>(warp_area + (size_t)E * 512) + lane;           // side_t[s * 32]
-    unsigned long long *side_p = reinterpret_cast<unsigned long long *>(warp_area + (size_t)E * 512 + RO_SIDE * 256) + lane;
+    double *side_t0 = reinterpret_cast<double *>(warp_area + (size_t)E * 512);                 // [RO_SIDE][32 lanes]
+    unsigned long long *side_p0 = reinterpret_cast<unsigned long long *>(warp_area + (size_t)E * 512 + RO_SIDE * 256);
+    double *side_t = side_t0 + lane;
+    unsigned long long *side_p = side_p0 + lane;
     unsigned char *pool = smem + p.tab_vec * 16 + (size_t)wpc * ra.warp_bytes;
     unsigned long long *tab_bar = reinterpret_cast<unsigned long long *>(pool + (size_t)ra.pool_tiles * ra.tile_bytes);
     unsigned *pool_free = reinterpret_cast<unsigned *>(tab_bar + 1);
@@ -205,29 +289,39 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     unsigned long long candw = *reinterpret_cast<const unsigned long long *>(p.cand + (size_t)e * 8);
     double *const ev_t = p.ev_time + (size_t)e * p.heap_cap;
     unsigned long long *const ev_p = p.ev_pay + (size_t)e * p.heap_cap;
-    double *const sc_t = ra.sc_t + (size_t)e * RO_WCAP;
-    unsigned long long *const sc_p = ra.sc_p + (size_t)e * RO_WCAP;
-    WinEntry *const win = ra.win + (size_t)e * RO_WCAP;
+    const WinEntry *const win = ra.win + (size_t)e * RO_WCAP;
 #pragma unroll
     for (int s = 0; s < RO_SIDE; s++) side_t[s * 32] = ORLG_INF;
     if (ridx != p.lockstep_ridx) err |= ORLG_ERR_LOCKSTEP;
     unsigned wh = 0, wn = 0;
     double tmin_tab = ORLG_INF, side_min = ORLG_INF, hzn = now + ra.span;
-    WinEntry head;
-    head.t = ORLG_INF; head.p = 0;
-    if (live) {
-        ro_rebuild(ev_t, ev_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn);
-        if (wn) head = win[0];
-    }
+    WinEntry head, nxt;
+    head.t = ORLG_INF; head.p = 0; nxt.t = ORLG_INF; nxt.p = 0;
     cp_async_wait<0>();
     __syncthreads();                 // pool word + table barrier initialised by thread 0 ...
     mbar_wait(tab_bar, 0);           // ... and the tables have landed
-    if (blockIdx.x * blockDim.x + wid * 32 >= p.n) return;              // a warp without environments (no CTA-wide barrier below)
+    if (env0 >= p.n) return;         // a warp without environments (no CTA-wide barrier below)
+    {
+        const unsigned tile = ro_tile_acquire(pool_free, lane);
+        ro_rebuild_warp(p, ra, env0, nvalid, lane, pool + (size_t)tile * ra.tile_bytes, side_t0, side_p0,
+                        n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt);
+        ro_tile_release(pool_free, tile, lane);
+    }
     int npaths_cur = min((int)s_pair_count[src * p.N + dst], KM);       // candidate paths of the pending request
 
     const unsigned long long gid = (unsigned long long)(p.env_id_base + e);
     const unsigned k0 = (unsigned)p.seed, k1 = (unsigned)(p.seed >> 32);
     const unsigned n_act = (unsigned)(p.k) + (p.allow_rejection ? 1u : 0u);     // j = 1
+
+    // release of the window head; the entry after it was requested one pop earlier
+#define RO_POP_DUE()                                                                                              \
+    while (head.t <= now) {                                                                                      \
+        const int rs_ = svc_start(head.p);                                                                       \
+        ro_path_update<true>(sm, s_path_lm[svc_row(head.p)], bits_range_short(rs_, svc_slots(head.p)));          \
+        nlive--; wh++;                                                                                           \
+        head = nxt;                                                                                              \
+        if (wh + 1 < wn) nxt = win_load(win + wh + 1); else nxt.t = ORLG_INF;                                    \
+    }
 
     RPH_MARK(8);                     // entry: state in + first window build
     for (int t = 0; t < ra.T; t++) {
@@ -296,7 +390,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                             const double rel = __dadd_rn(now, hold);
                             const unsigned long long pl = pack_service(a_row, (int)st, a_n, 0, sid);
                             bool in_side = false;
-                            if (rel < hzn) {                     // expires inside the window: side buffer
+                            if (rel <= hzn) {                    // expires inside the window: side buffer
 #pragma unroll
                                 for (int s = 0; s < RO_SIDE; s++) {
                                     if (!in_side && !(side_t[s * 32] < ORLG_INF)) {
@@ -328,12 +422,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             sid = ep_proc;
             d_proc += 1; ep_proc += 1; d_req += br; ep_req += br;
             npaths_cur = npaths;
-            while (head.t <= now) {                              // sorted window: the head is the earliest
-                const int rs = svc_start(head.p);
-                ro_path_update<true>(sm, s_path_lm[svc_row(head.p)], bits_range_short(rs, svc_slots(head.p)));
-                nlive--; wh++;
-                if (wh < wn) head = win[wh]; else head.t = ORLG_INF;
-            }
+            RO_POP_DUE();
             if (side_min <= now) {
                 double m2 = ORLG_INF;
 #pragma unroll
@@ -353,20 +442,16 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             }
         }
         RPH_MARK(2);                 // phase B + window / side releases
-        // ---- a table entry is due somewhere in the warp: every lane re-centres its window (rare: ~1 step in 30)
-        if (__any_sync(0xffffffffu, live && tmin_tab <= now)) {
+        // ---- a table entry is due somewhere in the warp: every lane re-centres its window (~1 step in 30)
+        for (int tries = 0; __any_sync(0xffffffffu, live && tmin_tab <= now); tries++) {
             RPH_COUNT(15);
-            if (live) {
-                hzn = now + ra.span;
-                ro_rebuild(ev_t, ev_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn);
-                if (wn) head = win[0]; else head.t = ORLG_INF;
-                while (head.t <= now) {
-                    const int rs = svc_start(head.p);
-                    ro_path_update<true>(sm, s_path_lm[svc_row(head.p)], bits_range_short(rs, svc_slots(head.p)));
-                    nlive--; wh++;
-                    if (wh < wn) head = win[wh]; else head.t = ORLG_INF;
-                }
-            }
+            // a retry means the window filled up before every due service was reached: shorter horizon, down to the clock itself
+            hzn = tries < 60 ? __dadd_rn(now, __dmul_rn(ra.span, __longlong_as_double((long long)(1023 - tries) << 52))) : now;
+            const unsigned tile = ro_tile_acquire(pool_free, lane);
+            ro_rebuild_warp(p, ra, env0, nvalid, lane, pool + (size_t)tile * ra.tile_bytes, side_t0, side_p0,
+                            n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt);
+            ro_tile_release(pool_free, tile, lane);
+            if (live) { RO_POP_DUE(); }
         }
         RPH_MARK(3);                 // rebuild
         if (live) {
@@ -375,29 +460,11 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             if (ra.done) ra.done[(size_t)t * p.n + env] = done ? 1 : 0;
         }
 
-        // ---- an observation tile from the CTA's pool
-        unsigned tile = 0;
-        if (ra.obs) {
-            if (lane == 0) {
-                unsigned got = 0;
-                while (!got) {
-                    const unsigned f = *reinterpret_cast<volatile unsigned *>(pool_free);
-                    if (f) {
-                        const unsigned bit = f & (0u - f);
-                        if (atomicAnd(pool_free, ~bit) & bit) got = bit;
-                    } else {
-                        __nanosleep(40);
-                    }
-                }
-                tile = (unsigned)__ffs(got) - 1u;
-            }
-            tile = __shfl_sync(0xffffffffu, tile, 0);
-        }
-        unsigned char *stage = pool + (size_t)tile * ra.tile_bytes;
-        RPH_MARK(4);                 // done + tile acquisition
-
+        // ---- Phase C (deeprmsa_env.py:60-121): free-slot mask of every candidate path, then the block features
+        unsigned feat[KM];
+#pragma unroll
+        for (int q = 0; q < KM; q++) feat[q] = 0;
         if (live) {
-            // ---- Phase C (deeprmsa_env.py:60-121): free-slot mask of every candidate path, then the block features
             Bits A[KM];
 #pragma unroll
             for (int q = 0; q < KM; q++) A[q] = (q < npaths) ? bits_ones() : Bits{{0u, 0u, 0u, 0u}};
@@ -423,15 +490,6 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                 }
             }
             RPH_MARK(5);             // candidate-path AND
-            float *so32 = reinterpret_cast<float *>(stage) + (size_t)lane * p.obs_dim;
-            const bool want_obs = ra.obs != nullptr;
-            if (want_obs) {
-                const int head_n = 1 + 2 * p.N;
-                float2 *r2 = reinterpret_cast<float2 *>(so32);
-                for (int q = 0; q < (head_n + 1) / 2; q++) r2[q] = make_float2(0.0f, 0.0f);
-                so32[0] = __fdiv_rn((float)br, 100.0f);
-                so32[1 + min(src, dst)] = 1.0f; so32[1 + p.N + max(src, dst)] = 1.0f;
-            }
             unsigned long long cand_out = 0xFFFFFFFFFFFFFFFFULL;
 #pragma unroll
             for (int q = 0; q < KM; q++) {
@@ -439,55 +497,63 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                 const Bits B = bits_runs_ge_sched(A[q], s_dbl[n]);
                 const int st = bits_ffs_flat(B);
                 const int fe = bits_ffs_flat(bits_andnot(B, bits_shr1(B)));
-                const int len = fe - st + n;
                 const int total = bits_popc(A[q]);
                 const int runs = bits_popc(bits_andnot(A[q], bits_shl1(A[q])));
-                const bool have = q < npaths;
-                const bool blk = st >= 0;
-                cand_out = blk ? ((cand_out & ~(0xFFULL << (8 * q))) | ((unsigned long long)st << (8 * q))) : cand_out;
-                if (want_obs) {
-                    const int ob = 1 + 2 * p.N + q * 5;
-                    so32[ob] = blk ? s_pos[max(st, 0)] : -1.0f;
-                    so32[ob + 1] = blk ? (float)(len - 8) * 0.125f : -1.0f;
-                    so32[ob + 2] = have ? s_nsl[n] : -1.0f;
-                    so32[ob + 3] = have ? s_pos[total] : -1.0f;
-                    so32[ob + 4] = runs > 0 ? (float)(total - 4 * runs) * s_rcp4[runs] : -1.0f;
-                }
+                cand_out = st >= 0 ? ((cand_out & ~(0xFFULL << (8 * q))) | ((unsigned long long)st << (8 * q))) : cand_out;
+                feat[q] = feat_pack(st, fe - st + n, total, runs, n);
             }
             candw = cand_out;
         }
-        RPH_MARK(6);                 // features + observation row
+        RPH_MARK(6);                 // features
         if (ra.obs) {
-            // the warp's 32 rows = one contiguous run of obs[t]: a single bulk store, then the tile goes back to the pool
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            const int row0 = blockIdx.x * blockDim.x + wid * 32;
-            const int rows = min(32, p.n - row0);
-            if (rows > 0) {
-                float *g = ra.obs + ((size_t)t * p.n + row0) * p.obs_dim;
-                const unsigned bytes = (unsigned)(rows * p.obs_dim * 4);
-                if ((reinterpret_cast<size_t>(g) & 15) == 0 && (bytes & 15u) == 0) {
-                    if (lane == 0) {
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                     ::"l"(g), "r"((unsigned)__cvta_generic_to_shared(stage)), "r"(bytes) : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    }
-                } else {
-                    const float *sv = reinterpret_cast<const float *>(stage);
-                    for (int q = lane; q < rows * p.obs_dim; q += 32) g[q] = sv[q];
+            // ---- the warp's 32 rows = one contiguous run of obs[t]: written to a pool tile, copied out with coalesced 16-byte stores
+            const unsigned tile = ro_tile_acquire(pool_free, lane);
+            unsigned char *stage = pool + (size_t)tile * ra.tile_bytes;
+            RPH_MARK(4);             // tile acquisition
+            if (live) {
+                float *so32 = reinterpret_cast<float *>(stage) + (size_t)lane * p.obs_dim;
+                const int head_n = 1 + 2 * p.N;
+                float2 *r2 = reinterpret_cast<float2 *>(so32);
+                for (int q = 0; q < (head_n + 1) / 2; q++) r2[q] = make_float2(0.0f, 0.0f);
+                so32[0] = __fdiv_rn((float)br, 100.0f);
+                so32[1 + min(src, dst)] = 1.0f; so32[1 + p.N + max(src, dst)] = 1.0f;
+#pragma unroll
+                for (int q = 0; q < KM; q++) {
+                    const unsigned f = feat[q];
+                    const int st = (int)(f & 127u), len = (int)((f >> 7) & 127u), total = (int)((f >> 14) & 127u);
+                    const int runs = (int)((f >> 21) & 63u), n = (int)(f >> 27);
+                    const bool have = q < npaths, blk = st != 127;
+                    const int ob = head_n + q * 5;
+                    so32[ob] = blk ? s_pos[blk ? st : 0] : -1.0f;
+                    so32[ob + 1] = blk ? (float)(len - 8) * 0.125f : -1.0f;
+                    so32[ob + 2] = have ? s_nsl[n] : -1.0f;
+                    so32[ob + 3] = have ? s_pos[total] : -1.0f;
+                    so32[ob + 4] = runs > 0 ? (float)(total - 4 * runs) * s_rcp4[runs] : -1.0f;   // x * fl(1/y): <= 1.5 ulp
                 }
             }
             __syncwarp();
-            if (lane == 0) atomicOr(pool_free, 1u << tile);
+            {
+                float *g = ra.obs + ((size_t)t * p.n + env0) * p.obs_dim;
+                const int total_el = nvalid * p.obs_dim;
+                if ((reinterpret_cast<size_t>(g) & 15) == 0 && (total_el & 3) == 0) {
+                    const uint4 *sv = reinterpret_cast<const uint4 *>(stage);
+                    uint4 *gv = reinterpret_cast<uint4 *>(g);
+                    for (int q = lane; q < total_el / 4; q += 32) gv[q] = sv[q];
+                } else {
+                    const float *sv = reinterpret_cast<const float *>(stage);
+                    for (int q = lane; q < total_el; q += 32) g[q] = sv[q];
+                }
+            }
+            ro_tile_release(pool_free, tile, lane);
         }
-        RPH_MARK(7);                 // tile store + release
+        RPH_MARK(7);                 // observation rows: tile write + copy out
     }
+#undef RO_POP_DUE
 
     // ---------------- state out: canonical form (orlg_device.cuh) for every other entry point
     if (live) {
         for (unsigned j = wh; j < wn; j++) {
-            const WinEntry w = win[j];
+            const WinEntry w = win_load(win + j);
             ev_t[n_tab] = w.t; ev_p[n_tab] = w.p; n_tab++;
         }
 #pragma unroll
