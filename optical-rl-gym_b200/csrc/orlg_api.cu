@@ -42,6 +42,8 @@ struct orlg_env {
     std::vector<void *> allocs;
     // T-steps-per-launch rollout path (orlg_rollout.cuh): window / scratch buffers, allocated by the first call
     WinEntry *ro_win = nullptr;
+    double *ro_sc_t = nullptr, *ro_rt_t = nullptr;
+    unsigned long long *ro_sc_p = nullptr, *ro_rt_p = nullptr;
     int *ro_actions = nullptr;    // [n, action_dim] scratch of the generic (kernel-per-step) rollout
 };
 
@@ -798,7 +800,12 @@ int orlg_rollout(orlg_env *env, int steps, int policy, void *obs_dev, float *rew
     if (persistent && rollout_plan(env, &wpc, &ra, &smem)) {
         if (!env->ro_win) {
             const size_t n = (size_t)p.n;
-            int rc = dev_alloc(env, &env->ro_win, n * RO_WCAP, false);
+            const size_t warps = (n + 31) / 32;
+            int rc = dev_alloc(env, &env->ro_win, warps * 32 * RO_WCAP, false);
+            if (!rc) rc = dev_alloc(env, &env->ro_sc_t, warps * 32 * RO_WCAP, false);
+            if (!rc) rc = dev_alloc(env, &env->ro_sc_p, warps * 32 * RO_WCAP, false);
+            if (!rc) rc = dev_alloc(env, &env->ro_rt_t, warps * 32 * (size_t)p.heap_cap, false);
+            if (!rc) rc = dev_alloc(env, &env->ro_rt_p, warps * 32 * (size_t)p.heap_cap, false);
             if (rc) return rc;
         }
         double span_steps = 40.0;
@@ -807,7 +814,7 @@ int orlg_rollout(orlg_env *env, int steps, int policy, void *obs_dev, float *rew
         ra.span = span_steps * p.mean_iat;
         ra.obs = reinterpret_cast<float *>(obs_dev);
         ra.reward = reward_dev; ra.done = done_dev; ra.actions = actions_dev;
-        ra.win = env->ro_win;
+        ra.win = env->ro_win; ra.sc_t = env->ro_sc_t; ra.sc_p = env->ro_sc_p; ra.rt_t = env->ro_rt_t; ra.rt_p = env->ro_rt_p;
         cudaError_t e = p.E == 22 ? launch_rollout<22>(env, ra, policy, wpc, smem, s) : launch_rollout<0>(env, ra, policy, wpc, smem, s);
         if (e != cudaSuccess) return fail(ORLG_E_CUDA, std::string("rollout launch: ") + cudaGetErrorString(e));
         p.lockstep_ridx += (unsigned)steps;

@@ -7,15 +7,16 @@
 //   * a warp owns 32 consecutive envs for the whole launch: their link masks ([link][lane] uint4, E x 512 B)
 //     stay in shared memory and the scalar block (clock, pending request, counters, cached block starts)
 //     stays in registers; HBM sees them once at entry and once at exit;
-//   * the release-event table (orlg_device.cuh) is consulted through a per-env WINDOW: every ~span steps the
-//     warp streams the tables of its 32 envs (one env at a time, all lanes: coalesced 256-byte loads, ballot /
-//     popc compaction), moves the services that expire before a horizon into a small list sorted by release
-//     time (HBM / L2, 16-byte entries) and compacts the rest in place.  A step then only compares the list
-//     head (registers; the following entry is fetched one pop ahead) with the clock: the directory -> group ->
-//     payload fetch chain of the per-step kernel is gone.  Services accepted with a release time inside the
-//     horizon wait in a 3-entry side buffer in shared memory.  The exact minimum of what is left in the table
-//     gates the next rebuild, so the scheme is exact whatever the horizon (which only tunes how often the
-//     tables are streamed);
+//   * for the duration of the launch the release-event tables of the warp's 32 envs are held LANE-INTERLEAVED
+//     ([slot][lane], copied in at entry and back at exit), so that a thread-per-env pass over "slot s of every
+//     env" is one coalesced access.  The table is consulted through a per-env WINDOW: every ~span steps each
+//     thread streams its table once, moves the services that expire before a horizon into a small list sorted
+//     by release time (HBM / L2, 16-byte entries) and compacts the rest in place.  A step then only compares
+//     the list head (registers; the following entry is fetched one pop ahead) with the clock: the directory ->
+//     group -> payload fetch chain of the per-step kernel is gone.  Services accepted with a release time
+//     inside the horizon wait in a 3-entry side buffer in shared memory.  The exact minimum of what is left in
+//     the table gates the next rebuild, so the scheme is exact whatever the horizon (which only tunes how
+//     often the tables are streamed); rebuilds are taken by the whole warp together (ballot);
 //   * the 32 observation rows of a warp are assembled in a shared-memory tile taken from a small per-CTA
 //     pool (held only while the rows are written and copied out with coalesced 16-byte stores); the topology
 //     tables arrive by one bulk (TMA) copy per CTA;
@@ -64,7 +65,12 @@ struct RolloutArgs {
     float *reward;               // [T][n]            (NULL: skip)
     unsigned char *done;         // [T][n]            (NULL: skip)
     int *actions;                // [T][n]            (NULL: skip)
-    WinEntry *win;               // [n][RO_WCAP] the sorted window
+    // launch-private event storage, lane-interleaved per warp of 32 envs: element (slot s, lane) of warp w at (w * cap + s) * 32 + lane
+    double *rt_t;                // [warps][heap_cap][32]  table: release times
+    unsigned long long *rt_p;    // [warps][heap_cap][32]  table: packed services
+    double *sc_t;                // [warps][RO_WCAP][32]   rebuild scratch: candidate times
+    unsigned long long *sc_p;    // [warps][RO_WCAP][32]   rebuild scratch: candidate payloads
+    WinEntry *win;               // [warps][RO_WCAP][32]   the sorted window
 };
 
 // apply a release / an allocation to the path's links in the warp's shared-memory mask tile
@@ -111,106 +117,67 @@ __device__ __forceinline__ void ro_tile_release(unsigned *pool_free, unsigned ti
     if (lane == 0) atomicOr(pool_free, 1u << tile);
 }
 
-__device__ __forceinline__ double warp_min_f64(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = dmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
-// Warp-cooperative window rebuild: for each of the warp's `nvalid` envs in turn, all 32 lanes
-//   * append the env's leftover window entries and its side-buffer entries to its table (coalesced),
-//   * stream the table once: entries with time <= h (at most RO_WCAP of them) go to the scratch list `ct` / `cp`
-//     (shared memory), the others are compacted in place (forward, stable; ballot + popc positions),
-//   * rank-sort the scratch list by time into the env's window in HBM,
-// and the env's owner lane takes the new table size, the exact minimum of the table and the first two window entries.
-// Lane i owns env env0 + i; `hzn` is each lane's NEW horizon.  If more than RO_WCAP entries lie below the horizon the
-// rest stays in the table (the caller retries with a shorter horizon while a table entry is still due).
-__device__ __forceinline__ void ro_rebuild_warp(const Params &p, const RolloutArgs &ra, const int env0, const int nvalid, const int lane,
-                                                unsigned char *scratch, double *side_t0, unsigned long long *side_p0,
-                                                unsigned &n_tab, unsigned &wh, unsigned &wn, double &tmin_tab, double &side_min,
-                                                const double hzn, WinEntry &head, WinEntry &nxt) {
-    double *ct = reinterpret_cast<double *>(scratch);                              // [RO_WCAP]
-    unsigned long long *cp = reinterpret_cast<unsigned long long *>(scratch + RO_WCAP * 8);   // [RO_WCAP]
-    WinEntry *first2 = reinterpret_cast<WinEntry *>(scratch + RO_WCAP * 16);       // ranks 0 and 1
-    const unsigned lt = (1u << lane) - 1u;
-    __syncwarp();
-    for (int i = 0; i < nvalid; i++) {
-        unsigned n_i = __shfl_sync(0xffffffffu, n_tab, i);
-        const unsigned wh_i = __shfl_sync(0xffffffffu, wh, i), wn_i = __shfl_sync(0xffffffffu, wn, i);
-        const double h_i = __shfl_sync(0xffffffffu, hzn, i);
-        double *ev_t = p.ev_time + (size_t)(env0 + i) * p.heap_cap;
-        unsigned long long *ev_p = p.ev_pay + (size_t)(env0 + i) * p.heap_cap;
-        WinEntry *win = ra.win + (size_t)(env0 + i) * RO_WCAP;
-        if (i + 1 < nvalid) {            // warm L2 with the next env's table while this one is processed
-            const unsigned n_n = __shfl_sync(0xffffffffu, n_tab, i + 1);
-            for (unsigned off = lane * 16; off < n_n; off += 512) {
-                prefetch_l2(ev_t + p.heap_cap + off);
-                prefetch_l2(ev_p + p.heap_cap + off);
-            }
-        }
-        for (unsigned j = wh_i + lane; j < wn_i; j += 32) {           // leftover window entries -> table
-            const WinEntry w = win_load(win + j);
-            ev_t[n_i + j - wh_i] = w.t; ev_p[n_i + j - wh_i] = w.p;
-        }
-        n_i += wn_i - wh_i;
-        {                                                             // side buffer -> table
-            double ts = ORLG_INF;
-            if (lane < RO_SIDE) ts = side_t0[lane * 32 + i];
-            const bool v = ts < ORLG_INF;
-            const unsigned m = __ballot_sync(0xffffffffu, v);
-            if (v) {
-                const unsigned pos = n_i + __popc(m & lt);
-                ev_t[pos] = ts; ev_p[pos] = side_p0[lane * 32 + i];
-                side_t0[lane * 32 + i] = ORLG_INF;
-            }
-            n_i += __popc(m);
-        }
-        __syncwarp();                                                 // the appended entries are read back below (L2)
-        unsigned k = 0, cnt = 0;
-        double mn = ORLG_INF;
-        for (unsigned c0 = 0; c0 < n_i; c0 += 32) {
-            const unsigned s = c0 + lane;
-            const bool in = s < n_i;
-            const double t = in ? __ldcg(ev_t + s) : ORLG_INF;
-            const unsigned long long pl = in ? __ldcg(ev_p + s) : 0ULL;
-            const bool sel = in && t <= h_i;
-            const unsigned msel = __ballot_sync(0xffffffffu, sel);
-            const unsigned r_sel = __popc(msel & lt);
-            const bool take = sel && (cnt + r_sel < (unsigned)RO_WCAP);     // window full: the rest stays in the table
-            const bool keep = in && !take;
-            const unsigned mtake = __ballot_sync(0xffffffffu, take), mkeep = __ballot_sync(0xffffffffu, keep);
-            if (take) { ct[cnt + r_sel] = t; cp[cnt + r_sel] = pl; }
-            if (keep) {
-                const unsigned idx = k + __popc(mkeep & lt);
-                if (idx != s) { ev_t[idx] = t; ev_p[idx] = pl; }
-                mn = dmin(mn, t);
-            }
-            cnt += __popc(mtake); k += __popc(mkeep);
-        }
-        for (unsigned s = k + lane; s < n_i; s += 32) ev_t[s] = ORLG_INF;       // "every slot >= n holds +INF"
-        mn = warp_min_f64(mn);
-        __syncwarp();
-        for (unsigned j = lane; j < cnt; j += 32) {                  // rank sort (cnt ~ 15)
-            const double tj = ct[j];
-            unsigned rank = 0;
-            for (unsigned q = 0; q < cnt; q++) {
-                const double tq = ct[q];
-                rank += (tq < tj || (tq == tj && q < j)) ? 1u : 0u;
-            }
-            WinEntry w;
-            w.t = tj; w.p = cp[j];
-            win[rank] = w;
-            if (rank < 2) first2[rank] = w;
-        }
-        __syncwarp();
-        if (lane == i) {
-            n_tab = k; wh = 0; wn = cnt; tmin_tab = mn; side_min = ORLG_INF;
-            head.t = ORLG_INF; nxt.t = ORLG_INF;
-            if (cnt > 0) head = first2[0];
-            if (cnt > 1) nxt = first2[1];
-        }
-        __syncwarp();
+// Thread-per-env window rebuild on the lane-interleaved storage (every pointer already includes the lane; stride 32).
+// On entry: table = slots [0, n) (unsorted), window = win[wh, wn) (sorted), side = up to RO_SIDE entries.  Everything
+// goes back to the table, then one streaming pass moves the entries with time <= h (at most RO_WCAP) to the scratch list
+// and compacts the others in place (forward, stable), and the scratch list is rank-sorted into the window.  Leaves
+// tmin = exact minimum of the table.  If more than RO_WCAP entries lie below the horizon the rest stays in the table
+// (the caller retries with a shorter horizon while a table entry is still due).
+__device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_p, double *sc_t, unsigned long long *sc_p,
+                                           WinEntry *win, double *side_t, unsigned long long *side_p,
+                                           unsigned &n, unsigned &wh, unsigned &wn, double &tmin, double &side_min,
+                                           const double h, WinEntry &head, WinEntry &nxt) {
+    for (unsigned j = wh; j < wn; j++) {                // leftover window entries
+        const WinEntry w = win_load(win + j * 32);
+        rt_t[n * 32] = w.t; rt_p[n * 32] = w.p; n++;
     }
+#pragma unroll
+    for (int s = 0; s < RO_SIDE; s++) {                 // side buffer
+        const double t = side_t[s * 32];
+        if (t < ORLG_INF) { rt_t[n * 32] = t; rt_p[n * 32] = side_p[s * 32]; n++; side_t[s * 32] = ORLG_INF; }
+    }
+    side_min = ORLG_INF;
+    unsigned k = 0, c = 0;
+    double mn = ORLG_INF;
+    for (unsigned s0 = 0; s0 < n; s0 += 4) {
+        double tt[4];
+        unsigned long long pp[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const bool in = s0 + i < n;
+            tt[i] = in ? __ldcg(rt_t + (s0 + i) * 32) : ORLG_INF;
+            pp[i] = in ? __ldcg(rt_p + (s0 + i) * 32) : 0ULL;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (s0 + i < n) {
+                if (tt[i] <= h && c < (unsigned)RO_WCAP) {
+                    sc_t[c * 32] = tt[i]; sc_p[c * 32] = pp[i]; c++;
+                } else {
+                    if (k != s0 + i) { rt_t[k * 32] = tt[i]; rt_p[k * 32] = pp[i]; }
+                    k++;
+                    mn = dmin(mn, tt[i]);
+                }
+            }
+        }
+    }
+    n = k;
+    tmin = mn;
+    head.t = ORLG_INF; nxt.t = ORLG_INF;
+    for (unsigned j = 0; j < c; j++) {                  // rank sort (c is ~15: quadratic is fine, the loads coalesce)
+        const double tj = __ldcg(sc_t + j * 32);
+        unsigned rank = 0;
+        for (unsigned q = 0; q < c; q++) {
+            const double tq = __ldcg(sc_t + q * 32);
+            rank += (tq < tj || (tq == tj && q < j)) ? 1u : 0u;
+        }
+        WinEntry w;
+        w.t = tj; w.p = __ldcg(sc_p + j * 32);
+        win[rank * 32] = w;
+        if (rank == 0) head = w;
+        if (rank == 1) nxt = w;
+    }
+    wh = 0; wn = c;
 }
 
 // packed integer pre-image of one path's features: start (7, 127 = no block) | length (7) | total free (7) | free runs (6) | slots (5)
@@ -287,9 +254,12 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     unsigned n_tab = nlive;
     unsigned err = p.errors[e];
     unsigned long long candw = *reinterpret_cast<const unsigned long long *>(p.cand + (size_t)e * 8);
-    double *const ev_t = p.ev_time + (size_t)e * p.heap_cap;
-    unsigned long long *const ev_p = p.ev_pay + (size_t)e * p.heap_cap;
-    const WinEntry *const win = ra.win + (size_t)e * RO_WCAP;
+    const size_t gw = (size_t)(env0 >> 5);                       // this warp's slice of the launch-private event storage
+    double *const rt_t = ra.rt_t + gw * p.heap_cap * 32 + lane;
+    unsigned long long *const rt_p = ra.rt_p + gw * p.heap_cap * 32 + lane;
+    double *const sc_t = ra.sc_t + gw * RO_WCAP * 32 + lane;
+    unsigned long long *const sc_p = ra.sc_p + gw * RO_WCAP * 32 + lane;
+    WinEntry *const win = ra.win + gw * RO_WCAP * 32 + lane;
 #pragma unroll
     for (int s = 0; s < RO_SIDE; s++) side_t[s * 32] = ORLG_INF;
     if (ridx != p.lockstep_ridx) err |= ORLG_ERR_LOCKSTEP;
@@ -301,12 +271,17 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     __syncthreads();                 // pool word + table barrier initialised by thread 0 ...
     mbar_wait(tab_bar, 0);           // ... and the tables have landed
     if (env0 >= p.n) return;         // a warp without environments (no CTA-wide barrier below)
-    {
-        const unsigned tile = ro_tile_acquire(pool_free, lane);
-        ro_rebuild_warp(p, ra, env0, nvalid, lane, pool + (size_t)tile * ra.tile_bytes, side_t0, side_p0,
-                        n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt);
-        ro_tile_release(pool_free, tile, lane);
+    // ---------------- event tables in: canonical [env][slot] -> lane-interleaved [slot][lane] (coalesced loads, one env at a time)
+    for (int i = 0; i < nvalid; i++) {
+        const unsigned n_i = __shfl_sync(0xffffffffu, n_tab, i);
+        const double *ct = p.ev_time + (size_t)(env0 + i) * p.heap_cap;
+        const unsigned long long *cp = p.ev_pay + (size_t)(env0 + i) * p.heap_cap;
+        double *dt = ra.rt_t + gw * p.heap_cap * 32 + i;
+        unsigned long long *dp = ra.rt_p + gw * p.heap_cap * 32 + i;
+        for (unsigned s = lane; s < n_i; s += 32) { dt[s * 32] = __ldcg(ct + s); dp[s * 32] = __ldcg(cp + s); }
     }
+    __syncwarp();
+    if (live) ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt);
     int npaths_cur = min((int)s_pair_count[src * p.N + dst], KM);       // candidate paths of the pending request
 
     const unsigned long long gid = (unsigned long long)(p.env_id_base + e);
@@ -320,7 +295,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
         ro_path_update<true>(sm, s_path_lm[svc_row(head.p)], bits_range_short(rs_, svc_slots(head.p)));          \
         nlive--; wh++;                                                                                           \
         head = nxt;                                                                                              \
-        if (wh + 1 < wn) nxt = win_load(win + wh + 1); else nxt.t = ORLG_INF;                                    \
+        if (wh + 1 < wn) nxt = win_load(win + (wh + 1) * 32); else nxt.t = ORLG_INF;                             \
     }
 
     RPH_MARK(8);                     // entry: state in + first window build
@@ -400,7 +375,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                                 if (in_side) side_min = dmin(side_min, rel);
                             }
                             if (!in_side) {                      // table push: two stores
-                                ev_t[n_tab] = rel; ev_p[n_tab] = pl; n_tab++;
+                                rt_t[n_tab * 32] = rel; rt_p[n_tab * 32] = pl; n_tab++;
                                 tmin_tab = dmin(tmin_tab, rel);
                             }
                             nlive++;
@@ -447,11 +422,10 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             RPH_COUNT(15);
             // a retry means the window filled up before every due service was reached: shorter horizon, down to the clock itself
             hzn = tries < 60 ? __dadd_rn(now, __dmul_rn(ra.span, __longlong_as_double((long long)(1023 - tries) << 52))) : now;
-            const unsigned tile = ro_tile_acquire(pool_free, lane);
-            ro_rebuild_warp(p, ra, env0, nvalid, lane, pool + (size_t)tile * ra.tile_bytes, side_t0, side_p0,
-                            n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt);
-            ro_tile_release(pool_free, tile, lane);
-            if (live) { RO_POP_DUE(); }
+            if (live) {
+                ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt);
+                RO_POP_DUE();
+            }
         }
         RPH_MARK(3);                 // rebuild
         if (live) {
@@ -551,18 +525,33 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
 #undef RO_POP_DUE
 
     // ---------------- state out: canonical form (orlg_device.cuh) for every other entry point
+    const unsigned n_entry = live ? p.nheap[e] : 0u;             // slots the canonical table used before this launch
     if (live) {
-        for (unsigned j = wh; j < wn; j++) {
-            const WinEntry w = win_load(win + j);
-            ev_t[n_tab] = w.t; ev_p[n_tab] = w.p; n_tab++;
+        for (unsigned j = wh; j < wn; j++) {                     // window + side entries back to the table
+            const WinEntry w = win_load(win + j * 32);
+            rt_t[n_tab * 32] = w.t; rt_p[n_tab * 32] = w.p; n_tab++;
         }
 #pragma unroll
         for (int s = 0; s < RO_SIDE; s++) {
             const double ts = side_t[s * 32];
-            if (ts < ORLG_INF) { ev_t[n_tab] = ts; ev_p[n_tab] = side_p[s * 32]; n_tab++; }
+            if (ts < ORLG_INF) { rt_t[n_tab * 32] = ts; rt_p[n_tab * 32] = side_p[s * 32]; n_tab++; }
         }
         if (n_tab != nlive) err |= ORLG_ERR_LOCKSTEP;            // internal consistency (never expected)
+    }
+    __syncwarp();
+    for (int i = 0; i < nvalid; i++) {                           // lane-interleaved -> canonical [env][slot] (coalesced stores)
+        const unsigned n_i = __shfl_sync(0xffffffffu, n_tab, i), old_i = __shfl_sync(0xffffffffu, n_entry, i);
+        double *ct = p.ev_time + (size_t)(env0 + i) * p.heap_cap;
+        unsigned long long *cp = p.ev_pay + (size_t)(env0 + i) * p.heap_cap;
+        const double *dt = ra.rt_t + gw * p.heap_cap * 32 + i;
+        const unsigned long long *dp = ra.rt_p + gw * p.heap_cap * 32 + i;
+        for (unsigned s = lane; s < n_i; s += 32) { ct[s] = __ldcg(dt + s * 32); cp[s] = __ldcg(dp + s * 32); }
+        for (unsigned s = n_i + lane; s < old_i; s += 32) ct[s] = ORLG_INF;      // "every slot >= n holds +INF"
+    }
+    __syncwarp();
+    if (live) {
         // directory: float lower bound per FULL group below the tail group, +INF from the tail group on
+        const double *ev_t = p.ev_time + (size_t)e * p.heap_cap;
         float *gmin = p.ev_gmin + (size_t)e * p.ev_groups;
         const int tail_g = n_tab ? (int)((n_tab - 1) / EV_GROUP) : 0;
         double all_min = ORLG_INF, tail_min = ORLG_INF;
@@ -570,7 +559,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             double m = ORLG_INF;
 #pragma unroll
             for (int q = 0; q < EV_GROUP / 2; q++) {
-                const double2 v = *reinterpret_cast<const double2 *>(ev_t + g * EV_GROUP + 2 * q);      // slots >= n hold +INF
+                const double2 v = __ldcg(reinterpret_cast<const double2 *>(ev_t + g * EV_GROUP + 2 * q));      // slots >= n hold +INF
                 m = dmin(m, dmin(v.x, v.y));
             }
             if (g < tail_g) gmin[g] = lower_f32(m); else tail_min = m;
