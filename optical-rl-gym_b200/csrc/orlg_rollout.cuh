@@ -27,6 +27,10 @@
 #pragma once
 #include "orlg_deeprmsa_fast.cuh"
 
+#ifndef ORLG_RO_BULK
+#define ORLG_RO_BULK 1          // observation tile leaves by one bulk (TMA) store per warp; 0 = coalesced 16-byte stores
+#endif
+
 namespace orlg {
 
 constexpr int RO_WCAP = 64;            // window entries per env
@@ -86,8 +90,9 @@ __device__ __forceinline__ void ro_path_update(uint4 *sm, unsigned lm, const Bit
     }
 }
 
-__device__ __forceinline__ WinEntry win_load(const WinEntry *w) {       // L2 (the window is rewritten by other lanes)
-    const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(w));
+// The launch-private event storage of a warp is only ever touched by that warp (one SM): ordinary L1-cached loads are coherent.
+__device__ __forceinline__ WinEntry win_load(const WinEntry *w) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(w);
     WinEntry e;
     e.t = __hiloint2double((int)v.y, (int)v.x);
     e.p = (unsigned long long)v.z | ((unsigned long long)v.w << 32);
@@ -139,17 +144,17 @@ __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_
     side_min = ORLG_INF;
     unsigned k = 0, c = 0;
     double mn = ORLG_INF;
-    for (unsigned s0 = 0; s0 < n; s0 += 4) {
-        double tt[4];
-        unsigned long long pp[4];
+    for (unsigned s0 = 0; s0 < n; s0 += 8) {            // 16 independent (coalesced) loads per pass
+        double tt[8];
+        unsigned long long pp[8];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < 8; i++) {
             const bool in = s0 + i < n;
-            tt[i] = in ? __ldcg(rt_t + (s0 + i) * 32) : ORLG_INF;
-            pp[i] = in ? __ldcg(rt_p + (s0 + i) * 32) : 0ULL;
+            tt[i] = in ? rt_t[(s0 + i) * 32] : ORLG_INF;
+            pp[i] = in ? rt_p[(s0 + i) * 32] : 0ULL;
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < 8; i++) {
             if (s0 + i < n) {
                 if (tt[i] <= h && c < (unsigned)RO_WCAP) {
                     sc_t[c * 32] = tt[i]; sc_p[c * 32] = pp[i]; c++;
@@ -165,14 +170,15 @@ __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_
     tmin = mn;
     head.t = ORLG_INF; nxt.t = ORLG_INF;
     for (unsigned j = 0; j < c; j++) {                  // rank sort (c is ~15: quadratic is fine, the loads coalesce)
-        const double tj = __ldcg(sc_t + j * 32);
+        const double tj = sc_t[j * 32];
         unsigned rank = 0;
+#pragma unroll 4
         for (unsigned q = 0; q < c; q++) {
-            const double tq = __ldcg(sc_t + q * 32);
+            const double tq = sc_t[q * 32];
             rank += (tq < tj || (tq == tj && q < j)) ? 1u : 0u;
         }
         WinEntry w;
-        w.t = tj; w.p = __ldcg(sc_p + j * 32);
+        w.t = tj; w.p = sc_p[j * 32];
         win[rank * 32] = w;
         if (rank == 0) head = w;
         if (rank == 1) nxt = w;
@@ -271,16 +277,26 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     __syncthreads();                 // pool word + table barrier initialised by thread 0 ...
     mbar_wait(tab_bar, 0);           // ... and the tables have landed
     if (env0 >= p.n) return;         // a warp without environments (no CTA-wide barrier below)
-    // ---------------- event tables in: canonical [env][slot] -> lane-interleaved [slot][lane] (coalesced loads, one env at a time)
-    for (int i = 0; i < nvalid; i++) {
-        const unsigned n_i = __shfl_sync(0xffffffffu, n_tab, i);
-        const double *ct = p.ev_time + (size_t)(env0 + i) * p.heap_cap;
-        const unsigned long long *cp = p.ev_pay + (size_t)(env0 + i) * p.heap_cap;
-        double *dt = ra.rt_t + gw * p.heap_cap * 32 + i;
-        unsigned long long *dp = ra.rt_p + gw * p.heap_cap * 32 + i;
-        for (unsigned s = lane; s < n_i; s += 32) { dt[s * 32] = __ldcg(ct + s); dp[s * 32] = __ldcg(cp + s); }
+    // ---------------- event tables in: canonical [env][slot] -> lane-interleaved [slot][lane].  Thread per env: the loads
+    // walk the env's own rows (one L2 fetch per 128-byte line, the rest are L1 hits), the stores coalesce.
+    if (live) {
+        const double *__restrict__ ct = p.ev_time + (size_t)e * p.heap_cap;
+        const unsigned long long *__restrict__ cp = p.ev_pay + (size_t)e * p.heap_cap;
+        for (unsigned s0 = 0; s0 < n_tab; s0 += 8) {                 // heap_cap is a multiple of 16: the vector loads stay inside the table
+            double2 a[4];
+            ulonglong2 b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                a[i] = *reinterpret_cast<const double2 *>(ct + s0 + 2 * i);
+                b[i] = *reinterpret_cast<const ulonglong2 *>(cp + s0 + 2 * i);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                rt_t[(s0 + 2 * i) * 32] = a[i].x; rt_t[(s0 + 2 * i + 1) * 32] = a[i].y;
+                rt_p[(s0 + 2 * i) * 32] = b[i].x; rt_p[(s0 + 2 * i + 1) * 32] = b[i].y;
+            }
+        }
     }
-    __syncwarp();
     if (live) ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt);
     int npaths_cur = min((int)s_pair_count[src * p.N + dst], KM);       // candidate paths of the pending request
 
@@ -463,7 +479,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                         if (pm[q] & (1u << l)) { A[q].w[0] &= v.x; A[q].w[1] &= v.y; A[q].w[2] &= v.z; A[q].w[3] &= v.w; }
                 }
             }
-            RPH_MARK(5);             // candidate-path AND
+            RPH_MARK(10);            // candidate-path AND
             unsigned long long cand_out = 0xFFFFFFFFFFFFFFFFULL;
 #pragma unroll
             for (int q = 0; q < KM; q++) {
@@ -478,45 +494,70 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             }
             candw = cand_out;
         }
-        RPH_MARK(6);                 // features
+        RPH_MARK(5);                 // features
         if (ra.obs) {
             // ---- the warp's 32 rows = one contiguous run of obs[t]: written to a pool tile, copied out with coalesced 16-byte stores
             const unsigned tile = ro_tile_acquire(pool_free, lane);
             unsigned char *stage = pool + (size_t)tile * ra.tile_bytes;
             RPH_MARK(4);             // tile acquisition
             if (live) {
+                // row = [bit rate / 100 | one-hot(min(src, dst)) | one-hot(max(src, dst)) | 5 x 5 features]: 1 + 2N is odd, so the
+                // last one-hot element pairs with the first feature and the whole tail goes out as 13 aligned float2 stores
                 float *so32 = reinterpret_cast<float *>(stage) + (size_t)lane * p.obs_dim;
-                const int head_n = 1 + 2 * p.N;
                 float2 *r2 = reinterpret_cast<float2 *>(so32);
-                for (int q = 0; q < (head_n + 1) / 2; q++) r2[q] = make_float2(0.0f, 0.0f);
-                so32[0] = __fdiv_rn((float)br, 100.0f);
-                so32[1 + min(src, dst)] = 1.0f; so32[1 + p.N + max(src, dst)] = 1.0f;
+                const int lo_n = min(src, dst), hi_n = max(src, dst);
+                for (int q = 0; q < p.N; q++) r2[q] = make_float2(0.0f, 0.0f);
+                float v[2 + 5 * KM];
+                v[0] = hi_n == p.N - 1 ? 1.0f : 0.0f;
+                v[1 + 5 * KM] = 0.0f;
 #pragma unroll
                 for (int q = 0; q < KM; q++) {
                     const unsigned f = feat[q];
                     const int st = (int)(f & 127u), len = (int)((f >> 7) & 127u), total = (int)((f >> 14) & 127u);
                     const int runs = (int)((f >> 21) & 63u), n = (int)(f >> 27);
                     const bool have = q < npaths, blk = st != 127;
-                    const int ob = head_n + q * 5;
-                    so32[ob] = blk ? s_pos[blk ? st : 0] : -1.0f;
-                    so32[ob + 1] = blk ? (float)(len - 8) * 0.125f : -1.0f;
-                    so32[ob + 2] = have ? s_nsl[n] : -1.0f;
-                    so32[ob + 3] = have ? s_pos[total] : -1.0f;
-                    so32[ob + 4] = runs > 0 ? (float)(total - 4 * runs) * s_rcp4[runs] : -1.0f;   // x * fl(1/y): <= 1.5 ulp
+                    v[1 + 5 * q] = blk ? s_pos[blk ? st : 0] : -1.0f;
+                    v[2 + 5 * q] = blk ? (float)(len - 8) * 0.125f : -1.0f;
+                    v[3 + 5 * q] = have ? s_nsl[n] : -1.0f;
+                    v[4 + 5 * q] = have ? s_pos[total] : -1.0f;
+                    v[5 + 5 * q] = runs > 0 ? (float)(total - 4 * runs) * s_rcp4[runs] : -1.0f;   // x * fl(1/y): <= 1.5 ulp
                 }
+#pragma unroll
+                for (int i = 0; i < (1 + 5 * KM + 1) / 2; i++) r2[p.N + i] = make_float2(v[2 * i], v[2 * i + 1]);
+                so32[0] = __fdiv_rn((float)br, 100.0f);
+                so32[1 + lo_n] = 1.0f;
+                if (hi_n != p.N - 1) so32[1 + p.N + hi_n] = 1.0f;
             }
-            __syncwarp();
+            RPH_MARK(6);             // observation rows into the tile
             {
                 float *g = ra.obs + ((size_t)t * p.n + env0) * p.obs_dim;
                 const int total_el = nvalid * p.obs_dim;
+#if ORLG_RO_BULK
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if ((reinterpret_cast<size_t>(g) & 15) == 0 && (total_el & 3) == 0) {
+                    if (lane == 0) {     // one bulk (TMA) store for the warp's rows; the tile is free once it has been read
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     ::"l"(g), "r"((unsigned)__cvta_generic_to_shared(stage)), "r"((unsigned)total_el * 4u) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                } else {
+                    const float *sv = reinterpret_cast<const float *>(stage);
+                    for (int q = lane; q < total_el; q += 32) g[q] = sv[q];
+                }
+#else
+                __syncwarp();
                 if ((reinterpret_cast<size_t>(g) & 15) == 0 && (total_el & 3) == 0) {
                     const uint4 *sv = reinterpret_cast<const uint4 *>(stage);
                     uint4 *gv = reinterpret_cast<uint4 *>(g);
+#pragma unroll 7
                     for (int q = lane; q < total_el / 4; q += 32) gv[q] = sv[q];
                 } else {
                     const float *sv = reinterpret_cast<const float *>(stage);
                     for (int q = lane; q < total_el; q += 32) g[q] = sv[q];
                 }
+#endif
             }
             ro_tile_release(pool_free, tile, lane);
         }
@@ -537,19 +578,25 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             if (ts < ORLG_INF) { rt_t[n_tab * 32] = ts; rt_p[n_tab * 32] = side_p[s * 32]; n_tab++; }
         }
         if (n_tab != nlive) err |= ORLG_ERR_LOCKSTEP;            // internal consistency (never expected)
-    }
-    __syncwarp();
-    for (int i = 0; i < nvalid; i++) {                           // lane-interleaved -> canonical [env][slot] (coalesced stores)
-        const unsigned n_i = __shfl_sync(0xffffffffu, n_tab, i), old_i = __shfl_sync(0xffffffffu, n_entry, i);
-        double *ct = p.ev_time + (size_t)(env0 + i) * p.heap_cap;
-        unsigned long long *cp = p.ev_pay + (size_t)(env0 + i) * p.heap_cap;
-        const double *dt = ra.rt_t + gw * p.heap_cap * 32 + i;
-        const unsigned long long *dp = ra.rt_p + gw * p.heap_cap * 32 + i;
-        for (unsigned s = lane; s < n_i; s += 32) { ct[s] = __ldcg(dt + s * 32); cp[s] = __ldcg(dp + s * 32); }
-        for (unsigned s = n_i + lane; s < old_i; s += 32) ct[s] = ORLG_INF;      // "every slot >= n holds +INF"
-    }
-    __syncwarp();
-    if (live) {
+        // lane-interleaved -> canonical [env][slot]: coalesced loads, each thread writes its own rows (16-byte stores)
+        double *ev_tw = p.ev_time + (size_t)e * p.heap_cap;
+        unsigned long long *ev_pw = p.ev_pay + (size_t)e * p.heap_cap;
+        const unsigned n_fill = max(n_tab, n_entry);                 // "every slot >= n holds +INF"
+        for (unsigned s0 = 0; s0 < n_fill; s0 += 8) {
+            double tt[8];
+            unsigned long long pp[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const bool in = s0 + i < n_tab;
+                tt[i] = in ? rt_t[(s0 + i) * 32] : ORLG_INF;
+                pp[i] = in ? rt_p[(s0 + i) * 32] : 0ULL;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                *reinterpret_cast<double2 *>(ev_tw + s0 + 2 * i) = make_double2(tt[2 * i], tt[2 * i + 1]);
+                *reinterpret_cast<ulonglong2 *>(ev_pw + s0 + 2 * i) = make_ulonglong2(pp[2 * i], pp[2 * i + 1]);
+            }
+        }
         // directory: float lower bound per FULL group below the tail group, +INF from the tail group on
         const double *ev_t = p.ev_time + (size_t)e * p.heap_cap;
         float *gmin = p.ev_gmin + (size_t)e * p.ev_groups;
@@ -559,7 +606,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             double m = ORLG_INF;
 #pragma unroll
             for (int q = 0; q < EV_GROUP / 2; q++) {
-                const double2 v = __ldcg(reinterpret_cast<const double2 *>(ev_t + g * EV_GROUP + 2 * q));      // slots >= n hold +INF
+                const double2 v = *reinterpret_cast<const double2 *>(ev_t + g * EV_GROUP + 2 * q);      // slots >= n hold +INF
                 m = dmin(m, dmin(v.x, v.y));
             }
             if (g < tail_g) gmin[g] = lower_f32(m); else tail_min = m;

@@ -13,8 +13,8 @@ import torch  # noqa: E402
 
 from optical_rl_gym_b200 import OpticalVecEnv, _native, nsfnet  # noqa: E402
 
-NAMES = ["request draw", "action + phase A", "phase B + releases", "window rebuild", "done + tile acquire", "path AND",
-         "features + obs row", "tile store + release", "ENTRY (per launch)", "EXIT (per launch)"]
+NAMES = ["request draw", "action + phase A", "phase B + releases", "window rebuild", "tile acquire", "features",
+         "obs rows -> tile", "tile copy-out + release", "ENTRY (per launch)", "EXIT (per launch)", "path AND"]
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 launches = int(sys.argv[3]) if len(sys.argv) > 3 else 5
@@ -32,8 +32,8 @@ torch.cuda.synchronize()
 assert L.orlg_debug_phase_cycles(buf) == 0, L.orlg_last_error()
 warps = (n + 31) // 32
 steps = T * launches
-tot = sum(buf[:8])
+tot = sum(buf[:8]) + buf[10]
 print("avg cycles per warp per step: %.0f (+ entry %.0f, exit %.0f per launch); warp rebuilds per step: %.4f" % (
     tot / warps / steps, buf[8] / warps / launches, buf[9] / warps / launches, buf[15] / warps / steps))
-for i, nm in enumerate(NAMES[:8]):
+for i, nm in [(j, NAMES[j]) for j in (0, 1, 2, 3, 10, 5, 4, 6, 7)]:
     print("%-22s %8.0f cycles  %5.1f%%" % (nm, buf[i] / warps / steps, 100.0 * buf[i] / tot))
