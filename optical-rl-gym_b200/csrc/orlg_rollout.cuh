@@ -33,7 +33,7 @@
 
 namespace orlg {
 
-constexpr int RO_WCAP = 64;            // window entries per env
+constexpr int RO_WCAP = 48;            // window entries per env (48 float sort keys x 32 lanes fit one pool tile)
 constexpr int RO_SIDE = 3;             // side-buffer entries per env (shared memory)
 constexpr int RO_MAX_THREADS = 448;    // 14 warps x 148 SMs >= 65536 envs in one wave
 enum { RO_POLICY_RANDOM = 0, RO_POLICY_SP_FF = 1, RO_POLICY_SAP_FF = 2 };
@@ -129,7 +129,7 @@ __device__ __forceinline__ void ro_tile_release(unsigned *pool_free, unsigned ti
 // tmin = exact minimum of the table.  If more than RO_WCAP entries lie below the horizon the rest stays in the table
 // (the caller retries with a shorter horizon while a table entry is still due).
 __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_p, double *sc_t, unsigned long long *sc_p,
-                                           WinEntry *win, double *side_t, unsigned long long *side_p,
+                                           WinEntry *win, double *side_t, unsigned long long *side_p, float *keys,
                                            unsigned &n, unsigned &wh, unsigned &wn, double &tmin, double &side_min,
                                            const double h, WinEntry &head, WinEntry &nxt) {
     for (unsigned j = wh; j < wn; j++) {                // leftover window entries
@@ -157,7 +157,9 @@ __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_
         for (int i = 0; i < 8; i++) {
             if (s0 + i < n) {
                 if (tt[i] <= h && c < (unsigned)RO_WCAP) {
-                    sc_t[c * 32] = tt[i]; sc_p[c * 32] = pp[i]; c++;
+                    sc_t[c * 32] = tt[i]; sc_p[c * 32] = pp[i];
+                    keys[c * 32] = __double2float_rd(tt[i] - h);         // monotone: key_a < key_b implies t_a < t_b
+                    c++;
                 } else {
                     if (k != s0 + i) { rt_t[k * 32] = tt[i]; rt_p[k * 32] = pp[i]; }
                     k++;
@@ -169,16 +171,25 @@ __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_
     n = k;
     tmin = mn;
     head.t = ORLG_INF; nxt.t = ORLG_INF;
-    for (unsigned j = 0; j < c; j++) {                  // rank sort (c is ~15: quadratic is fine, the loads coalesce)
-        const double tj = sc_t[j * 32];
-        unsigned rank = 0;
+    // rank sort on the float keys in shared memory; equal keys (about one pair in a million) are ordered by the exact times
+    for (unsigned j = 0; j < c; j++) {
+        WinEntry w;
+        w.t = sc_t[j * 32]; w.p = sc_p[j * 32];         // requested first: the latency overlaps the key loop
+        const float kj = keys[j * 32];
+        unsigned rank = 0, ties = 0;
 #pragma unroll 4
         for (unsigned q = 0; q < c; q++) {
-            const double tq = sc_t[q * 32];
-            rank += (tq < tj || (tq == tj && q < j)) ? 1u : 0u;
+            const float kq = keys[q * 32];
+            rank += kq < kj ? 1u : 0u;
+            ties += kq == kj ? 1u : 0u;
         }
-        WinEntry w;
-        w.t = tj; w.p = sc_p[j * 32];
+        if (ties > 1) {
+            rank = 0;
+            for (unsigned q = 0; q < c; q++) {
+                const double tq = sc_t[q * 32];
+                rank += (tq < w.t || (tq == w.t && q < j)) ? 1u : 0u;
+            }
+        }
         win[rank * 32] = w;
         if (rank == 0) head = w;
         if (rank == 1) nxt = w;
@@ -297,7 +308,12 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             }
         }
     }
-    if (live) ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt);
+    {
+        const unsigned tile = ro_tile_acquire(pool_free, lane);
+        float *keys = reinterpret_cast<float *>(pool + (size_t)tile * ra.tile_bytes) + lane;
+        if (live) ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, keys, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt);
+        ro_tile_release(pool_free, tile, lane);
+    }
     int npaths_cur = min((int)s_pair_count[src * p.N + dst], KM);       // candidate paths of the pending request
 
     const unsigned long long gid = (unsigned long long)(p.env_id_base + e);
@@ -438,10 +454,11 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             RPH_COUNT(15);
             // a retry means the window filled up before every due service was reached: shorter horizon, down to the clock itself
             hzn = tries < 60 ? __dadd_rn(now, __dmul_rn(ra.span, __longlong_as_double((long long)(1023 - tries) << 52))) : now;
-            if (live) {
-                ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt);
-                RO_POP_DUE();
-            }
+            const unsigned tile = ro_tile_acquire(pool_free, lane);
+            float *keys = reinterpret_cast<float *>(pool + (size_t)tile * ra.tile_bytes) + lane;
+            if (live) ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, keys, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt);
+            ro_tile_release(pool_free, tile, lane);
+            if (live) { RO_POP_DUE(); }
         }
         RPH_MARK(3);                 // rebuild
         if (live) {
