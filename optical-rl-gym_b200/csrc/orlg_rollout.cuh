@@ -27,6 +27,9 @@
 #pragma once
 #include "orlg_deeprmsa_fast.cuh"
 
+#ifndef ORLG_RO_SMEMSORT
+#define ORLG_RO_SMEMSORT 1      // window rebuild ranks on float keys in shared memory (0: exact times from L2 only)
+#endif
 #ifndef ORLG_RO_BULK
 #define ORLG_RO_BULK 1          // observation tile leaves by one bulk (TMA) store per warp; 0 = coalesced 16-byte stores
 #endif
@@ -129,9 +132,9 @@ __device__ __forceinline__ void ro_tile_release(unsigned *pool_free, unsigned ti
 // tmin = exact minimum of the table.  If more than RO_WCAP entries lie below the horizon the rest stays in the table
 // (the caller retries with a shorter horizon while a table entry is still due).
 __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_p, double *sc_t, unsigned long long *sc_p,
-                                           WinEntry *win, double *side_t, unsigned long long *side_p, float *keys,
+                                           WinEntry *win, double *side_t, unsigned long long *side_p,
                                            unsigned &n, unsigned &wh, unsigned &wn, double &tmin, double &side_min,
-                                           const double h, WinEntry &head, WinEntry &nxt) {
+                                           const double h) {
     for (unsigned j = wh; j < wn; j++) {                // leftover window entries
         const WinEntry w = win_load(win + j * 32);
         rt_t[n * 32] = w.t; rt_p[n * 32] = w.p; n++;
@@ -157,9 +160,7 @@ __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_
         for (int i = 0; i < 8; i++) {
             if (s0 + i < n) {
                 if (tt[i] <= h && c < (unsigned)RO_WCAP) {
-                    sc_t[c * 32] = tt[i]; sc_p[c * 32] = pp[i];
-                    keys[c * 32] = __double2float_rd(tt[i] - h);         // monotone: key_a < key_b implies t_a < t_b
-                    c++;
+                    sc_t[c * 32] = tt[i]; sc_p[c * 32] = pp[i]; c++;
                 } else {
                     if (k != s0 + i) { rt_t[k * 32] = tt[i]; rt_p[k * 32] = pp[i]; }
                     k++;
@@ -170,8 +171,16 @@ __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_
     }
     n = k;
     tmin = mn;
+    wh = 0; wn = c;
+}
+
+// second half of the rebuild: the wn candidates of the scratch list, rank-sorted into the window.  The ranks are computed on
+// float keys in shared memory (`keys`, one pool tile per warp, held only here); equal keys (about one pair in a million) are
+// ordered by the exact times.
+__device__ __forceinline__ void ro_rebuild_sort(const double *sc_t, const unsigned long long *sc_p, WinEntry *win, float *keys,
+                                                const unsigned c, const double h, WinEntry &head, WinEntry &nxt) {
     head.t = ORLG_INF; nxt.t = ORLG_INF;
-    // rank sort on the float keys in shared memory; equal keys (about one pair in a million) are ordered by the exact times
+    for (unsigned j = 0; j < c; j++) keys[j * 32] = __double2float_rd(sc_t[j * 32] - h);      // monotone: key_a < key_b implies t_a < t_b
     for (unsigned j = 0; j < c; j++) {
         WinEntry w;
         w.t = sc_t[j * 32]; w.p = sc_p[j * 32];         // requested first: the latency overlaps the key loop
@@ -183,7 +192,7 @@ __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_
             rank += kq < kj ? 1u : 0u;
             ties += kq == kj ? 1u : 0u;
         }
-        if (ties > 1) {
+        if (ties > 1 || !ORLG_RO_SMEMSORT) {
             rank = 0;
             for (unsigned q = 0; q < c; q++) {
                 const double tq = sc_t[q * 32];
@@ -194,7 +203,6 @@ __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_
         if (rank == 0) head = w;
         if (rank == 1) nxt = w;
     }
-    wh = 0; wn = c;
 }
 
 // packed integer pre-image of one path's features: start (7, 127 = no block) | length (7) | total free (7) | free runs (6) | slots (5)
@@ -309,9 +317,10 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
         }
     }
     {
+        if (live) ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn);
         const unsigned tile = ro_tile_acquire(pool_free, lane);
         float *keys = reinterpret_cast<float *>(pool + (size_t)tile * ra.tile_bytes) + lane;
-        if (live) ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, keys, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt);
+        if (live) ro_rebuild_sort(sc_t, sc_p, win, keys, wn, hzn, head, nxt);
         ro_tile_release(pool_free, tile, lane);
     }
     int npaths_cur = min((int)s_pair_count[src * p.N + dst], KM);       // candidate paths of the pending request
@@ -454,9 +463,10 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             RPH_COUNT(15);
             // a retry means the window filled up before every due service was reached: shorter horizon, down to the clock itself
             hzn = tries < 60 ? __dadd_rn(now, __dmul_rn(ra.span, __longlong_as_double((long long)(1023 - tries) << 52))) : now;
+            if (live) ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn);
             const unsigned tile = ro_tile_acquire(pool_free, lane);
             float *keys = reinterpret_cast<float *>(pool + (size_t)tile * ra.tile_bytes) + lane;
-            if (live) ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, keys, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt);
+            if (live) ro_rebuild_sort(sc_t, sc_p, win, keys, wn, hzn, head, nxt);
             ro_tile_release(pool_free, tile, lane);
             if (live) { RO_POP_DUE(); }
         }

@@ -33,11 +33,18 @@ for r in range(reps):
     torch.cuda.synchronize()
     times.append(a.elapsed_time(b))
 times.sort()
+try:
+    import pynvml
+    pynvml.nvmlInit()
+    hnd = pynvml.nvmlDeviceGetHandleByIndex(0)
+    clk = "sm %d MHz (max %d), %.0f W" % (pynvml.nvmlDeviceGetClockInfo(hnd, pynvml.NVML_CLOCK_SM), pynvml.nvmlDeviceGetMaxClockInfo(hnd, pynvml.NVML_CLOCK_SM), pynvml.nvmlDeviceGetPowerUsage(hnd) / 1e3)
+except Exception as exc:  # noqa: BLE001
+    clk = "clocks n/a (%s)" % exc
 med = times[len(times) // 2]
 print("rollout: n=%d T=%d span=%s warps=%s tiles=%s  median %.3f ms/launch = %.2f us/step, %.3e env-steps/s (min %.3f max %.3f)  accept %.3f err %d" % (
     n, T, os.environ.get("ORLG_RO_SPAN"), os.environ.get("ORLG_RO_WARPS"), os.environ.get("ORLG_RO_TILES"),
     med, med / T * 1e3, n * T / (med * 1e-3), times[0], times[-1], float((rew > 0).float().mean()),
-    int((env.error_flags() != 0).sum())))
+    int((env.error_flags() != 0).sum())), clk)
 if os.environ.get("STEP_PATH"):
     a1 = torch.empty((n, 1), dtype=torch.int32, device="cuda")
     for _ in range(50):
