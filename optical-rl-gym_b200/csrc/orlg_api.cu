@@ -44,6 +44,10 @@ struct orlg_env {
     WinEntry *ro_win = nullptr;
     double *ro_sc_t = nullptr, *ro_rt_t = nullptr;
     unsigned long long *ro_sc_p = nullptr, *ro_rt_p = nullptr;
+    unsigned *ro_st_u32 = nullptr;             // [4][n] table size, window head, window end, canonical size
+    double *ro_st_f64 = nullptr;               // [2 + RO_SIDE][n] table minimum, horizon, side-buffer times
+    unsigned long long *ro_st_u64 = nullptr;   // [RO_SIDE][n] side-buffer payloads
+    bool ro_valid = false;                     // the events live in the rollout-private storage (canonical tables are stale)
     int *ro_actions = nullptr;    // [n, action_dim] scratch of the generic (kernel-per-step) rollout
 };
 
@@ -224,6 +228,27 @@ int launch_step(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s)
     return ORLG_OK;
 }
 
+void rollout_state_args(const orlg_env *env, RolloutArgs *ra) {
+    const size_t n = (size_t)env->p.n;
+    ra->win = env->ro_win; ra->sc_t = env->ro_sc_t; ra->sc_p = env->ro_sc_p; ra->rt_t = env->ro_rt_t; ra->rt_p = env->ro_rt_p;
+    ra->st_ntab = env->ro_st_u32; ra->st_wh = env->ro_st_u32 + n; ra->st_wn = env->ro_st_u32 + 2 * n; ra->st_ncanon = env->ro_st_u32 + 3 * n;
+    ra->st_tmin = env->ro_st_f64; ra->st_hzn = env->ro_st_f64 + n; ra->st_side_t = env->ro_st_f64 + 2 * n;
+    ra->st_side_p = env->ro_st_u64;
+}
+
+// Every entry point that reads or writes the release-event tables calls this first: after an orlg_rollout the events live in
+// the rollout kernel's private storage until somebody else needs them.
+int ensure_canonical(orlg_env *env, cudaStream_t s) {
+    if (!env->ro_valid) return ORLG_OK;
+    RolloutArgs ra;
+    std::memset(&ra, 0, sizeof(ra));
+    rollout_state_args(env, &ra);
+    ro_canonicalize_kernel<<<(env->p.n + 127) / 128, 128, 0, s>>>(env->p, ra);
+    CUDA_OK(cudaGetLastError());
+    env->ro_valid = false;
+    return ORLG_OK;
+}
+
 // shared-memory plan of the rollout kernel: as many warps per CTA as cover the batch in one wave (<= 14), each with
 // its mask tile + side buffer, plus a pool of observation tiles
 bool rollout_plan(const orlg_env *env, int *wpc_out, RolloutArgs *ra, size_t *smem_out) {
@@ -233,8 +258,7 @@ bool rollout_plan(const orlg_env *env, int *wpc_out, RolloutArgs *ra, size_t *sm
     if (wpc > RO_MAX_THREADS / 32) wpc = RO_MAX_THREADS / 32;
     if (wpc < 1) wpc = 1;
     if (const char *v = std::getenv("ORLG_RO_WARPS")) { int w = std::atoi(v); if (w >= 1 && w <= RO_MAX_THREADS / 32) wpc = w; }
-    int tile = (32 * p.obs_dim * 4 + 127) / 128 * 128;
-    if (tile < RO_WCAP * 128) tile = RO_WCAP * 128;              // a tile also holds the float sort keys of a window rebuild
+    const int tile = (32 * p.obs_dim * 4 + 127) / 128 * 128;
     const int warp_bytes = p.E * 512 + RO_SIDE * 512;
     const size_t budget = 227 * 1024;
     for (; wpc >= 1; wpc--) {
@@ -576,6 +600,11 @@ int orlg_reset(orlg_env *env, int full, void *obs_dev, orlg_stream stream) {
     StepIO io;
     std::memset(&io, 0, sizeof(io));
     io.obs = env->p.obs_dim ? obs_dev : nullptr;
+    if (full) env->ro_valid = false;           // everything is reset below: nothing to convert back
+    else {
+        int rc0 = ensure_canonical(env, (cudaStream_t)stream);
+        if (rc0) return rc0;
+    }
     if (full) {
         fill_events_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(env->p);
         CUDA_OK(cudaGetLastError());
@@ -589,6 +618,10 @@ int orlg_step(orlg_env *env, const int32_t *actions_dev, void *obs_dev, float *r
               int32_t *decision_dev, int64_t *info_dev, orlg_stream stream) {
     if (!env || !actions_dev) return fail(ORLG_E_INVALID, "null handle or actions");
     DeviceGuard guard(env->device);
+    {
+        int rc0 = ensure_canonical(env, (cudaStream_t)stream);
+        if (rc0) return rc0;
+    }
     StepIO io;
     io.actions = actions_dev;
     io.obs = env->p.obs_dim ? obs_dev : nullptr;
@@ -669,6 +702,10 @@ static int run_export(orlg_env *env, uint32_t *masks, int32_t *alloc, double *no
     if (!env) return fail(ORLG_E_INVALID, "null handle");
     DeviceGuard guard(env->device);
     const int threads = 128, blocks = (env->p.n + threads - 1) / threads;
+    if (alloc) {                               // the allocation matrix is rebuilt from the release-event table
+        int rc0 = ensure_canonical(env, (cudaStream_t)stream);
+        if (rc0) return rc0;
+    }
     if (env->wide && (masks || alloc)) {
         export_wide_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(env->p, masks, alloc);
         CUDA_OK(cudaGetLastError());
@@ -807,6 +844,9 @@ int orlg_rollout(orlg_env *env, int steps, int policy, void *obs_dev, float *rew
             if (!rc) rc = dev_alloc(env, &env->ro_sc_p, warps * 32 * RO_WCAP, false);
             if (!rc) rc = dev_alloc(env, &env->ro_rt_t, warps * 32 * (size_t)p.heap_cap, false);
             if (!rc) rc = dev_alloc(env, &env->ro_rt_p, warps * 32 * (size_t)p.heap_cap, false);
+            if (!rc) rc = dev_alloc(env, &env->ro_st_u32, 4 * n, false);
+            if (!rc) rc = dev_alloc(env, &env->ro_st_f64, (2 + RO_SIDE) * n, false);
+            if (!rc) rc = dev_alloc(env, &env->ro_st_u64, RO_SIDE * n, false);
             if (rc) return rc;
         }
         double span_steps = 40.0;
@@ -815,13 +855,19 @@ int orlg_rollout(orlg_env *env, int steps, int policy, void *obs_dev, float *rew
         ra.span = span_steps * p.mean_iat;
         ra.obs = reinterpret_cast<float *>(obs_dev);
         ra.reward = reward_dev; ra.done = done_dev; ra.actions = actions_dev;
-        ra.win = env->ro_win; ra.sc_t = env->ro_sc_t; ra.sc_p = env->ro_sc_p; ra.rt_t = env->ro_rt_t; ra.rt_p = env->ro_rt_p;
+        rollout_state_args(env, &ra);
+        ra.resume = env->ro_valid ? 1 : 0;
         cudaError_t e = p.E == 22 ? launch_rollout<22>(env, ra, policy, wpc, smem, s) : launch_rollout<0>(env, ra, policy, wpc, smem, s);
         if (e != cudaSuccess) return fail(ORLG_E_CUDA, std::string("rollout launch: ") + cudaGetErrorString(e));
         p.lockstep_ridx += (unsigned)steps;
+        env->ro_valid = true;
         return ORLG_OK;
     }
     // generic: the same T steps as separate policy + step launches
+    {
+        int rc = ensure_canonical(env, s);
+        if (rc) return rc;
+    }
     const int adim = orlg_action_dim(env);
     if (!actions_dev && !env->ro_actions) {
         int rc = dev_alloc(env, &env->ro_actions, (size_t)p.n * adim, false);

@@ -27,16 +27,13 @@
 #pragma once
 #include "orlg_deeprmsa_fast.cuh"
 
-#ifndef ORLG_RO_SMEMSORT
-#define ORLG_RO_SMEMSORT 1      // window rebuild ranks on float keys in shared memory (0: exact times from L2 only)
-#endif
 #ifndef ORLG_RO_BULK
 #define ORLG_RO_BULK 1          // observation tile leaves by one bulk (TMA) store per warp; 0 = coalesced 16-byte stores
 #endif
 
 namespace orlg {
 
-constexpr int RO_WCAP = 48;            // window entries per env (48 float sort keys x 32 lanes fit one pool tile)
+constexpr int RO_WCAP = 64;            // window entries per env
 constexpr int RO_SIDE = 3;             // side-buffer entries per env (shared memory)
 constexpr int RO_MAX_THREADS = 448;    // 14 warps x 148 SMs >= 65536 envs in one wave
 enum { RO_POLICY_RANDOM = 0, RO_POLICY_SP_FF = 1, RO_POLICY_SAP_FF = 2 };
@@ -78,6 +75,13 @@ struct RolloutArgs {
     double *sc_t;                // [warps][RO_WCAP][32]   rebuild scratch: candidate times
     unsigned long long *sc_p;    // [warps][RO_WCAP][32]   rebuild scratch: candidate payloads
     WinEntry *win;               // [warps][RO_WCAP][32]   the sorted window
+    // window state kept between launches (the event storage stays in the launch-private form until another entry point
+    // needs the canonical tables: ro_canonicalize_kernel)
+    int resume;                  // 1: continue from the saved window state; 0: convert the canonical tables first
+    unsigned *st_ntab, *st_wh, *st_wn, *st_ncanon;      // [n]
+    double *st_tmin, *st_hzn;                           // [n]
+    double *st_side_t;                                  // [RO_SIDE][n]
+    unsigned long long *st_side_p;                      // [RO_SIDE][n]
 };
 
 // apply a release / an allocation to the path's links in the warp's shared-memory mask tile
@@ -134,7 +138,7 @@ __device__ __forceinline__ void ro_tile_release(unsigned *pool_free, unsigned ti
 __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_p, double *sc_t, unsigned long long *sc_p,
                                            WinEntry *win, double *side_t, unsigned long long *side_p,
                                            unsigned &n, unsigned &wh, unsigned &wn, double &tmin, double &side_min,
-                                           const double h) {
+                                           const double h, WinEntry &head, WinEntry &nxt) {
     for (unsigned j = wh; j < wn; j++) {                // leftover window entries
         const WinEntry w = win_load(win + j * 32);
         rt_t[n * 32] = w.t; rt_p[n * 32] = w.p; n++;
@@ -171,38 +175,22 @@ __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_
     }
     n = k;
     tmin = mn;
-    wh = 0; wn = c;
-}
-
-// second half of the rebuild: the wn candidates of the scratch list, rank-sorted into the window.  The ranks are computed on
-// float keys in shared memory (`keys`, one pool tile per warp, held only here); equal keys (about one pair in a million) are
-// ordered by the exact times.
-__device__ __forceinline__ void ro_rebuild_sort(const double *sc_t, const unsigned long long *sc_p, WinEntry *win, float *keys,
-                                                const unsigned c, const double h, WinEntry &head, WinEntry &nxt) {
     head.t = ORLG_INF; nxt.t = ORLG_INF;
-    for (unsigned j = 0; j < c; j++) keys[j * 32] = __double2float_rd(sc_t[j * 32] - h);      // monotone: key_a < key_b implies t_a < t_b
-    for (unsigned j = 0; j < c; j++) {
-        WinEntry w;
-        w.t = sc_t[j * 32]; w.p = sc_p[j * 32];         // requested first: the latency overlaps the key loop
-        const float kj = keys[j * 32];
-        unsigned rank = 0, ties = 0;
+    for (unsigned j = 0; j < c; j++) {                  // rank sort (c is ~15: quadratic is fine, the loads coalesce)
+        const double tj = sc_t[j * 32];
+        unsigned rank = 0;
 #pragma unroll 4
         for (unsigned q = 0; q < c; q++) {
-            const float kq = keys[q * 32];
-            rank += kq < kj ? 1u : 0u;
-            ties += kq == kj ? 1u : 0u;
+            const double tq = sc_t[q * 32];
+            rank += (tq < tj || (tq == tj && q < j)) ? 1u : 0u;
         }
-        if (ties > 1 || !ORLG_RO_SMEMSORT) {
-            rank = 0;
-            for (unsigned q = 0; q < c; q++) {
-                const double tq = sc_t[q * 32];
-                rank += (tq < w.t || (tq == w.t && q < j)) ? 1u : 0u;
-            }
-        }
+        WinEntry w;
+        w.t = tj; w.p = sc_p[j * 32];
         win[rank * 32] = w;
         if (rank == 0) head = w;
         if (rank == 1) nxt = w;
     }
+    wh = 0; wn = c;
 }
 
 // packed integer pre-image of one path's features: start (7, 127 = no block) | length (7) | total free (7) | free runs (6) | slots (5)
@@ -296,32 +284,43 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     __syncthreads();                 // pool word + table barrier initialised by thread 0 ...
     mbar_wait(tab_bar, 0);           // ... and the tables have landed
     if (env0 >= p.n) return;         // a warp without environments (no CTA-wide barrier below)
-    // ---------------- event tables in: canonical [env][slot] -> lane-interleaved [slot][lane].  Thread per env: the loads
-    // walk the env's own rows (one L2 fetch per 128-byte line, the rest are L1 hits), the stores coalesce.
-    if (live) {
-        const double *__restrict__ ct = p.ev_time + (size_t)e * p.heap_cap;
-        const unsigned long long *__restrict__ cp = p.ev_pay + (size_t)e * p.heap_cap;
-        for (unsigned s0 = 0; s0 < n_tab; s0 += 8) {                 // heap_cap is a multiple of 16: the vector loads stay inside the table
-            double2 a[4];
-            ulonglong2 b[4];
+    if (ra.resume) {
+        // ---------------- the previous launch left the window state behind: nothing to convert or rebuild
+        if (live) {
+            n_tab = ra.st_ntab[e]; wh = ra.st_wh[e]; wn = ra.st_wn[e];
+            tmin_tab = ra.st_tmin[e]; hzn = ra.st_hzn[e];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                a[i] = *reinterpret_cast<const double2 *>(ct + s0 + 2 * i);
-                b[i] = *reinterpret_cast<const ulonglong2 *>(cp + s0 + 2 * i);
+            for (int s = 0; s < RO_SIDE; s++) {
+                const double ts = ra.st_side_t[(size_t)s * p.n + e];
+                side_t[s * 32] = ts; side_p[s * 32] = ra.st_side_p[(size_t)s * p.n + e];
+                side_min = dmin(side_min, ts);
             }
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                rt_t[(s0 + 2 * i) * 32] = a[i].x; rt_t[(s0 + 2 * i + 1) * 32] = a[i].y;
-                rt_p[(s0 + 2 * i) * 32] = b[i].x; rt_p[(s0 + 2 * i + 1) * 32] = b[i].y;
-            }
+            if (wh < wn) head = win_load(win + wh * 32);
+            if (wh + 1 < wn) nxt = win_load(win + (wh + 1) * 32);
         }
-    }
-    {
-        if (live) ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn);
-        const unsigned tile = ro_tile_acquire(pool_free, lane);
-        float *keys = reinterpret_cast<float *>(pool + (size_t)tile * ra.tile_bytes) + lane;
-        if (live) ro_rebuild_sort(sc_t, sc_p, win, keys, wn, hzn, head, nxt);
-        ro_tile_release(pool_free, tile, lane);
+    } else {
+        // ---------------- event tables in: canonical [env][slot] -> lane-interleaved [slot][lane].  Thread per env: the loads
+        // walk the env's own rows (one L2 fetch per 128-byte line, the rest are L1 hits), the stores coalesce.
+        if (live) {
+            ra.st_ncanon[e] = n_tab;
+            const double *__restrict__ ct = p.ev_time + (size_t)e * p.heap_cap;
+            const unsigned long long *__restrict__ cp = p.ev_pay + (size_t)e * p.heap_cap;
+            for (unsigned s0 = 0; s0 < n_tab; s0 += 8) {             // heap_cap is a multiple of 16: the vector loads stay inside the table
+                double2 a[4];
+                ulonglong2 b[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    a[i] = *reinterpret_cast<const double2 *>(ct + s0 + 2 * i);
+                    b[i] = *reinterpret_cast<const ulonglong2 *>(cp + s0 + 2 * i);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    rt_t[(s0 + 2 * i) * 32] = a[i].x; rt_t[(s0 + 2 * i + 1) * 32] = a[i].y;
+                    rt_p[(s0 + 2 * i) * 32] = b[i].x; rt_p[(s0 + 2 * i + 1) * 32] = b[i].y;
+                }
+            }
+            ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt);
+        }
     }
     int npaths_cur = min((int)s_pair_count[src * p.N + dst], KM);       // candidate paths of the pending request
 
@@ -463,12 +462,10 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             RPH_COUNT(15);
             // a retry means the window filled up before every due service was reached: shorter horizon, down to the clock itself
             hzn = tries < 60 ? __dadd_rn(now, __dmul_rn(ra.span, __longlong_as_double((long long)(1023 - tries) << 52))) : now;
-            if (live) ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn);
-            const unsigned tile = ro_tile_acquire(pool_free, lane);
-            float *keys = reinterpret_cast<float *>(pool + (size_t)tile * ra.tile_bytes) + lane;
-            if (live) ro_rebuild_sort(sc_t, sc_p, win, keys, wn, hzn, head, nxt);
-            ro_tile_release(pool_free, tile, lane);
-            if (live) { RO_POP_DUE(); }
+            if (live) {
+                ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt);
+                RO_POP_DUE();
+            }
         }
         RPH_MARK(3);                 // rebuild
         if (live) {
@@ -592,54 +589,16 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     }
 #undef RO_POP_DUE
 
-    // ---------------- state out: canonical form (orlg_device.cuh) for every other entry point
-    const unsigned n_entry = live ? p.nheap[e] : 0u;             // slots the canonical table used before this launch
+    // ---------------- state out: masks, scalars and the window state.  The event storage stays in the launch-private form
+    // (the next orlg_rollout resumes from it; ro_canonicalize_kernel rebuilds the canonical tables for everybody else).
     if (live) {
-        for (unsigned j = wh; j < wn; j++) {                     // window + side entries back to the table
-            const WinEntry w = win_load(win + j * 32);
-            rt_t[n_tab * 32] = w.t; rt_p[n_tab * 32] = w.p; n_tab++;
-        }
+        ra.st_ntab[env] = n_tab; ra.st_wh[env] = wh; ra.st_wn[env] = wn;
+        ra.st_tmin[env] = tmin_tab; ra.st_hzn[env] = hzn;
 #pragma unroll
         for (int s = 0; s < RO_SIDE; s++) {
-            const double ts = side_t[s * 32];
-            if (ts < ORLG_INF) { rt_t[n_tab * 32] = ts; rt_p[n_tab * 32] = side_p[s * 32]; n_tab++; }
+            ra.st_side_t[(size_t)s * p.n + env] = side_t[s * 32];
+            ra.st_side_p[(size_t)s * p.n + env] = side_p[s * 32];
         }
-        if (n_tab != nlive) err |= ORLG_ERR_LOCKSTEP;            // internal consistency (never expected)
-        // lane-interleaved -> canonical [env][slot]: coalesced loads, each thread writes its own rows (16-byte stores)
-        double *ev_tw = p.ev_time + (size_t)e * p.heap_cap;
-        unsigned long long *ev_pw = p.ev_pay + (size_t)e * p.heap_cap;
-        const unsigned n_fill = max(n_tab, n_entry);                 // "every slot >= n holds +INF"
-        for (unsigned s0 = 0; s0 < n_fill; s0 += 8) {
-            double tt[8];
-            unsigned long long pp[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const bool in = s0 + i < n_tab;
-                tt[i] = in ? rt_t[(s0 + i) * 32] : ORLG_INF;
-                pp[i] = in ? rt_p[(s0 + i) * 32] : 0ULL;
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                *reinterpret_cast<double2 *>(ev_tw + s0 + 2 * i) = make_double2(tt[2 * i], tt[2 * i + 1]);
-                *reinterpret_cast<ulonglong2 *>(ev_pw + s0 + 2 * i) = make_ulonglong2(pp[2 * i], pp[2 * i + 1]);
-            }
-        }
-        // directory: float lower bound per FULL group below the tail group, +INF from the tail group on
-        const double *ev_t = p.ev_time + (size_t)e * p.heap_cap;
-        float *gmin = p.ev_gmin + (size_t)e * p.ev_groups;
-        const int tail_g = n_tab ? (int)((n_tab - 1) / EV_GROUP) : 0;
-        double all_min = ORLG_INF, tail_min = ORLG_INF;
-        for (int g = 0; g <= tail_g && n_tab; g++) {
-            double m = ORLG_INF;
-#pragma unroll
-            for (int q = 0; q < EV_GROUP / 2; q++) {
-                const double2 v = *reinterpret_cast<const double2 *>(ev_t + g * EV_GROUP + 2 * q);      // slots >= n hold +INF
-                m = dmin(m, dmin(v.x, v.y));
-            }
-            if (g < tail_g) gmin[g] = lower_f32(m); else tail_min = m;
-            all_min = dmin(all_min, g < tail_g ? (double)lower_f32(m) : m);
-        }
-        for (int g = tail_g; g < p.ev_groups; g++) gmin[g] = ORLG_INF_F;
         uint4 *mw = p.masks + env;
         for (int l = 0; l < E; l++) mw[(size_t)l * p.n] = sm[l * 32];
         p.now[env] = now;
@@ -654,13 +613,74 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
         p.counters[(size_t)6 * p.n + env] = ep_req;
         p.counters[(size_t)7 * p.n + env] = ep_prov;
         p.req_index[env] = ridx;
-        p.nheap[env] = n_tab;
-        p.heap_min[env] = all_min;
-        p.ev_tail[env] = tail_min;
+        p.nheap[env] = nlive;
         p.errors[env] = err;
         *reinterpret_cast<unsigned long long *>(p.cand + (size_t)env * 8) = candw;
     }
-    RPH_MARK(9);                     // exit: canonical state out
+    RPH_MARK(9);                     // exit: state out
+}
+
+// Launch-private event storage -> canonical release-event tables (orlg_device.cuh): window and side entries go back to the
+// table, the table is written out [env][slot] with +INF above, and the directory / tail bound / global bound are rebuilt.
+// Thread per env; launched by the host before any entry point other than orlg_rollout touches the events.
+__global__ void __launch_bounds__(128) ro_canonicalize_kernel(const Params p, const RolloutArgs ra) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.n) return;
+    const int lane = threadIdx.x & 31;
+    const size_t gw = (size_t)(env >> 5);
+    double *const rt_t = ra.rt_t + gw * p.heap_cap * 32 + lane;
+    unsigned long long *const rt_p = ra.rt_p + gw * p.heap_cap * 32 + lane;
+    const WinEntry *const win = ra.win + gw * RO_WCAP * 32 + lane;
+    unsigned n_tab = ra.st_ntab[env];
+    const unsigned wh = ra.st_wh[env], wn = ra.st_wn[env], n_entry = ra.st_ncanon[env];
+    unsigned err = 0;
+    for (unsigned j = wh; j < wn; j++) {                         // window + side entries back to the table
+        const WinEntry w = win_load(win + j * 32);
+        rt_t[n_tab * 32] = w.t; rt_p[n_tab * 32] = w.p; n_tab++;
+    }
+#pragma unroll
+    for (int s = 0; s < RO_SIDE; s++) {
+        const double ts = ra.st_side_t[(size_t)s * p.n + env];
+        if (ts < ORLG_INF) { rt_t[n_tab * 32] = ts; rt_p[n_tab * 32] = ra.st_side_p[(size_t)s * p.n + env]; n_tab++; }
+    }
+    if (n_tab != p.nheap[env]) err |= ORLG_ERR_LOCKSTEP;        // internal consistency (never expected)
+    // lane-interleaved -> canonical [env][slot]: coalesced loads, each thread writes its own rows (16-byte stores)
+    double *ev_t = p.ev_time + (size_t)env * p.heap_cap;
+    unsigned long long *ev_p = p.ev_pay + (size_t)env * p.heap_cap;
+    float *gmin = p.ev_gmin + (size_t)env * p.ev_groups;
+    const unsigned n_fill = max(n_tab, n_entry);                 // "every slot >= n holds +INF"
+    for (unsigned s0 = 0; s0 < n_fill; s0 += 8) {
+        double tt[8];
+        unsigned long long pp[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const bool in = s0 + i < n_tab;
+            tt[i] = in ? rt_t[(s0 + i) * 32] : ORLG_INF;
+            pp[i] = in ? rt_p[(s0 + i) * 32] : 0ULL;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            *reinterpret_cast<double2 *>(ev_t + s0 + 2 * i) = make_double2(tt[2 * i], tt[2 * i + 1]);
+            *reinterpret_cast<ulonglong2 *>(ev_p + s0 + 2 * i) = make_ulonglong2(pp[2 * i], pp[2 * i + 1]);
+        }
+    }
+    // directory: float lower bound per FULL group below the tail group, +INF from the tail group on
+    const int tail_g = n_tab ? (int)((n_tab - 1) / EV_GROUP) : 0;
+    double all_min = ORLG_INF, tail_min = ORLG_INF;
+    for (int g = 0; g <= tail_g && n_tab; g++) {
+        double m = ORLG_INF;
+#pragma unroll
+        for (int q = 0; q < EV_GROUP; q++) {
+            const unsigned sl = (unsigned)(g * EV_GROUP + q);
+            m = dmin(m, sl < n_tab ? rt_t[sl * 32] : ORLG_INF);
+        }
+        if (g < tail_g) gmin[g] = lower_f32(m); else tail_min = m;
+        all_min = dmin(all_min, g < tail_g ? (double)lower_f32(m) : m);
+    }
+    for (int g = tail_g; g < p.ev_groups; g++) gmin[g] = ORLG_INF_F;
+    p.heap_min[env] = all_min;
+    p.ev_tail[env] = tail_min;
+    if (err) p.errors[env] |= err;
 }
 
 }  // namespace orlg
