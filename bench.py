@@ -5,9 +5,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one VecEnv.step of the whole batch (one env-step for each of the 65536 envs of every
-rank) with the uniform random policy drawn on the device.  Prints ONE JSON line (rank 0).
-See DESIGN.md "Measurement" for the definitions of value / e2e / roofline / cpu_baseline.
+One "step" = one env.step of the whole batch (one env-step for each of the 65536 envs of every rank)
+with the uniform random policy drawn on the device.  The K timed steps run as ONE orlg_rollout call
+(persistent kernel: K steps per launch, every step's observation / reward / done / action written to
+[K, N, ...] device buffers), repeated R times; the median repetition is reported (the list is in the
+line).  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for value / e2e / roofline /
+cpu_baseline.
 """
 import argparse
 import json
@@ -133,13 +136,19 @@ def run_reference(args, rank, world):
     vec.run(FILL_STEPS)
     if args.warmup:
         vec.run(args.warmup)
-    t0 = time.perf_counter()
-    vec.run(args.steps)
-    dt = time.perf_counter() - t0
+    # the --steps chunk is repeated until the timed window is at least 2 s (a 20-step chunk alone lasts ~2 ms: pure noise)
+    chunks, t0 = 0, time.perf_counter()
+    while True:
+        vec.run(args.steps)
+        chunks += 1
+        dt = time.perf_counter() - t0
+        if dt >= float(os.environ.get("ORLG_REF_MIN_SECONDS", 2.0)):
+            break
     vec.close()
-    value = n_envs * args.steps / dt
-    sample = "%d of %d envs, %d steps each after a %d-step fill, %d pthreads" % (
-        n_envs, ENVS_PER_GPU * args.gpus, args.steps, FILL_STEPS, threads)
+    value = n_envs * args.steps * chunks / dt
+    dt = dt / chunks
+    sample = "%d of %d envs, %d chunks of %d steps after a %d-step fill, %d pthreads" % (
+        n_envs, ENVS_PER_GPU * args.gpus, chunks, args.steps, FILL_STEPS, threads)
     print(json.dumps({
         "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -150,23 +159,34 @@ def run_reference(args, rank, world):
     }))
 
 
+ROLLOUT_CHUNK = 256      # steps per orlg_rollout launch (bounds the [chunk, N, 54] float32 output buffer: 3.6 GB)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--reps", type=int, default=7, help="repetitions of the --steps block (median reported)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU (default: BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    args.reps = max(args.reps, 1)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+
+    # The CPU baseline runs FIRST, on rank 0, while the other ranks are still blocked in the rendezvous of
+    # init_process_group (a socket wait, no spinning): it has the host cores to itself.
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(os.cpu_count() or 1)
 
     import torch
     import torch.distributed as dist
@@ -180,64 +200,76 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-    n = args.envs
+    n, K = args.envs, args.steps
     env = OpticalVecEnv(ENV_ID, n, nsfnet(), device=dev, env_id_base=rank * n, seed=1, collect_info=False, **ENV_ARGS)
-    actions = torch.empty((n, 1), dtype=torch.int32, device=dev)
-    launches_per_step = 2                               # random_action_kernel + step_kernel
+    chunk = min(K, ROLLOUT_CHUNK)
+    obs = torch.empty((chunk, n, env.obs_dim), dtype=torch.float32, device=dev)
+    rew = torch.empty((chunk, n), dtype=torch.float32, device=dev)
+    done = torch.empty((chunk, n), dtype=torch.uint8, device=dev)
+    act = torch.empty((chunk, n, 1), dtype=torch.int32, device=dev)
+    launches = (K + chunk - 1) // chunk                 # kernel launches per K-step block
 
-    def one_step():
-        env.sample_actions(out=actions)
-        env.step_raw(actions)
+    def k_steps(k):
+        """k env-steps of every env: orlg_rollout launches of <= chunk steps, all outputs written every step."""
+        left = k
+        while left > 0:
+            t = min(left, chunk)
+            env.rollout(t, "random", obs=obs[:t], reward=rew[:t], done=done[:t], actions=act[:t])
+            left -= t
 
-    for _ in range(FILL_STEPS):                         # bring the network to steady state (setup, untimed)
-        one_step()
-    for _ in range(args.warmup):
-        one_step()
+    k_steps(FILL_STEPS)                                 # bring the network to steady state (setup, untimed)
+    k_steps(args.warmup)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
 
-    # ---- timed region: K steps, CUDA events on the launching stream
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- timed region: R repetitions of exactly K steps; each is bracketed by barrier + synchronize and timed with CUDA
+    # events on the launching stream.  A short device-side sleep is queued first so that the host has enqueued
+    # [start event, the block's launches, end event] before the GPU reaches them: no host jitter inside the region.
     sampler = ClockSampler(local_rank)
+    rep_ms = []
     with sampler:
-        ev0.record()
-        for _ in range(args.steps):
-            one_step()
-        ev1.record()
-        torch.cuda.synchronize()
-        elapsed_ms = ev0.elapsed_time(ev1)
+        for _ in range(args.reps):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(400000)
+            ev0.record()
+            k_steps(K)
+            ev1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)        # max over ranks, per repetition
+            rep_ms.append(float(t.item()))
         # keep the GPU under the same load a little longer so that the clock sampler sees it
         t_end = time.perf_counter() + 0.25
         while time.perf_counter() < t_end:
-            for _ in range(200):
-                one_step()
+            k_steps(chunk)
             torch.cuda.synchronize()
+    elapsed_ms = sorted(rep_ms)[len(rep_ms) // 2]
+    value = n * world * K / (elapsed_ms * 1e-3)
     stats = sharding.global_statistics(env.reduce_counters())      # the per-rollout NCCL all-reduce (8e)
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    value = n * world * args.steps / (elapsed_ms * 1e-3)
 
     # ---- end to end through the public API with HOST buffers (pinned): H2D actions, step, D2H obs/reward/done.
     # Every rank runs it at the same time (they share the host's PCIe / memory), max over ranks.
     e2e_result = None
+    actions = torch.empty((n, 1), dtype=torch.int32, device=dev)
+    env.sample_actions(out=actions)
     if not args.no_e2e:
         h_act = torch.zeros((n, 1), dtype=torch.int32).pin_memory()
         h_obs = torch.zeros((n, env.obs_dim), dtype=torch.float32).pin_memory()
         h_rew = torch.zeros(n, dtype=torch.float32).pin_memory()
         h_done = torch.zeros(n, dtype=torch.uint8).pin_memory()
         h_act.copy_(actions.cpu())
-        k_e2e = max(20, min(args.steps, 300))
+        k_e2e = max(20, min(K, 300))
 
         def e2e_step():
             d_act = h_act.to(dev, non_blocking=True)
-            obs, rew, done, _ = env.step(d_act)
-            h_obs.copy_(obs, non_blocking=True)
-            h_rew.copy_(rew, non_blocking=True)
-            h_done.copy_(done, non_blocking=True)
+            o, r, d, _ = env.step(d_act)
+            h_obs.copy_(o, non_blocking=True)
+            h_rew.copy_(r, non_blocking=True)
+            h_done.copy_(d, non_blocking=True)
             torch.cuda.synchronize()            # the host policy needs the observation before it can act
 
         for _ in range(5):
@@ -258,60 +290,52 @@ def main():
 
     out = None
     if rank == 0:
-        # ---- roofline of the dominant kernel (step_kernel): events around each step launch only
-        reps = min(args.steps, 500)
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-        for a, b in evs:
-            env.sample_actions(out=actions)
-            a.record()
-            env.step_raw(actions)
-            b.record()
-        torch.cuda.synchronize()
-        step_ms = sum(a.elapsed_time(b) for a, b in evs) / reps
+        # ---- roofline of the dominant kernel: the timed region IS that kernel (one launch per <= 256 steps)
         peak, peak_src = read_peaks()
-        achieved = B_STEP * n / (step_ms * 1e-3) / 1e9
-        # in the timed region the kernels are chained by programmatic dependent launch, so the step kernel's prologue
-        # runs under the previous kernel's tail; ms_per_step (action kernel included) bounds its in-stream cost
-        in_stream = B_STEP * n / (elapsed_ms / args.steps * 1e-3) / 1e9
+        achieved = B_STEP * n * K / (elapsed_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "deeprmsa_fast_kernel<22,5,1,false,true>", "kernel_ms": step_ms,
-                    "algorithmic_bytes_per_env_step": B_STEP, "peak_source": peak_src,
-                    "note": "kernel_ms = events around isolated step-kernel launches (no overlap with neighbours)",
-                    "achieved_in_stream": in_stream, "frac_in_stream": in_stream / peak}
+                    "traffic": None, "kernel": "deeprmsa_rollout_kernel<22,0>", "kernel_ms": elapsed_ms / launches,
+                    "steps_per_launch": chunk, "algorithmic_bytes_per_env_step": B_STEP,
+                    "algorithmic_bytes_per_launch": B_STEP * n * chunk, "peak_source": peak_src,
+                    "note": "achieved = 868 B x envs x steps of one launch / its CUDA-event duration; the kernel keeps masks and "
+                            "scalars on chip across the steps of a launch, so its DRAM traffic is BELOW the algorithmic bytes"}
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                roofline["traffic"] = json.load(f).get("step_kernel_dram_bytes_per_launch")
+                tj = json.load(f)
+            roofline["traffic"] = tj.get("rollout_kernel_dram_bytes_per_launch")
+            roofline["traffic_steps_per_launch"] = tj.get("rollout_kernel_steps_per_launch")
         except Exception:  # noqa: BLE001
             pass
 
-        # ---- cold-L2 variant: flush L2 (write a 256 MB buffer) before every timed step
-        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-        cold = []
-        for _ in range(50):
+        # ---- the step-by-step path (one policy launch + one step launch per step), for comparison
+        for _ in range(20):
             env.sample_actions(out=actions)
-            flush.fill_(1)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
             env.step_raw(actions)
-            b.record()
-            torch.cuda.synchronize()
-            cold.append(a.elapsed_time(b))
-        del flush
-        cold_ms = sorted(cold)[len(cold) // 2]
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(400000)
+        a.record()
+        for _ in range(200):
+            env.sample_actions(out=actions)
+            env.step_raw(actions)
+        b.record()
+        torch.cuda.synchronize()
+        step_path_ms = a.elapsed_time(b) / 200
 
-        e2e = e2e_result
-
-        cpu = None if args.no_cpu_baseline else cpu_baseline(os.cpu_count() or 1)
         out = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "steps": K, "warmup": args.warmup, "ms_per_step": elapsed_ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": WORKLOAD % n, "envs_per_gpu": n, "fill_steps": FILL_STEPS, "obs": "float32 [N,54] on device",
-                       "l2": "no flush: state %.0f MB/GPU (> 126 MB L2) is re-touched every step as in a rollout; "
-                             "cold-L2 step time in cold_l2_ms_per_step" % (env.state_bytes / 1e6),
+            "config": {"workload": WORKLOAD % n, "envs_per_gpu": n, "fill_steps": FILL_STEPS,
+                       "obs": "float32 [steps, N, 54] on device, every step written",
+                       "call": "orlg_rollout: %d steps per launch, %d launch(es) per timed block" % (chunk, launches),
+                       "l2": "no flush: the %d-step output block (%.0f MB) and the event storage (%.0f MB) exceed the 126 MB L2; "
+                             "masks and scalars stay on chip by design" % (chunk, chunk * n * (env.obs_dim * 4 + 9) / 1e6,
+                                                                            env.state_bytes / 1e6),
                        "parallelism": "env-sharded x%d, no data-path collective" % world},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "clocks": sampler.summary(), "cold_l2_ms_per_step": cold_ms,
+            "timing": {"reps": args.reps, "rep_ms": rep_ms, "stat": "median of the repetitions (each: max over ranks)"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e_result, "gpu_launches": launches,
+            "clocks": sampler.summary(), "step_path_ms_per_step": step_path_ms,
             "accept_rate": 1.0 - stats["service_blocking_rate"], "envs_with_errors": stats["envs_with_errors"],
         }
     if world > 1:

@@ -139,6 +139,7 @@ __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_
                                            WinEntry *win, double *side_t, unsigned long long *side_p,
                                            unsigned &n, unsigned &wh, unsigned &wn, double &tmin, double &side_min,
                                            const double h, WinEntry &head, WinEntry &nxt) {
+    RPH_INIT();
     for (unsigned j = wh; j < wn; j++) {                // leftover window entries
         const WinEntry w = win_load(win + j * 32);
         rt_t[n * 32] = w.t; rt_p[n * 32] = w.p; n++;
@@ -149,6 +150,7 @@ __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_
         if (t < ORLG_INF) { rt_t[n * 32] = t; rt_p[n * 32] = side_p[s * 32]; n++; side_t[s * 32] = ORLG_INF; }
     }
     side_min = ORLG_INF;
+    RPH_MARK(11);                                       // rebuild: window + side back to the table
     unsigned k = 0, c = 0;
     double mn = ORLG_INF;
     for (unsigned s0 = 0; s0 < n; s0 += 8) {            // 16 independent (coalesced) loads per pass
@@ -175,6 +177,7 @@ __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_
     }
     n = k;
     tmin = mn;
+    RPH_MARK(12);                                       // rebuild: streaming pass
     head.t = ORLG_INF; nxt.t = ORLG_INF;
     for (unsigned j = 0; j < c; j++) {                  // rank sort (c is ~15: quadratic is fine, the loads coalesce)
         const double tj = sc_t[j * 32];
@@ -191,6 +194,7 @@ __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_
         if (rank == 1) nxt = w;
     }
     wh = 0; wn = c;
+    RPH_MARK(13);                                       // rebuild: rank sort
 }
 
 // packed integer pre-image of one path's features: start (7, 127 = no block) | length (7) | total free (7) | free runs (6) | slots (5)

@@ -1,2 +1,1 @@
-python -m pytest tests/test_rollout.py -x -q 2>&1 | tail -3
-for T in 256 64 20; do python tools/time_rollout.py 65536 $T 10 2>&1 | tail -1; done
+ORLG_NVCC_EXTRA=-DORLG_PHASE_TIMING python optical-rl-gym_b200/optical_rl_gym_b200/build.py > /dev/null 2>&1; python tools/rollout_phases.py 65536 256 2;  python tools/rollout_phases.py 65536 20 10

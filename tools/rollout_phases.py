@@ -37,3 +37,5 @@ print("avg cycles per warp per step: %.0f (+ entry %.0f, exit %.0f per launch); 
     tot / warps / steps, buf[8] / warps / launches, buf[9] / warps / launches, buf[15] / warps / steps))
 for i, nm in [(j, NAMES[j]) for j in (0, 1, 2, 3, 10, 5, 4, 6, 7)]:
     print("%-22s %8.0f cycles  %5.1f%%" % (nm, buf[i] / warps / steps, 100.0 * buf[i] / tot))
+for i, nm in ((11, "  rebuild: flush"), (12, "  rebuild: scan"), (13, "  rebuild: sort")):
+    print("%-22s %8.0f cycles per rebuild" % (nm, buf[i] / max(buf[15], 1)))
