@@ -178,6 +178,13 @@ int orlg_random_actions(orlg_env *env, int32_t *actions_dev, orlg_stream stream)
 int orlg_num_bit_rates(const orlg_env *env);    /* 0 unless RMSA-v0 with discrete bit rates */
 int orlg_bit_rate_blocking(orlg_env *env, double *out_dev, orlg_stream stream);
 
+/* RWA-v0: info["path_action_probability"] and info["wavelength_action_probability"] (rwa_env.py:148-151), the normalised
+ * marginals of the actions_output histogram (rwa_env.py:52-58, 103) as of the last orlg_step: float64
+ * [num_envs, orlg_action_hist_dim] = (k + rej) path entries, then (W + rej) wavelength entries (rej = allow_rejection).
+ * An action outside the histogram (IndexError in the reference) is not counted and sets ORLG_ERR_NO_SUCH_PATH. */
+int orlg_action_hist_dim(const orlg_env *env);  /* 0 unless RWA-v0 */
+int orlg_action_probability(orlg_env *env, double *out_dev, orlg_stream stream);
+
 /* ---- gym wrappers of the reference, batched ---------------------------- */
 /* SimpleMatrixObservation.observation (rmsa_env.py:806-837, rmcsa_env.py:914-947) of every env:
  * uint8 [num_envs, orlg_matrix_obs_dim] = one-hot(min(src_id, dst_id)) [nodes], one-hot(max(src_id, dst_id))

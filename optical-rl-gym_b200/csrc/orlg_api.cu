@@ -457,6 +457,7 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     if (!rc && wide && cfg->kind == ORLG_DEEPRMSA) rc = dev_alloc(env, &p.cand16, n * (size_t)p.cand_stride);
     if (!rc) rc = dev_alloc(env, &p.errors, n);
     if (!rc && cfg->kind == ORLG_RMSA && t->num_bit_rates > 0) rc = dev_alloc(env, &p.br_hist, 2 * (size_t)t->num_bit_rates * n);
+    if (!rc && cfg->kind == ORLG_RWA) rc = dev_alloc(env, &p.act_hist, (size_t)(p.k + p.S + 2 * p.allow_rejection) * n);
     if (rc) { orlg_destroy(env); return rc; }
 
     // ---- fast DeepRMSA kernel: small tables packed for shared-memory staging
@@ -785,6 +786,17 @@ int orlg_bit_rate_blocking(orlg_env *env, double *out_dev, orlg_stream stream) {
     DeviceGuard guard(env->device);
     if (!env->p.br_hist) return fail(ORLG_E_UNSUPPORTED, "per-bit-rate statistics exist for RMSA-v0 with bit_rate_selection='discrete'");
     bit_rate_blocking_kernel<<<(env->p.n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->p, out_dev);
+    CUDA_OK(cudaGetLastError());
+    return ORLG_OK;
+}
+
+int orlg_action_hist_dim(const orlg_env *env) { return env->p.act_hist ? env->p.k + env->p.S + 2 * env->p.allow_rejection : 0; }
+
+int orlg_action_probability(orlg_env *env, double *out_dev, orlg_stream stream) {
+    if (!env || !out_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
+    if (!env->p.act_hist) return fail(ORLG_E_UNSUPPORTED, "action probabilities are part of info for RWA-v0 only (rwa_env.py:148-151)");
+    DeviceGuard guard(env->device);
+    action_probability_kernel<<<(env->p.n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->p, out_dev);
     CUDA_OK(cudaGetLastError());
     return ORLG_OK;
 }

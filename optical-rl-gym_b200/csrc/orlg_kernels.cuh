@@ -74,6 +74,8 @@ struct Params {
     const int *link_order;             // [E] link indices in topology.edges() order (np.mean over the links)
     // ---- discrete bit-rate selection (row f4: rmsa_env.py:88-110, 217-227, 268-273, 408-415, 579-581)
     int *br_hist;                      // [2][n_bit_rates][n] bit_rate_requested_histogram / bit_rate_provisioned_histogram
+    // ---- RWA actions_output (rwa_env.py:52-58, 103): only its marginals reach `info` (rwa_env.py:148-151)
+    int *act_hist;                     // [(k + rej) + (S + rej)][n] row sums, then column sums (NULL unless RWA-v0)
 };
 
 // position of a bit rate in the discrete list (-1: not one of them, e.g. a foreign trace)
@@ -86,6 +88,23 @@ __device__ __forceinline__ void br_hist_bump(const Params &p, int env, int which
     if (!p.br_hist) return;
     const int i = br_index(p, br);
     if (i >= 0) p.br_hist[((size_t)which * p.n_bit_rates + i) * p.n + env] += 1;
+}
+// self.actions_output[path, wavelength] += 1 (rwa_env.py:103); an index outside the (k + rej, W + rej) histogram is an
+// IndexError in the reference: flagged here, nothing counted
+__device__ __forceinline__ void act_hist_bump(const Params &p, int env, int path, int slot, unsigned &err) {
+    if (!p.act_hist) return;
+    const int R = p.k + p.allow_rejection, Cn = p.S + p.allow_rejection;
+    if (path >= 0 && path < R && slot >= 0 && slot < Cn) {
+        p.act_hist[(size_t)path * p.n + env] += 1;
+        p.act_hist[(size_t)(R + slot) * p.n + env] += 1;
+    } else {
+        err |= ORLG_ERR_NO_SUCH_PATH;
+    }
+}
+__device__ __forceinline__ void act_hist_clear(const Params &p, int env) {
+    if (!p.act_hist) return;
+    const int rows = p.k + p.S + 2 * p.allow_rejection;
+    for (int i = 0; i < rows; i++) p.act_hist[(size_t)i * p.n + env] = 0;
 }
 __device__ __forceinline__ void br_hist_clear(const Params &p, int env) {
     if (!p.br_hist) return;
@@ -297,6 +316,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
 #pragma unroll
         for (int q = 0; q < 8; q++) cnt[q] = 0;
         if (KIND == ORLG_RMSA) br_hist_clear(p, env);
+        if (KIND == ORLG_RWA) act_hist_clear(p, env);          // rwa_env.py:195-201
     }
 
     if (mode == MODE_STEP) {
@@ -329,6 +349,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
         } else if (KIND == ORLG_RMSA || KIND == ORLG_RWA) {
             // rmsa_env.py:174-200 / rwa_env.py:104-127
             int path = io.actions[2 * e], slot = io.actions[2 * e + 1];
+            if (KIND == ORLG_RWA) act_hist_bump(p, env, path, slot, err);
             if (path >= 0 && path < p.k && slot >= 0 && slot < p.S) {
                 if (path < npaths) {
                     row = first + path;
@@ -815,6 +836,18 @@ __global__ void bit_rate_blocking_kernel(const Params p, double *out) {
         hi = i == 0 ? b : fmax(hi, b);
     }
     out[(size_t)env * (B + 1) + B] = __dadd_rn(hi, -lo);
+}
+
+// info["path_action_probability"] ++ info["wavelength_action_probability"] (rwa_env.py:148-151): marginals of
+// actions_output divided by its total (int / int -> float64, like numpy)
+__global__ void action_probability_kernel(const Params p, double *out) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.n) return;
+    const int R = p.k + p.allow_rejection, Cn = p.S + p.allow_rejection;
+    long long total = 0;
+    for (int i = 0; i < R; i++) total += p.act_hist[(size_t)i * p.n + env];
+    for (int i = 0; i < R + Cn; i++)
+        out[(size_t)env * (R + Cn) + i] = __ddiv_rn((double)p.act_hist[(size_t)i * p.n + env], (double)total);
 }
 
 // per-device sums of the 8 counters (+ #envs with an error flag) for the cross-GPU all-reduce

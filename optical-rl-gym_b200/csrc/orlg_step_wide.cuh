@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(128) step_wide_kernel(const Params p, const St
 #pragma unroll
         for (int q = 0; q < 8; q++) cnt[q] = 0;
         if (KIND == ORLG_RMSA) br_hist_clear(p, env);
+        if (KIND == ORLG_RWA) act_hist_clear(p, env);
     }
 
     if (mode == MODE_STEP) {
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(128) step_wide_kernel(const Params p, const St
             }
         } else if (KIND == ORLG_RMSA || KIND == ORLG_RWA) {
             const int path = io.actions[2 * env], slot = io.actions[2 * env + 1];
+            if (KIND == ORLG_RWA) act_hist_bump(p, env, path, slot, err);
             if (path >= 0 && path < p.k && slot >= 0 && slot < p.S) {
                 if (path < npaths) {
                     row = first + path;

@@ -86,6 +86,8 @@ def lib():
     L.orlg_matrix_obs_dim.argtypes = [vp]
     L.orlg_matrix_observation.argtypes = [vp, vp, vp]
     L.orlg_path_only_first_fit.argtypes = [vp, vp, vp, vp]
+    L.orlg_action_hist_dim.argtypes = [vp]
+    L.orlg_action_probability.argtypes = [vp, vp, vp]
     L.orlg_rollout.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     _lib = L
     return L
@@ -101,4 +103,4 @@ EXPORTED = ["orlg_create", "orlg_destroy", "orlg_last_error", "orlg_version", "o
             "orlg_observation", "orlg_observation_int", "orlg_heuristic", "orlg_random_actions", "orlg_get_counters",
             "orlg_get_requests", "orlg_export_state", "orlg_error_flags", "orlg_reduce_counters", "orlg_enable_stats",
             "orlg_num_bit_rates", "orlg_bit_rate_blocking", "orlg_matrix_obs_dim", "orlg_matrix_observation",
-            "orlg_path_only_first_fit", "orlg_rollout"]
+            "orlg_path_only_first_fit", "orlg_rollout", "orlg_action_hist_dim", "orlg_action_probability"]

@@ -60,12 +60,16 @@ class StepInfo:
             "bit_rate_blocking_rate": (4, 5), "episode_bit_rate_blocking_rate": (6, 7)}
 
     def __init__(self, counters: torch.Tensor, keys, stats: Optional[torch.Tensor] = None,
-                 bit_rate_blocking: Optional[torch.Tensor] = None, bit_rates=()):
+                 bit_rate_blocking: Optional[torch.Tensor] = None, bit_rates=(),
+                 action_probability: Optional[torch.Tensor] = None, n_path_actions: int = 0):
         self.counters = counters       # int64 [N, 8]
         self.stats = stats             # float64 [N, 4] (rmsa_env.py:249-263) when link_stats=True
         self.bit_rate_blocking = bit_rate_blocking     # float64 [N, B + 1] (rmsa_env.py:217-227, 268-273), discrete mode
         self._br_keys = ["bit_rate_blocking_%d" % int(b) for b in bit_rates] + ["fairness"] if bit_rate_blocking is not None else []
-        self._keys = list(keys) + (STAT_KEYS if stats is not None else []) + self._br_keys
+        # RWA-v0: float64 [N, (k + rej) + (W + rej)] (rwa_env.py:148-151)
+        self.action_probability, self._n_path_actions = action_probability, n_path_actions
+        self._ap_keys = ["path_action_probability", "wavelength_action_probability"] if action_probability is not None else []
+        self._keys = list(keys) + (STAT_KEYS if stats is not None else []) + self._br_keys + self._ap_keys
 
     def keys(self):
         return list(self._keys)
@@ -83,6 +87,10 @@ class StepInfo:
             return self.stats[:, STAT_KEYS.index(key)]
         if key in self._br_keys:
             return self.bit_rate_blocking[:, self._br_keys.index(key)]
+        if key == "path_action_probability":
+            return self.action_probability[:, :self._n_path_actions]
+        if key == "wavelength_action_probability":
+            return self.action_probability[:, self._n_path_actions:]
         a, b = self._COL[key]
         c = self.counters
         return (c[:, a] - c[:, b]).to(torch.float64) / c[:, a].to(torch.float64)
@@ -241,6 +249,11 @@ class OpticalVecEnv:
         nb = self._lib.orlg_num_bit_rates(self._h)
         if nb and collect_info:
             self._brb = torch.zeros((n, nb + 1), dtype=torch.float64, device=dev)
+        # RWA-v0: the action-probability entries of `info` (rwa_env.py:148-151)
+        self._ap = None
+        nh = self._lib.orlg_action_hist_dim(self._h)
+        if nh and collect_info:
+            self._ap = torch.zeros((n, nh), dtype=torch.float64, device=dev)
         if traffic == "philox" and a.get("reset", True):
             self.reset(full=True)
 
@@ -322,7 +335,10 @@ class OpticalVecEnv:
         if self._info is not None:
             if self._brb is not None:
                 nat.check(self._lib.orlg_bit_rate_blocking(self._h, _ptr(self._brb), self._stream()))
-            info = StepInfo(self._info, self.metadata["metrics"], self._stats, self._brb, self.bit_rates)
+            if self._ap is not None:
+                nat.check(self._lib.orlg_action_probability(self._h, _ptr(self._ap), self._stream()))
+            info = StepInfo(self._info, self.metadata["metrics"], self._stats, self._brb, self.bit_rates,
+                            self._ap, self.k_paths + self.reject_action)
         return self._obs, self._reward, self._done, info
 
     def step(self, actions):

@@ -65,6 +65,7 @@ def lib():
         L.oracle_get_request.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_get_counters.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_get_bit_rate_blocking.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_get_action_probability.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 4
         L.oracle_error.argtypes = [C.c_void_p]
         L.oracle_error.restype = C.c_int
@@ -197,6 +198,14 @@ class OracleEnv:
         out = np.zeros(self.cfg.num_bit_rates + 1, np.float64)
         self.L.oracle_get_bit_rate_blocking(self.h, _ptr(out))
         return out
+
+    def action_probability(self):
+        """RWA: (info["path_action_probability"], info["wavelength_action_probability"]) after the last step."""
+        rej = int(self.cfg.allow_rejection)
+        R, Cn = self.cfg.k_paths + rej, self.cfg.num_slots + rej
+        out = np.zeros(R + Cn, np.float64)
+        self.L.oracle_get_action_probability(self.h, _ptr(out))
+        return out[:R].copy(), out[R:].copy()
 
     def state(self):
         avail = np.zeros(self.cells, np.int8)

@@ -94,6 +94,8 @@ typedef struct {
        and what step() derives from them for `info` (rmsa_env.py:217-227, 268-273) */
     int64_t hist_req[64], hist_prov[64];
     double br_blocking[65];                       /* per bit rate (order of bit_rates), then fairness */
+    /* RWA actions_output (rwa_env.py:52-58, 103): only its marginals reach `info` (rwa_env.py:148-151) */
+    int64_t act_rows[32], act_cols[520], act_total;
 } oenv_t;
 
 static int br_slot(const oenv_t *e, int bit_rate) {
@@ -558,6 +560,7 @@ void oracle_reset(void *p, int full) {
     e->processed = e->accepted = 0; e->br_req = e->br_prov = 0;
     e->req_index = 0;
     memset(e->hist_req, 0, sizeof(e->hist_req)); memset(e->hist_prov, 0, sizeof(e->hist_prov));   /* rmsa_env.py:348-349 */
+    memset(e->act_rows, 0, sizeof(e->act_rows)); memset(e->act_cols, 0, sizeof(e->act_cols)); e->act_total = 0;   /* rwa_env.py:195-201 */
     e->sum_nh = 0;
     for (int l = 0; l < e->c.num_links; l++) { e->link_util[l] = 0.0; e->link_comp[l] = 0.0; e->link_last[l] = 0.0; }
     size_t cells = (size_t)e->c.num_cores * e->c.num_links * e->c.num_slots;
@@ -649,6 +652,11 @@ int oracle_step(void *p, const int32_t *action, ostep_t *o) {
     case KIND_RWA: {                               /* rwa_env.py:101-162 */
         int path = action[0], w = action[1], rc = 0;
         e->cur.accepted = 0;
+        {   /* self.actions_output[path, wavelength] += 1 (rwa_env.py:103); shape (k + rej, W + rej) */
+            const int rej = e->c.allow_rejection ? 1 : 0;
+            if (path >= 0 && path < k + rej && w >= 0 && w < S + rej) { e->act_rows[path]++; e->act_cols[w]++; e->act_total++; }
+            else rc = -1;                              /* numpy would raise IndexError */
+        }
         if (path < k && w < S && path >= 0 && w >= 0) {
             int row = pair_row(e, e->cur.src, e->cur.dst, path);
             if (row < 0) rc = -1;
@@ -866,6 +874,15 @@ void oracle_get_request(void *p, double *arrival, double *holding, int32_t *ints
 void oracle_get_bit_rate_blocking(void *p, double *out /* [num_bit_rates + 1] */) {
     oenv_t *e = (oenv_t *)p;
     for (int i = 0; i <= e->c.num_bit_rates; i++) out[i] = e->br_blocking[i];
+}
+
+/* info["path_action_probability"] ++ info["wavelength_action_probability"] (rwa_env.py:148-151):
+   np.sum(actions_output, axis=1) / np.sum(actions_output), then axis=0 */
+void oracle_get_action_probability(void *p, double *out /* [(k + rej) + (W + rej)] */) {
+    oenv_t *e = (oenv_t *)p;
+    const int rej = e->c.allow_rejection ? 1 : 0, R = e->c.k_paths + rej, Cn = e->c.num_slots + rej;
+    for (int i = 0; i < R; i++) out[i] = (double)e->act_rows[i] / (double)e->act_total;
+    for (int i = 0; i < Cn; i++) out[R + i] = (double)e->act_cols[i] / (double)e->act_total;
 }
 
 void oracle_get_counters(void *p, int64_t *c /* [8] */) {

@@ -193,6 +193,9 @@ def record(kind, env_args, policy, n_envs, T, seed0, n_mask_envs=1):
             for key, val in info.items():
                 if np.ndim(val) == 0:
                     put("info_" + key, i, t, float(val), (n_envs, T), np.float64)
+                elif key in ("path_action_probability", "wavelength_action_probability"):      # rwa_env.py:148-151
+                    val = np.asarray(val, np.float64)
+                    put("info_" + key, i, t, val, (n_envs, T, len(val)), np.float64)
             if i < n_mask_envs:
                 bits = np.packbits(avail_of(env, kind).reshape(Cc * E, S).astype(np.uint8), axis=1, bitorder="little")
                 put("avail_bits", i, t, bits, (n_mask_envs, T, Cc * E, bits.shape[1]), np.uint8)

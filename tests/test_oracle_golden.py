@@ -49,6 +49,10 @@ def replay(g, i, use_heuristic=False):
             assert o.stats[1] == g["info_network_compactness_difference"][i, t], ("compactness difference", t)
             assert o.stats[2] == g["info_avg_link_compactness"][i, t], ("avg_link_compactness", t, o.stats[2], g["info_avg_link_compactness"][i, t])
             assert o.stats[3] == g["info_avg_link_utilization"][i, t], ("avg_link_utilization", t)
+        if "info_path_action_probability" in g:      # a18: rwa_env.py:148-151, marginals of actions_output
+            pa, wa = e.action_probability()
+            assert np.array_equal(pa, g["info_path_action_probability"][i, t]), ("path_action_probability", t)
+            assert np.array_equal(wa, g["info_wavelength_action_probability"][i, t]), ("wavelength_action_probability", t)
         if "info_fairness" in g:                     # row f4: discrete bit rates (rmsa_env.py:217-227, 268-273)
             brb = e.bit_rate_blocking()
             for b, rate in enumerate(helpers.sim_kwargs(meta)["bit_rates"]):
