@@ -12,7 +12,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def golden_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not p.endswith("nsfnet_tables.npz") and not os.path.basename(p).startswith(("wrap_", "topo_")))
+                  if not p.endswith("nsfnet_tables.npz") and not os.path.basename(p).startswith(("wrap_", "topo_", "traffic_")))
 
 
 def load_golden(name):
