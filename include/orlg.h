@@ -38,7 +38,8 @@ enum {
     ORLG_ERR_HEAP_OVERFLOW = 2,    /* more live services than heap_capacity: the request was blocked */
     ORLG_ERR_NO_SUCH_PATH = 4,     /* action chose path >= number of candidate paths (reference: IndexError) */
     ORLG_ERR_LOCKSTEP = 8,         /* internal: an env's request counter left the handle's lockstep count */
-    ORLG_ERR_STATS_ORDER = 16      /* > 24 services released in one step: float statistics updated out of time order */
+    ORLG_ERR_STATS_ORDER = 16,     /* > 24 services released in one step: float statistics updated out of time order */
+    ORLG_ERR_TRACE_RANGE = 32      /* orlg_rollout replay: a trace bit rate above 127 Gb/s (clamped) */
 };
 
 typedef struct orlg_env orlg_env;     /* opaque handle: owns all per-environment state in HBM */
@@ -142,13 +143,14 @@ int orlg_step(orlg_env *env, const int32_t *actions_dev, void *obs_dev, float *r
 /* T consecutive steps in ONE call: T iterations of { action = policy(env); obs, reward, done, _ = env.step(action) }
  * (the rollout loop of examples/stable_baselines3/DeepRMSA.ipynb / utils.py:103-141 evaluate_heuristic), every step's
  * results kept:
- *   policy        ORLG_POLICY_RANDOM (orlg_random_actions) or an ORLG_HEUR_* id (orlg_heuristic)
+ *   policy        ORLG_POLICY_RANDOM (orlg_random_actions), an ORLG_HEUR_* id (orlg_heuristic), or ORLG_POLICY_REPLAY
+ *                 (actions_dev holds the actions to apply: with trace traffic this replays a recorded reference run)
  *   obs_dev       [steps, num_envs, obs_dim]  (NULL: skip)      reward_dev  f32 [steps, num_envs]  (NULL: skip)
  *   done_dev      u8 [steps, num_envs]        (NULL: skip)      actions_dev int32 [steps, num_envs, action_dim] (NULL: skip)
  * Identical results to the step-by-step calls.  For DeepRMSA-v0 on NSFNET-class topologies with Philox traffic and
  * float32 observations the T steps run inside one persistent kernel (state stays on chip); every other configuration
  * issues the per-step kernels. */
-enum { ORLG_POLICY_RANDOM = -1 };
+enum { ORLG_POLICY_RANDOM = -1, ORLG_POLICY_REPLAY = -2 };   /* REPLAY: actions_dev is the INPUT action sequence [steps, num_envs, action_dim] */
 int orlg_rollout(orlg_env *env, int steps, int policy, void *obs_dev, float *reward_dev, uint8_t *done_dev,
                  int32_t *actions_dev, orlg_stream stream);
 

@@ -286,7 +286,13 @@ cudaError_t launch_rollout(const orlg_env *env, const RolloutArgs &ra, int polic
         e = cudaFuncSetAttribute(deeprmsa_rollout_kernel<ET, POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, deeprmsa_rollout_kernel<ET, POL>, env->p, ra);            \
     } while (0)
-    if (policy == ORLG_POLICY_RANDOM) ORLG_RO_LAUNCH(RO_POLICY_RANDOM);
+    const bool trace = env->p.traffic == ORLG_TRAFFIC_TRACE;
+    if (policy == ORLG_POLICY_REPLAY) {
+        if (trace) {
+            e = cudaFuncSetAttribute(deeprmsa_rollout_kernel<ET, RO_POLICY_REPLAY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, deeprmsa_rollout_kernel<ET, RO_POLICY_REPLAY, true>, env->p, ra);
+        } else ORLG_RO_LAUNCH(RO_POLICY_REPLAY);
+    } else if (policy == ORLG_POLICY_RANDOM) ORLG_RO_LAUNCH(RO_POLICY_RANDOM);
     else if (policy == ORLG_HEUR_SP_FF) ORLG_RO_LAUNCH(RO_POLICY_SP_FF);
     else ORLG_RO_LAUNCH(RO_POLICY_SAP_FF);
 #undef ORLG_RO_LAUNCH
@@ -836,12 +842,16 @@ int orlg_rollout(orlg_env *env, int steps, int policy, void *obs_dev, float *rew
     if (!env) return fail(ORLG_E_INVALID, "null handle");
     DeviceGuard guard(env->device);
     if (steps < 0) return fail(ORLG_E_INVALID, "steps must be >= 0");
-    if (policy != ORLG_POLICY_RANDOM && (policy < 0 || policy > ORLG_HEUR_SAP_LF)) return fail(ORLG_E_INVALID, "unknown policy");
+    if (policy != ORLG_POLICY_RANDOM && policy != ORLG_POLICY_REPLAY && (policy < 0 || policy > ORLG_HEUR_SAP_LF)) return fail(ORLG_E_INVALID, "unknown policy");
+    if (policy == ORLG_POLICY_REPLAY && !actions_dev) return fail(ORLG_E_INVALID, "ORLG_POLICY_REPLAY needs the action sequence in actions_dev");
+    if (env->p.traffic == ORLG_TRAFFIC_TRACE && env->p.trace == nullptr) return fail(ORLG_E_INVALID, "trace traffic selected but orlg_set_trace was not called");
     if (steps == 0) return ORLG_OK;
     Params &p = env->p;
     cudaStream_t s = (cudaStream_t)stream;
-    const bool persistent = env->hot && !p.stats && p.traffic == ORLG_TRAFFIC_PHILOX && !p.obs_f64 &&
-                            (policy == ORLG_POLICY_RANDOM || policy == ORLG_HEUR_SP_FF || policy == ORLG_HEUR_SAP_FF) &&
+    const bool persistent = env->hot && !p.stats && !p.obs_f64 &&
+                            (p.traffic == ORLG_TRAFFIC_PHILOX ? (policy == ORLG_POLICY_RANDOM || policy == ORLG_POLICY_REPLAY ||
+                                                                 policy == ORLG_HEUR_SP_FF || policy == ORLG_HEUR_SAP_FF)
+                                                              : policy == ORLG_POLICY_REPLAY) &&
                             !std::getenv("ORLG_NO_ROLLOUT_KERNEL");
     RolloutArgs ra;
     std::memset(&ra, 0, sizeof(ra));
@@ -881,14 +891,15 @@ int orlg_rollout(orlg_env *env, int steps, int policy, void *obs_dev, float *rew
         if (rc) return rc;
     }
     const int adim = orlg_action_dim(env);
-    if (!actions_dev && !env->ro_actions) {
+    if (policy != ORLG_POLICY_REPLAY && !actions_dev && !env->ro_actions) {
         int rc = dev_alloc(env, &env->ro_actions, (size_t)p.n * adim, false);
         if (rc) return rc;
     }
     const size_t obs_row = (size_t)p.obs_dim * (p.obs_f64 ? 8 : 4);
     for (int t = 0; t < steps; t++) {
         int32_t *a = actions_dev ? actions_dev + (size_t)t * p.n * adim : env->ro_actions;
-        int rc = policy == ORLG_POLICY_RANDOM ? orlg_random_actions(env, a, stream) : orlg_heuristic(env, policy, a, stream);
+        int rc = policy == ORLG_POLICY_REPLAY ? ORLG_OK
+                 : (policy == ORLG_POLICY_RANDOM ? orlg_random_actions(env, a, stream) : orlg_heuristic(env, policy, a, stream));
         if (rc) return rc;
         rc = orlg_step(env, a, (obs_dev && p.obs_dim) ? reinterpret_cast<unsigned char *>(obs_dev) + (size_t)t * p.n * obs_row : nullptr,
                        reward_dev ? reward_dev + (size_t)t * p.n : nullptr, done_dev ? done_dev + (size_t)t * p.n : nullptr,

@@ -36,7 +36,7 @@ namespace orlg {
 constexpr int RO_WCAP = 64;            // window entries per env
 constexpr int RO_SIDE = 3;             // side-buffer entries per env (shared memory)
 constexpr int RO_MAX_THREADS = 448;    // 14 warps x 148 SMs >= 65536 envs in one wave
-enum { RO_POLICY_RANDOM = 0, RO_POLICY_SP_FF = 1, RO_POLICY_SAP_FF = 2 };
+enum { RO_POLICY_RANDOM = 0, RO_POLICY_SP_FF = 1, RO_POLICY_SAP_FF = 2, RO_POLICY_REPLAY = 3 };
 
 // optional cycle accounting per warp (instrumented builds: -DORLG_PHASE_TIMING, tools/rollout_phases.py)
 #ifdef ORLG_PHASE_TIMING
@@ -68,7 +68,7 @@ struct RolloutArgs {
     float *obs;                  // [T][n][obs_dim]   (NULL: skip)
     float *reward;               // [T][n]            (NULL: skip)
     unsigned char *done;         // [T][n]            (NULL: skip)
-    int *actions;                // [T][n]            (NULL: skip)
+    int *actions;                // [T][n]            (NULL: skip; RO_POLICY_REPLAY: the INPUT action sequence)
     // launch-private event storage, lane-interleaved per warp of 32 envs: element (slot s, lane) of warp w at (w * cap + s) * 32 + lane
     double *rt_t;                // [warps][heap_cap][32]  table: release times
     unsigned long long *rt_p;    // [warps][heap_cap][32]  table: packed services
@@ -202,7 +202,9 @@ __device__ __forceinline__ unsigned feat_pack(int st, int len, int total, int ru
     return (unsigned)(st < 0 ? 127 : st) | ((unsigned)(len & 127) << 7) | ((unsigned)total << 14) | ((unsigned)runs << 21) | ((unsigned)n << 27);
 }
 
-template <int ET, int POLICY>
+// TRACE: the requests come from the recorded trace (orlg_set_trace) instead of the Philox generator; with
+// RO_POLICY_REPLAY (actions given up front) this replays a reference run through the persistent kernel.
+template <int ET, int POLICY, bool TRACE = false>
 __global__ void __launch_bounds__(RO_MAX_THREADS, 1)
 deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     constexpr int KM = 5;
@@ -350,21 +352,34 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
         int ns[KM];
         if (live) {
             // ---- the next request (rmsa_env.py:545-561): a pure function of (seed, global env id, request index)
-            uint32_t rc_[4] = {ridx, 0u, (uint32_t)gid, 0u}, rd_[4] = {ridx, 0u, (uint32_t)gid, 1u};
-            philox4x32_10(rc_, k0, k1);
-            philox4x32_10(rd_, k0, k1);
-            const double e_iat = __dmul_rn(neg_log_u32(rc_[0]), p.mean_iat);
-            const double e_hold = __dmul_rn(neg_log_u32(rc_[1]), p.mean_holding);
-            const int nn = p.N;
-            const int p_src = pick_thr_bsearch(s_node_thr, nn, p.node_top_step, rc_[2]);
-            const unsigned lo = p_src ? s_node_thr[p_src - 1] : 0u;
-            const unsigned long long hi = (p_src == nn - 1) ? 4294967296ULL : (unsigned long long)s_node_thr[p_src];
-            const unsigned long long mass = hi - lo;
-            unsigned long long tt = ((unsigned long long)rc_[3] * (4294967296ULL - mass)) >> 32;
-            if (tt >= lo) tt += mass;
-            int p_dst = pick_thr_bsearch(s_node_thr, nn, p.node_top_step, (unsigned)tt);
-            if (p_dst == p_src) p_dst = (p_src + 1) % nn;
-            const int p_br = p.br_lo + (int)__umulhi(rd_[0], (unsigned)p.br_span);
+            double e_iat = 0.0, e_hold = 0.0, t_arrival = now;
+            int p_src = 0, p_dst = 1, p_br = p.br_lo;
+            if (TRACE) {
+                if ((long long)ridx < p.trace_len) {
+                    const orlg_request r = p.trace[(size_t)e * p.trace_len + ridx];
+                    t_arrival = r.arrival; e_hold = r.holding; p_src = r.src; p_dst = r.dst;
+                    p_br = min(max(r.bit_rate, 0), 127);
+                    if (r.bit_rate > 127) err |= ORLG_ERR_TRACE_RANGE;        // beyond the slot-count table of this kernel
+                } else {
+                    err |= ORLG_ERR_TRACE_EXHAUSTED;
+                }
+            } else {
+                uint32_t rc_[4] = {ridx, 0u, (uint32_t)gid, 0u}, rd_[4] = {ridx, 0u, (uint32_t)gid, 1u};
+                philox4x32_10(rc_, k0, k1);
+                philox4x32_10(rd_, k0, k1);
+                e_iat = __dmul_rn(neg_log_u32(rc_[0]), p.mean_iat);
+                e_hold = __dmul_rn(neg_log_u32(rc_[1]), p.mean_holding);
+                const int nn = p.N;
+                p_src = pick_thr_bsearch(s_node_thr, nn, p.node_top_step, rc_[2]);
+                const unsigned lo = p_src ? s_node_thr[p_src - 1] : 0u;
+                const unsigned long long hi = (p_src == nn - 1) ? 4294967296ULL : (unsigned long long)s_node_thr[p_src];
+                const unsigned long long mass = hi - lo;
+                unsigned long long tt = ((unsigned long long)rc_[3] * (4294967296ULL - mass)) >> 32;
+                if (tt >= lo) tt += mass;
+                p_dst = pick_thr_bsearch(s_node_thr, nn, p.node_top_step, (unsigned)tt);
+                if (p_dst == p_src) p_dst = (p_src + 1) % nn;
+                p_br = p.br_lo + (int)__umulhi(rd_[0], (unsigned)p.br_span);
+            }
             const int npair = p_src * p.N + p_dst;
             const int p_first = s_pair_first[npair];
             npaths = min((int)s_pair_count[npair], KM);
@@ -383,6 +398,8 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                 uint32_t ra_[4] = {ridx, 0u, (uint32_t)gid, 2u};
                 philox4x32_10(ra_, k0, k1);
                 act = (int)__umulhi(ra_[0], n_act);
+            } else if (POLICY == RO_POLICY_REPLAY) {             // a recorded action sequence
+                act = ra.actions[(size_t)t * p.n + env];
             } else if (POLICY == RO_POLICY_SP_FF) {              // deeprmsa_env.py:135-143
                 act = (!p.allow_rejection || (candw & 0xffu) != CAND_NONE) ? 0 : p.k;
             } else {                                             // deeprmsa_env.py:146-155
@@ -390,7 +407,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                 for (int q = npaths_cur - 1; q >= 0; q--)
                     if (((candw >> (8 * q)) & 0xffu) != CAND_NONE) act = q;
             }
-            if (ra.actions) ra.actions[(size_t)t * p.n + env] = act;
+            if (POLICY != RO_POLICY_REPLAY && ra.actions) ra.actions[(size_t)t * p.n + env] = act;
 
             // ---- Phase A (deeprmsa_env.py:48-58 -> rmsa_env.py:163-209): the cached block start decides
             bool accepted = false;
@@ -435,7 +452,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
 
             RPH_MARK(1);             // action + phase A
             // ---- Phase B: _next_service (rmsa_env.py:545-597)
-            now = __dadd_rn(now, e_iat);
+            now = TRACE ? t_arrival : __dadd_rn(now, e_iat);
             hold = e_hold; src = p_src; dst = p_dst; br = p_br;
             ridx++;
             sid = ep_proc;

@@ -15,7 +15,7 @@ HEURISTICS = {"shortest_path_first_fit": 0, "sp_ff": 0, "sp": 0,
               "shortest_available_path_best_modulation_first_core_first_fit": 1,
               "least_loaded_path_first_fit": 2, "llp_ff": 2,
               "shortest_available_path_last_fit": 3, "sap_lf": 3}
-ERR_TRACE_EXHAUSTED, ERR_HEAP_OVERFLOW, ERR_NO_SUCH_PATH, ERR_LOCKSTEP, ERR_STATS_ORDER = 1, 2, 4, 8, 16
+ERR_TRACE_EXHAUSTED, ERR_HEAP_OVERFLOW, ERR_NO_SUCH_PATH, ERR_LOCKSTEP, ERR_STATS_ORDER, ERR_TRACE_RANGE = 1, 2, 4, 8, 16, 32
 MAX_BIT_RATE = 1023       # bit rates (Gb/s) are tabulated up to here (orlg_api.cu)
 
 

@@ -359,7 +359,12 @@ class OpticalVecEnv:
         ``policy``: "random" (:meth:`sample_actions`) or a heuristic name (:meth:`heuristic`).  Identical to the
         step-by-step loop; DeepRMSA-v0 with Philox traffic and float32 observations runs as one persistent kernel."""
         T, n, dev = int(steps), self.num_envs, self.device
-        pol = -1 if policy in ("random", None) else (nat.HEURISTICS[policy] if isinstance(policy, str) else int(policy))
+        if policy == "replay":          # the given `actions` [T, N, action_dim] are applied (with trace traffic: a recorded run)
+            assert actions is not None, "policy='replay' needs the action sequence"
+            actions = torch.as_tensor(actions, device=dev).to(torch.int32).reshape(T, n, self.action_dim).contiguous()
+            pol = -2
+        else:
+            pol = -1 if policy in ("random", None) else (nat.HEURISTICS[policy] if isinstance(policy, str) else int(policy))
         if obs is None and want_obs and self.obs_dim:
             obs = torch.empty((T, n, self.obs_dim), dtype=self.obs_dtype, device=dev)
         if reward is None:

@@ -180,3 +180,49 @@ def test_rollout_full_size_65536_envs_invariants_and_sampled_oracle():
         assert np.array_equal(cnt[i], o.counters()), ("counters", i)
         np.testing.assert_allclose(last_obs[i].cpu().numpy(), o.observation(), rtol=OBS_RTOL, atol=0)
     env.close()
+
+
+@pytest.mark.parametrize("name", helpers.golden_names())
+def test_rollout_replays_reference_trace(name):
+    """The requests AND actions recorded from the live reference, replayed through orlg_rollout in chunks: for the
+    DeepRMSA j = 1 goldens this is the persistent kernel (the one bench.py times) consuming reference traces
+    directly; every other golden goes through the same entry point on the per-step kernels."""
+    from optical_rl_gym_b200 import OpticalVecEnv
+
+    g = helpers.load_golden(name)
+    meta = g["meta"]
+    n, T, kind = meta["n_envs"], meta["T"], meta["kind"]
+    env = OpticalVecEnv(kind, n, helpers.golden_tables(), traffic="trace", **meta["env_args"])
+    env.set_trace(g["req_arrival"], g["req_holding"], g["req_src"], g["req_dst"], g["req_bit_rate"])
+    env.reset(full=True)
+    obs0 = env.reset(full=False)           # evaluate_heuristic's reset() before the first episode (utils.py:113)
+    if kind == "DeepRMSA-v0":
+        np.testing.assert_allclose(obs0.cpu().numpy(), g["obs"][:, 0], rtol=OBS_RTOL, atol=0)
+    actions = torch.as_tensor(np.ascontiguousarray(np.swapaxes(g["actions"], 0, 1)), device="cuda")     # [T, n, A]
+    t0 = 0
+    for chunk in (1, 13, 200, T):
+        t1 = min(T, t0 + chunk)
+        if t1 <= t0:
+            break
+        obs, rew, done, _ = env.rollout(t1 - t0, "replay", actions=actions[t0:t1])
+        acc = (rew > 0).cpu().numpy() if kind == "DeepRMSA-v0" else (rew > 0.5).cpu().numpy()
+        assert np.array_equal(acc, np.swapaxes(g["accepted"], 0, 1)[t0:t1].astype(bool)), ("accepted", t0)
+        assert np.array_equal(rew.cpu().numpy().astype(np.float64), np.swapaxes(g["reward"], 0, 1)[t0:t1]), ("reward", t0)
+        assert np.array_equal(done.cpu().numpy(), np.swapaxes(g["done"], 0, 1)[t0:t1]), ("done", t0)
+        if kind == "DeepRMSA-v0":
+            np.testing.assert_allclose(obs.cpu().numpy(), np.swapaxes(g["obs"], 0, 1)[t0 + 1:t1 + 1], rtol=OBS_RTOL, atol=0)
+        t0 = t1
+    m, alloc, now, nheap = env.export_state(allocation=True)
+    avail = env.available_slots().cpu().numpy().reshape(g["final_avail"].shape)
+    assert np.array_equal(avail, g["final_avail"])
+    assert np.array_equal(alloc.cpu().numpy(), g["final_alloc"])
+    assert np.array_equal(now.cpu().numpy(), g["final_now"]) and np.array_equal(nheap.cpu().numpy(), g["final_nheap"])
+    want = g["counters"][:, T - 1].copy()
+    dn = g["done"][:, T - 1].astype(bool)
+    if kind == "RWA-v0":
+        want[dn, 2] = 0; want[dn, 3] = 0
+    else:
+        want[dn, 2] = 1; want[dn, 3] = 0; want[dn, 6] = g["req_bit_rate"][dn, T]; want[dn, 7] = 0
+    assert np.array_equal(env.counters().cpu().numpy(), want)
+    assert int(env.error_flags().abs().sum()) == 0
+    env.close()
