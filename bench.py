@@ -122,6 +122,20 @@ def cpu_baseline(threads, seconds=12.0):
                       "%d pthreads" % (n_envs, done_steps, FILL_STEPS, threads)}
 
 
+def python_reference_baseline(seconds=8.0):
+    """The UNMODIFIED Python reference (baseline/_ref), one env per process over all host cores, pipe-driven like
+    SB3's SubprocVecEnv (baseline/subproc_reference.py).  None when the install did not travel to this box."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import subproc_reference as sr
+
+        if not sr.available():
+            return None
+        return sr.measure(ENV_ID, dict(ENV_ARGS), workers=os.cpu_count() or 1, seconds=seconds)
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port: the reference is
     pure Python and cannot travel to the GPU box), all host threads, same config / metric / unit."""
@@ -155,6 +169,7 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8/f64", "data": "synthetic",
         "config": {"workload": WORKLOAD % ENVS_PER_GPU, "sample": sample},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline_python": python_reference_baseline(),
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -184,9 +199,10 @@ def main():
 
     # The CPU baseline runs FIRST, on rank 0, while the other ranks are still blocked in the rendezvous of
     # init_process_group (a socket wait, no spinning): it has the host cores to itself.
-    cpu = None
+    cpu = cpu_py = None
     if rank == 0 and not args.no_cpu_baseline:
         cpu = cpu_baseline(os.cpu_count() or 1)
+        cpu_py = python_reference_baseline()
 
     import torch
     import torch.distributed as dist
@@ -334,7 +350,7 @@ def main():
                                                                             env.state_bytes / 1e6),
                        "parallelism": "env-sharded x%d, no data-path collective" % world},
             "timing": {"reps": args.reps, "rep_ms": rep_ms, "stat": "median of the repetitions (each: max over ranks)"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e_result, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_python": cpu_py, "e2e": e2e_result, "gpu_launches": launches,
             "clocks": sampler.summary(), "step_path_ms_per_step": step_path_ms,
             "accept_rate": 1.0 - stats["service_blocking_rate"], "envs_with_errors": stats["envs_with_errors"],
         }
