@@ -115,3 +115,24 @@ def test_number_of_slots_integer_form_matches_reference_float_expression():
     for se in range(1, 7):
         for b in range(1, 1024):
             assert math.ceil(b / (se * 12.5)) + 1 == (2 * b + 25 * se - 1) // (25 * se) + 1
+
+
+def test_integration_md_stub_matches_the_header_structs():
+    """The ctypes stub printed in INTEGRATION.md section 2 is what a maintainer would copy: its Config / Tables
+    must have exactly the layout of include/orlg.h (a short Tables hands orlg_create a garbage link_order pointer)."""
+    import ctypes as C
+    import re
+
+    from optical_rl_gym_b200 import _native
+
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"```python\nimport ctypes as C, numpy as np, torch\n(.*?)```", text, re.S).group(1)
+    classes = block[block.index("class Config"):block.index("class BatchedDeepRMSA")]
+    ns = {"C": C}
+    exec(classes, ns)
+    for name in ("Config", "Tables"):
+        doc, real = ns[name], getattr(_native, name)
+        assert [f[0] for f in doc._fields_] == [f[0] for f in real._fields_], name
+        assert C.sizeof(doc) == C.sizeof(real), name
+        for f in real._fields_:
+            assert getattr(doc, f[0]).offset == getattr(real, f[0]).offset, (name, f[0])
