@@ -365,7 +365,13 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
         cap = (int)std::ceil(want < hard ? want : hard);
     }
     cap = ((cap + EV_GROUP - 1) / EV_GROUP) * EV_GROUP;
-    if (cap > 64 * EV_GROUP) cap = 64 * EV_GROUP;        // the directory bitmap is 64 bits wide
+    // up to 4096 live services per env (RWA's physical bound on NSFNET is E * W = 1760).  A derived capacity is capped
+    // there (overflow is flagged per env, ORLG_ERR_HEAP_OVERFLOW); an explicit request beyond it is refused.
+    if (cfg->heap_capacity > 256 * EV_GROUP) {
+        delete env;
+        return fail(ORLG_E_UNSUPPORTED, "heap_capacity above 4096 live services per environment");
+    }
+    if (cap > 256 * EV_GROUP) cap = 256 * EV_GROUP;
     p.ev_groups = ((cap / EV_GROUP + 15) / 16) * 16;
     p.heap_cap = cap;
 

@@ -265,79 +265,88 @@ __device__ __forceinline__ void events_release(const Events &ev, unsigned &n, do
     SUBPHASE_BEGIN();
     if (n == 0 || tmin > now) return;
     const unsigned tail0 = (n - 1) / EV_GROUP;     // tail group on entry
-    // ---- directory: which full groups may hold a due service?  (entries >= tail0 are +INF)
-    unsigned long long due_groups = 0;
-    float fbound = ORLG_INF_F;                      // lower bound over the full groups that stay
     const float now_up = __double2float_ru(now);    // f <= now_up whenever (double)f <= now
-    for (unsigned c = 0; c < tail0; c += 16) {
-        float4 d[4];
+    float fb = ORLG_INF_F;                          // lower bound over everything that stays
+    unsigned tail_pub = tail0;                      // the group that `tail_min` currently describes
+    // The directory is walked in blocks of 64 groups, HIGHEST block first and highest group first inside a block, so that
+    // the tail entry that fills a hole is never itself due (any number of groups: the capacity is not tied to a 64-bit mask).
+    for (int blk = (int)(tail0 / 64); blk >= 0; blk--) {
+        const unsigned g0 = (unsigned)blk * 64;
+        // ---- directory: which full groups of this block may hold a due service?  (entries >= tail0 are +INF)
+        unsigned long long due_groups = 0;
+        const unsigned gend = min(g0 + 64u, tail0);
+        for (unsigned c = g0; c < gend; c += 16) {
+            float4 d[4];
 #pragma unroll
-        for (int q = 0; q < 4; q++) d[q] = reinterpret_cast<const float4 *>(ev.gmin + c)[q];
-        unsigned m16 = 0;
+            for (int q = 0; q < 4; q++) d[q] = reinterpret_cast<const float4 *>(ev.gmin + c)[q];
+            unsigned m16 = 0;
 #pragma unroll
-        for (int q = 0; q < 16; q++) {
-            const float4 v = d[q >> 2];
-            const float f = (q & 3) == 0 ? v.x : ((q & 3) == 1 ? v.y : ((q & 3) == 2 ? v.z : v.w));
-            const bool due = f <= now_up;
-            m16 |= due ? (1u << q) : 0u;
-            fbound = fminf(fbound, due ? ORLG_INF_F : f);
-        }
-        due_groups |= (unsigned long long)m16 << c;
-    }
-    float fb = fbound;
-    if (tail_min <= now) due_groups |= 1ULL << tail0; else fb = fminf(fb, lower_f32(tail_min));
-    SUBPHASE_MARK(13);                         // directory
-    {   // start every fetch the scans below will need (times + payloads of the due groups, the tail entry)
-        unsigned long long m = due_groups;
-        while (m) {
-            const unsigned g = 63 - __clzll(m);
-            m &= ~(1ULL << g);
-            prefetch_l2(ev.t + g * EV_GROUP);
-            prefetch_l2(ev.p + g * EV_GROUP);
-        }
-        prefetch_l2(ev.t + (n - 1));
-        prefetch_l2(ev.p + (n - 1));
-    }
-    unsigned tail_pub = tail0;                 // the group that `tail_min` currently describes
-    while (due_groups) {
-        const unsigned g = 63 - __clzll(due_groups);
-        due_groups &= ~(1ULL << g);
-        const unsigned s0 = g * EV_GROUP;
-        if (s0 >= n) continue;                 // the group vanished while the tail shrank
-        unsigned duebits = 0;
-        float gm = ORLG_INF_F;                 // lower bound of what stays in this group
-#pragma unroll
-        for (int q = 0; q < EV_GROUP / 2; q++) {
-            const double2 v = reinterpret_cast<const double2 *>(ev.t + s0)[q];
-            const bool d0 = v.x <= now, d1 = v.y <= now;        // slots >= n hold +INF: never due
-            duebits |= (d0 ? (1u << (2 * q)) : 0u) | (d1 ? (2u << (2 * q)) : 0u);
-            gm = fminf(gm, d0 ? ORLG_INF_F : lower_f32(v.x));
-            gm = fminf(gm, d1 ? ORLG_INF_F : lower_f32(v.y));
-        }
-        SUBPHASE_MARK(14);                     // group fetch + classify
-        while (duebits) {                      // highest slot first
-            const unsigned q = 31 - __clz(duebits);
-            duebits &= ~(1u << q);
-            const unsigned s = s0 + q;
-            const unsigned last = n - 1;
-            const unsigned long long pl = ev.p[s];
-            const double pt = Apply::wants_time ? ev.t[s] : 0.0;
-            if (s != last) {                   // fill the hole with the tail entry (never due, see above)
-                const double lt = ev.t[last];
-                const unsigned long long lp = ev.p[last];
-                ev.t[s] = lt;
-                ev.p[s] = lp;
-                gm = fminf(gm, lower_f32(lt));
+            for (int q = 0; q < 16; q++) {
+                const float4 v = d[q >> 2];
+                const float f = (q & 3) == 0 ? v.x : ((q & 3) == 1 ? v.y : ((q & 3) == 2 ? v.z : v.w));
+                const bool due = f <= now_up;
+                m16 |= due ? (1u << q) : 0u;
+                fb = fminf(fb, due ? ORLG_INF_F : f);
             }
-            ev.t[last] = ORLG_INF;             // keep "t[s] = +INF for s >= n"
-            n--;
-            apply(pl, pt);
+            due_groups |= (unsigned long long)m16 << (c - g0);
         }
-        SUBPHASE_MARK(15);                     // payload fetch, hole fill, apply
-        if (s0 < n) {                          // publish the bound of what is left of this group
-            if (g == (n - 1) / EV_GROUP) { tail_min = (double)gm; tail_pub = g; }
-            else ev.gmin[g] = gm;
-            fb = fminf(fb, gm);
+        if (tail0 >= g0 && tail0 < g0 + 64u) {      // the open tail group lives in this block
+            if (tail_min <= now) due_groups |= 1ULL << (tail0 - g0); else fb = fminf(fb, lower_f32(tail_min));
+        }
+        SUBPHASE_MARK(13);                         // directory
+        {   // start every fetch the scans below will need (times + payloads of the due groups, the tail entry)
+            unsigned long long m = due_groups;
+            while (m) {
+                const unsigned g = g0 + 63 - __clzll(m);
+                m &= ~(1ULL << (g - g0));
+                prefetch_l2(ev.t + g * EV_GROUP);
+                prefetch_l2(ev.p + g * EV_GROUP);
+            }
+            if (due_groups && n > 0) {
+                prefetch_l2(ev.t + (n - 1));
+                prefetch_l2(ev.p + (n - 1));
+            }
+        }
+        while (due_groups) {
+            const unsigned g = g0 + 63 - __clzll(due_groups);
+            due_groups &= ~(1ULL << (g - g0));
+            const unsigned s0 = g * EV_GROUP;
+            if (s0 >= n) continue;                 // the group vanished while the tail shrank
+            unsigned duebits = 0;
+            float gm = ORLG_INF_F;                 // lower bound of what stays in this group
+#pragma unroll
+            for (int q = 0; q < EV_GROUP / 2; q++) {
+                const double2 v = reinterpret_cast<const double2 *>(ev.t + s0)[q];
+                const bool d0 = v.x <= now, d1 = v.y <= now;        // slots >= n hold +INF: never due
+                duebits |= (d0 ? (1u << (2 * q)) : 0u) | (d1 ? (2u << (2 * q)) : 0u);
+                gm = fminf(gm, d0 ? ORLG_INF_F : lower_f32(v.x));
+                gm = fminf(gm, d1 ? ORLG_INF_F : lower_f32(v.y));
+            }
+            SUBPHASE_MARK(14);                     // group fetch + classify
+            while (duebits) {                      // highest slot first
+                const unsigned q = 31 - __clz(duebits);
+                duebits &= ~(1u << q);
+                const unsigned s = s0 + q;
+                const unsigned last = n - 1;
+                const unsigned long long pl = ev.p[s];
+                const double pt = Apply::wants_time ? ev.t[s] : 0.0;
+                if (s != last) {                   // fill the hole with the tail entry (never due, see above)
+                    const double lt = ev.t[last];
+                    const unsigned long long lp = ev.p[last];
+                    ev.t[s] = lt;
+                    ev.p[s] = lp;
+                    gm = fminf(gm, lower_f32(lt));
+                }
+                ev.t[last] = ORLG_INF;             // keep "t[s] = +INF for s >= n"
+                n--;
+                apply(pl, pt);
+            }
+            SUBPHASE_MARK(15);                     // payload fetch, hole fill, apply
+            if (s0 < n) {                          // publish the bound of what is left of this group
+                if (g == (n - 1) / EV_GROUP) { tail_min = (double)gm; tail_pub = g; }
+                else ev.gmin[g] = gm;
+                fb = fminf(fb, gm);
+            }
         }
     }
     if (n == 0) {
