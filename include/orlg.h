@@ -154,6 +154,23 @@ enum { ORLG_POLICY_RANDOM = -1, ORLG_POLICY_REPLAY = -2 };   /* REPLAY: actions_
 int orlg_rollout(orlg_env *env, int steps, int policy, void *obs_dev, float *reward_dev, uint8_t *done_dev,
                  int32_t *actions_dev, orlg_stream stream);
 
+/* The same rollout with ONE 32-byte record per env-step instead of the float observation: uint32 [steps, num_envs, 8]
+ *   w0..w4  per candidate path: first-block start (7 bits, 127 = none) | its length (7) | free slots (7) | free runs (6) | slots needed (5)
+ *   w5      bit rate (8) | source << 8 | destination << 16 | candidate paths << 24 | accepted << 28 | done << 29  (request = the NEXT one)
+ *   w6      the action taken;   w7 reserved
+ * i.e. the integer pre-image of deeprmsa_env.py:60-121 (orlg_observation_int) plus reward / done: 6.75x fewer bytes than the
+ * float32 row when the result has to cross PCIe.  DeepRMSA-v0 with k = 5, j = 1 (the persistent-kernel configuration) only. */
+int orlg_rollout_packed(orlg_env *env, int steps, int policy, uint32_t *packed_dev, int32_t *actions_dev, orlg_stream stream);
+/* HOST function: expands `rows` packed records into what env.step returned for them -- float32 observation rows
+ * [rows, 1 + 2 * num_nodes + 25] (bit-identical to the rows orlg_rollout writes), reward f32, done u8, action i32 (any output
+ * may be NULL) -- using `threads` host threads (<= 0: all cores). */
+int orlg_expand_packed(const uint32_t *packed_host, int64_t rows, int num_nodes, int num_slots, float *obs_host, float *reward_host,
+                       uint8_t *done_host, int32_t *action_host, int threads);
+/* orlg_rollout with HOST result buffers (pageable or pinned): the steps run in chunks on the device while the previous chunk's
+ * records cross PCIe and are expanded by the host threads.  obs_host f32 [steps, num_envs, obs_dim] etc.; any may be NULL. */
+int orlg_rollout_host(orlg_env *env, int steps, int policy, float *obs_host, float *reward_host, uint8_t *done_host,
+                      int32_t *actions_host, int chunk_steps, int threads, orlg_stream stream);
+
 /* Float statistics of `info` (rmsa_env.py:229-264, 439-543, 699-744; RMSA-v0 / DeepRMSA-v0, <= 32 links,
  * <= 128 slots): after this call every orlg_step also writes, per env, float64
  *   stats_dev[env][0..3] = network_compactness, network_compactness_difference,

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "orlg_deeprmsa_fast.cuh"
@@ -48,6 +49,11 @@ struct orlg_env {
     double *ro_st_f64 = nullptr;               // [2 + RO_SIDE][n] table minimum, horizon, side-buffer times
     unsigned long long *ro_st_u64 = nullptr;   // [RO_SIDE][n] side-buffer payloads
     bool ro_valid = false;                     // the events live in the rollout-private storage (canonical tables are stale)
+    // orlg_rollout_host: double-buffered packed records on the device and in pinned host memory
+    uint4 *ro_pk_dev[2] = {nullptr, nullptr};
+    uint4 *ro_pk_host[2] = {nullptr, nullptr};
+    size_t ro_pk_rows = 0;                     // rows (env-steps) each buffer holds
+    cudaEvent_t ro_pk_ev[2] = {nullptr, nullptr};
     int *ro_actions = nullptr;    // [n, action_dim] scratch of the generic (kernel-per-step) rollout
 };
 
@@ -258,7 +264,8 @@ bool rollout_plan(const orlg_env *env, int *wpc_out, RolloutArgs *ra, size_t *sm
     if (wpc > RO_MAX_THREADS / 32) wpc = RO_MAX_THREADS / 32;
     if (wpc < 1) wpc = 1;
     if (const char *v = std::getenv("ORLG_RO_WARPS")) { int w = std::atoi(v); if (w >= 1 && w <= RO_MAX_THREADS / 32) wpc = w; }
-    const int tile = (32 * p.obs_dim * 4 + 127) / 128 * 128;
+    int tile = (32 * p.obs_dim * 4 + 127) / 128 * 128;
+    if (tile < RO_WCAP * (128 + 32)) tile = RO_WCAP * (128 + 32);      // a tile also holds the sort keys + indices of a window rebuild
     const int warp_bytes = p.E * 512 + RO_SIDE * 512;
     const size_t budget = 227 * 1024;
     for (; wpc >= 1; wpc--) {
@@ -580,6 +587,11 @@ int orlg_destroy(orlg_env *env) {
     if (!env) return ORLG_OK;
     DeviceGuard guard(env->device);
     for (void *ptr : env->allocs) cudaFree(ptr);
+    for (int i = 0; i < 2; i++) {
+        if (env->ro_pk_dev[i]) cudaFree(env->ro_pk_dev[i]);
+        if (env->ro_pk_host[i]) cudaFreeHost(env->ro_pk_host[i]);
+        if (env->ro_pk_ev[i]) cudaEventDestroy(env->ro_pk_ev[i]);
+    }
     delete env;
     return ORLG_OK;
 }
@@ -843,8 +855,8 @@ int orlg_path_only_first_fit(orlg_env *env, const int32_t *path_actions_dev, int
     return ORLG_OK;
 }
 
-int orlg_rollout(orlg_env *env, int steps, int policy, void *obs_dev, float *reward_dev, uint8_t *done_dev,
-                 int32_t *actions_dev, orlg_stream stream) {
+static int rollout_impl(orlg_env *env, int steps, int policy, void *obs_dev, float *reward_dev, uint8_t *done_dev,
+                        int32_t *actions_dev, uint32_t *packed_dev, orlg_stream stream) {
     if (!env) return fail(ORLG_E_INVALID, "null handle");
     DeviceGuard guard(env->device);
     if (steps < 0) return fail(ORLG_E_INVALID, "steps must be >= 0");
@@ -883,6 +895,7 @@ int orlg_rollout(orlg_env *env, int steps, int policy, void *obs_dev, float *rew
         ra.span = span_steps * p.mean_iat;
         ra.obs = reinterpret_cast<float *>(obs_dev);
         ra.reward = reward_dev; ra.done = done_dev; ra.actions = actions_dev;
+        ra.packed = reinterpret_cast<uint4 *>(packed_dev);
         rollout_state_args(env, &ra);
         ra.resume = env->ro_valid ? 1 : 0;
         cudaError_t e = p.E == 22 ? launch_rollout<22>(env, ra, policy, wpc, smem, s) : launch_rollout<0>(env, ra, policy, wpc, smem, s);
@@ -891,6 +904,7 @@ int orlg_rollout(orlg_env *env, int steps, int policy, void *obs_dev, float *rew
         env->ro_valid = true;
         return ORLG_OK;
     }
+    if (packed_dev) return fail(ORLG_E_UNSUPPORTED, "packed records exist for the persistent DeepRMSA rollout kernel only (k = 5, j = 1, float32)");
     // generic: the same T steps as separate policy + step launches
     {
         int rc = ensure_canonical(env, s);
@@ -911,6 +925,110 @@ int orlg_rollout(orlg_env *env, int steps, int policy, void *obs_dev, float *rew
                        reward_dev ? reward_dev + (size_t)t * p.n : nullptr, done_dev ? done_dev + (size_t)t * p.n : nullptr,
                        nullptr, nullptr, stream);
         if (rc) return rc;
+    }
+    return ORLG_OK;
+}
+
+
+int orlg_rollout(orlg_env *env, int steps, int policy, void *obs_dev, float *reward_dev, uint8_t *done_dev,
+                 int32_t *actions_dev, orlg_stream stream) {
+    return rollout_impl(env, steps, policy, obs_dev, reward_dev, done_dev, actions_dev, nullptr, stream);
+}
+
+int orlg_rollout_packed(orlg_env *env, int steps, int policy, uint32_t *packed_dev, int32_t *actions_dev, orlg_stream stream) {
+    if (!packed_dev) return fail(ORLG_E_INVALID, "null record buffer");
+    return rollout_impl(env, steps, policy, nullptr, nullptr, nullptr, actions_dev, packed_dev, stream);
+}
+
+// one packed record -> what env.step returned (same float expressions as the device tables built in orlg_create)
+static void expand_rows(const uint32_t *pk, int64_t r0, int64_t r1, int N, int S, float *obs, float *reward, uint8_t *done, int32_t *action) {
+    const int D = 1 + 2 * N + 25;
+    for (int64_t r = r0; r < r1; r++) {
+        const uint32_t *w = pk + r * 8;
+        const uint32_t q5 = w[5];
+        if (obs) {
+            float *o = obs + r * D;
+            const int br = (int)(q5 & 0xffu), src = (int)((q5 >> 8) & 0xffu), dst = (int)((q5 >> 16) & 0xffu), npaths = (int)((q5 >> 24) & 0xfu);
+            for (int i = 0; i < 1 + 2 * N; i++) o[i] = 0.0f;
+            o[0] = (float)br / 100.0f;
+            o[1 + (src < dst ? src : dst)] = 1.0f;
+            o[1 + N + (src < dst ? dst : src)] = 1.0f;
+            for (int q = 0; q < 5; q++) {
+                const uint32_t f = w[q];
+                const int st = (int)(f & 127u), len = (int)((f >> 7) & 127u), total = (int)((f >> 14) & 127u);
+                const int runs = (int)((f >> 21) & 63u), n = (int)(f >> 27);
+                float *v = o + 1 + 2 * N + 5 * q;
+                v[0] = st != 127 ? (float)(2 * st - S) / (float)S : -1.0f;
+                v[1] = st != 127 ? (float)(len - 8) * 0.125f : -1.0f;
+                v[2] = q < npaths ? (float)(2 * n - 11) / 7.0f : -1.0f;
+                v[3] = q < npaths ? (float)(2 * total - S) / (float)S : -1.0f;
+                v[4] = runs > 0 ? (float)(total - 4 * runs) * (1.0f / (float)(4 * runs)) : -1.0f;
+            }
+        }
+        if (reward) reward[r] = (q5 >> 28) & 1u ? 1.0f : -1.0f;
+        if (done) done[r] = (uint8_t)((q5 >> 29) & 1u);
+        if (action) action[r] = (int32_t)w[6];
+    }
+}
+
+int orlg_expand_packed(const uint32_t *packed_host, int64_t rows, int num_nodes, int num_slots, float *obs_host, float *reward_host,
+                       uint8_t *done_host, int32_t *action_host, int threads) {
+    if (!packed_host || rows < 0 || num_nodes < 2 || num_slots < 1) return fail(ORLG_E_INVALID, "bad arguments");
+    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if ((int64_t)nt > rows / 4096 + 1) nt = (int)(rows / 4096 + 1);
+    if (nt == 1) { expand_rows(packed_host, 0, rows, num_nodes, num_slots, obs_host, reward_host, done_host, action_host); return ORLG_OK; }
+    std::vector<std::thread> pool;
+    const int64_t per = (rows + nt - 1) / nt;
+    for (int i = 0; i < nt; i++) {
+        const int64_t r0 = i * per, r1 = r0 + per < rows ? r0 + per : rows;
+        if (r0 >= r1) break;
+        pool.emplace_back(expand_rows, packed_host, r0, r1, num_nodes, num_slots, obs_host, reward_host, done_host, action_host);
+    }
+    for (auto &t : pool) t.join();
+    return ORLG_OK;
+}
+
+int orlg_rollout_host(orlg_env *env, int steps, int policy, float *obs_host, float *reward_host, uint8_t *done_host,
+                      int32_t *actions_host, int chunk_steps, int threads, orlg_stream stream) {
+    if (!env) return fail(ORLG_E_INVALID, "null handle");
+    if (steps <= 0) return steps == 0 ? ORLG_OK : fail(ORLG_E_INVALID, "steps must be >= 0");
+    if (policy == ORLG_POLICY_REPLAY) return fail(ORLG_E_UNSUPPORTED, "orlg_rollout_host takes device-side policies (random / heuristics)");
+    DeviceGuard guard(env->device);
+    Params &p = env->p;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int chunk = chunk_steps > 0 ? chunk_steps : 8;
+    const size_t rows = (size_t)chunk * p.n;
+    if (env->ro_pk_rows < rows) {                       // (re)allocate the double buffers
+        for (int i = 0; i < 2; i++) {
+            if (env->ro_pk_dev[i]) cudaFree(env->ro_pk_dev[i]);
+            if (env->ro_pk_host[i]) cudaFreeHost(env->ro_pk_host[i]);
+            env->ro_pk_dev[i] = nullptr; env->ro_pk_host[i] = nullptr;
+            if (cudaMalloc(&env->ro_pk_dev[i], rows * 32) != cudaSuccess) return fail(ORLG_E_NOMEM, "cudaMalloc (packed records) failed");
+            if (cudaHostAlloc(&env->ro_pk_host[i], rows * 32, cudaHostAllocDefault) != cudaSuccess) return fail(ORLG_E_NOMEM, "cudaHostAlloc (packed records) failed");
+            if (!env->ro_pk_ev[i]) CUDA_OK(cudaEventCreateWithFlags(&env->ro_pk_ev[i], cudaEventDisableTiming));
+        }
+        env->ro_pk_rows = rows;
+    }
+    const int nchunks = (steps + chunk - 1) / chunk;
+    const size_t D = (size_t)p.obs_dim;
+    for (int c = 0; c <= nchunks; c++) {
+        if (c < nchunks) {                              // chunk c: device rollout, then its records start crossing PCIe
+            const int t0 = c * chunk, tc = steps - t0 < chunk ? steps - t0 : chunk;
+            int rc = rollout_impl(env, tc, policy, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<uint32_t *>(env->ro_pk_dev[c & 1]), stream);
+            if (rc) return rc;
+            CUDA_OK(cudaMemcpyAsync(env->ro_pk_host[c & 1], env->ro_pk_dev[c & 1], (size_t)tc * p.n * 32, cudaMemcpyDeviceToHost, s));
+            CUDA_OK(cudaEventRecord(env->ro_pk_ev[c & 1], s));
+        }
+        if (c >= 1) {                                   // chunk c - 1: expand on the host threads while the device runs chunk c
+            const int t0 = (c - 1) * chunk, tc = steps - t0 < chunk ? steps - t0 : chunk;
+            CUDA_OK(cudaEventSynchronize(env->ro_pk_ev[(c - 1) & 1]));
+            const size_t off = (size_t)t0 * p.n;
+            int rc = orlg_expand_packed(reinterpret_cast<const uint32_t *>(env->ro_pk_host[(c - 1) & 1]), (int64_t)tc * p.n, p.N, p.S,
+                                        obs_host ? obs_host + off * D : nullptr, reward_host ? reward_host + off : nullptr,
+                                        done_host ? done_host + off : nullptr, actions_host ? actions_host + off : nullptr, threads);
+            if (rc) return rc;
+        }
     }
     return ORLG_OK;
 }

@@ -380,6 +380,51 @@ class OpticalVecEnv:
             nat.check(self._lib.orlg_rollout(self._h, T, pol, _ptr(obs), _ptr(reward), _ptr(done), _ptr(actions), self._stream()))
         return obs, reward, done, actions
 
+    def rollout_packed(self, steps: int, policy="random", out=None):
+        """Like :meth:`rollout`, but ONE 32-byte record per env-step (int32 ``[T, N, 8]`` on the device): the integer
+        pre-image of the observation + request + action / accepted / done (``orlg_rollout_packed``, include/orlg.h).
+        :meth:`expand_packed` turns records (on the host) into float32 rows identical to :meth:`rollout`'s."""
+        T, n = int(steps), self.num_envs
+        pol = -1 if policy in ("random", None) else (nat.HEURISTICS[policy] if isinstance(policy, str) else int(policy))
+        if out is None:
+            out = torch.empty((T, n, 8), dtype=torch.int32, device=self.device)
+        assert tuple(out.shape) == (T, n, 8) and out.is_contiguous() and out.dtype == torch.int32
+        with torch.cuda.device(self._dev_index):
+            nat.check(self._lib.orlg_rollout_packed(self._h, T, pol, _ptr(out), None, self._stream()))
+        return out
+
+    def expand_packed(self, packed, threads: int = 0):
+        """Host-side decoder of packed records (numpy / CPU tensor ``[..., 8]`` int32) -> ``(obs f32 [..., obs_dim], reward f32,
+        done u8, action i32)`` numpy arrays (``orlg_expand_packed``: all host cores by default)."""
+        pk = np.ascontiguousarray(packed.cpu().numpy() if torch.is_tensor(packed) else packed).view(np.uint32)
+        lead = pk.shape[:-1]
+        rows = int(np.prod(lead))
+        obs = np.empty(lead + (self.obs_dim,), np.float32)
+        rew, done, act = np.empty(lead, np.float32), np.empty(lead, np.uint8), np.empty(lead, np.int32)
+        nat.check(self._lib.orlg_expand_packed(pk.ctypes.data_as(C.c_void_p), rows, self.tables.num_nodes, self.num_spectrum_resources,
+                                               obs.ctypes.data_as(C.c_void_p), rew.ctypes.data_as(C.c_void_p),
+                                               done.ctypes.data_as(C.c_void_p), act.ctypes.data_as(C.c_void_p), int(threads)))
+        return obs, rew, done, act
+
+    def rollout_host(self, steps: int, policy="random", *, obs=None, reward=None, done=None, actions=None, chunk: int = 8,
+                     threads: int = 0):
+        """:meth:`rollout` with the results delivered in HOST memory (numpy arrays, pageable is fine): the device runs chunk
+        c + 1 while chunk c's packed records cross PCIe and the host threads expand them (``orlg_rollout_host``)."""
+        T, n = int(steps), self.num_envs
+        pol = -1 if policy in ("random", None) else (nat.HEURISTICS[policy] if isinstance(policy, str) else int(policy))
+        obs = np.empty((T, n, self.obs_dim), np.float32) if obs is None else obs
+        reward = np.empty((T, n), np.float32) if reward is None else reward
+        done = np.empty((T, n), np.uint8) if done is None else done
+        actions = np.empty((T, n), np.int32) if actions is None else actions
+        for a, shape, dt in ((obs, (T, n, self.obs_dim), np.float32), (reward, (T, n), np.float32), (done, (T, n), np.uint8),
+                             (actions, (T, n), np.int32)):
+            assert a.shape == shape and a.dtype == dt and a.flags["C_CONTIGUOUS"], (a.shape, shape, a.dtype)
+        with torch.cuda.device(self._dev_index):
+            nat.check(self._lib.orlg_rollout_host(self._h, T, pol, obs.ctypes.data_as(C.c_void_p), reward.ctypes.data_as(C.c_void_p),
+                                                  done.ctypes.data_as(C.c_void_p), actions.ctypes.data_as(C.c_void_p),
+                                                  int(chunk), int(threads), self._stream()))
+        return obs, reward, done, actions
+
     def observation(self):
         if not self.obs_dim:
             return None

@@ -226,3 +226,27 @@ def test_rollout_replays_reference_trace(name):
     assert np.array_equal(env.counters().cpu().numpy(), want)
     assert int(env.error_flags().abs().sum()) == 0
     env.close()
+
+
+def test_packed_records_and_host_rollout_equal_the_device_rollout():
+    """orlg_rollout_packed + orlg_expand_packed (host decoder) and orlg_rollout_host (chunked, pipelined) against orlg_rollout:
+    bit-identical float32 rows, rewards, dones, actions; the three handles end in the same state."""
+    from optical_rl_gym_b200 import OpticalVecEnv
+
+    tables = helpers.golden_tables()
+    kw = dict(traffic="philox", seed=12, episode_length=33)
+    a = OpticalVecEnv("DeepRMSA-v0", 1000, tables, **kw)
+    b = OpticalVecEnv("DeepRMSA-v0", 1000, tables, **kw)
+    c = OpticalVecEnv("DeepRMSA-v0", 1000, tables, **kw)
+    for T, pol in ((1, "random"), (37, "random"), (90, "sap")):
+        o, r, d, act = a.rollout(T, pol)
+        pk = b.rollout_packed(T, pol)
+        o2, r2, d2, a2 = b.expand_packed(pk)
+        assert np.array_equal(o.cpu().numpy(), o2), ("obs", T)
+        assert np.array_equal(r.cpu().numpy(), r2) and np.array_equal(d.cpu().numpy(), d2), T
+        assert np.array_equal(act.cpu().numpy()[..., 0], a2), T
+        o3, r3, d3, a3 = c.rollout_host(T, pol, chunk=8, threads=3)
+        assert np.array_equal(o2, o3) and np.array_equal(r2, r3) and np.array_equal(d2, d3) and np.array_equal(a2, a3), T
+    _final_state_equal(a, b)
+    _final_state_equal(a, c)
+    a.close(); b.close(); c.close()
