@@ -35,8 +35,7 @@ namespace orlg {
 
 constexpr int RO_WCAP = 48;            // window entries per env (48 float sort keys + 48 index bytes x 32 lanes fit one pool tile)
 constexpr int RO_SIDE = 3;             // side-buffer entries per env (shared memory)
-constexpr int RO_MAX_THREADS = 448;    // 14 warps x 148 SMs >= 65536 envs in one wave
-constexpr int RO_MAX_REGS = 144;       // 448 threads x 144 registers = 63 K of the SM's 64 K
+constexpr int RO_MAX_THREADS = 448;    // 14 warps x 148 SMs >= 65536 envs in one wave (128 registers: the next allocation step, 144, fits 13 warps only)
 enum { RO_POLICY_RANDOM = 0, RO_POLICY_SP_FF = 1, RO_POLICY_SAP_FF = 2, RO_POLICY_REPLAY = 3 };
 
 // optional cycle accounting per warp (instrumented builds: -DORLG_PHASE_TIMING, tools/rollout_phases.py)
@@ -255,7 +254,7 @@ __device__ __forceinline__ unsigned feat_pack(int st, int len, int total, int ru
 // TRACE: the requests come from the recorded trace (orlg_set_trace) instead of the Philox generator; with
 // RO_POLICY_REPLAY (actions given up front) this replays a reference run through the persistent kernel.
 template <int ET, int POLICY, bool TRACE = false>
-__global__ void __maxnreg__(RO_MAX_REGS)
+__global__ void __launch_bounds__(RO_MAX_THREADS, 1)
 deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     constexpr int KM = 5;
     extern __shared__ __align__(16) unsigned char smem[];
