@@ -264,8 +264,7 @@ bool rollout_plan(const orlg_env *env, int *wpc_out, RolloutArgs *ra, size_t *sm
     if (wpc > RO_MAX_THREADS / 32) wpc = RO_MAX_THREADS / 32;
     if (wpc < 1) wpc = 1;
     if (const char *v = std::getenv("ORLG_RO_WARPS")) { int w = std::atoi(v); if (w >= 1 && w <= RO_MAX_THREADS / 32) wpc = w; }
-    int tile = (32 * p.obs_dim * 4 + 127) / 128 * 128;
-    if (tile < RO_WCAP * (128 + 32)) tile = RO_WCAP * (128 + 32);      // a tile also holds the sort keys + indices of a window rebuild
+    const int tile = (32 * p.obs_dim * 4 + 127) / 128 * 128;
     const int warp_bytes = p.E * 512 + RO_SIDE * 512;
     const size_t budget = 227 * 1024;
     for (; wpc >= 1; wpc--) {

@@ -33,9 +33,9 @@
 
 namespace orlg {
 
-constexpr int RO_WCAP = 48;            // window entries per env (48 float sort keys + 48 index bytes x 32 lanes fit one pool tile)
+constexpr int RO_WCAP = 64;            // window entries per env
 constexpr int RO_SIDE = 3;             // side-buffer entries per env (shared memory)
-constexpr int RO_MAX_THREADS = 448;    // 14 warps x 148 SMs >= 65536 envs in one wave (128 registers: the next allocation step, 144, fits 13 warps only)
+constexpr int RO_MAX_THREADS = 448;    // 14 warps x 148 SMs >= 65536 envs in one wave
 enum { RO_POLICY_RANDOM = 0, RO_POLICY_SP_FF = 1, RO_POLICY_SAP_FF = 2, RO_POLICY_REPLAY = 3 };
 
 // optional cycle accounting per warp (instrumented builds: -DORLG_PHASE_TIMING, tools/rollout_phases.py)
@@ -132,26 +132,19 @@ __device__ __forceinline__ void ro_tile_release(unsigned *pool_free, unsigned ti
 }
 
 // Thread-per-env window rebuild on the lane-interleaved storage (every pointer already includes the lane; stride 32).
-// First half.  On entry: table = slots [0, n) (unsorted), window = win[wh, wn) (sorted), side = up to RO_SIDE entries.
-// Everything goes back to the table, then one streaming pass moves the entries with time <= h (at most RO_WCAP) to the
-// scratch list and compacts the others in place (forward, stable).  Leaves tmin = exact minimum of the table and
-// wn = number of candidates in the scratch list (wh = 0).  If more than RO_WCAP entries lie below the horizon the rest
-// stays in the table (the caller retries with a shorter horizon while a table entry is still due).
-__device__ __forceinline__ void ro_rebuild_scan(double *__restrict__ rt_t, unsigned long long *__restrict__ rt_p,
-                                                double *__restrict__ sc_t, unsigned long long *__restrict__ sc_p,
-                                                const WinEntry *__restrict__ win, double *side_t, unsigned long long *side_p,
-                                                unsigned &n, unsigned &wh, unsigned &wn, double &tmin, double &side_min, const double h) {
+// On entry: table = slots [0, n) (unsorted), window = win[wh, wn) (sorted), side = up to RO_SIDE entries.  Everything
+// goes back to the table, then one streaming pass moves the entries with time <= h (at most RO_WCAP) to the scratch list
+// and compacts the others in place (forward, stable), and the scratch list is rank-sorted into the window.  Leaves
+// tmin = exact minimum of the table.  If more than RO_WCAP entries lie below the horizon the rest stays in the table
+// (the caller retries with a shorter horizon while a table entry is still due).
+__device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_p, double *sc_t, unsigned long long *sc_p,
+                                           WinEntry *win, double *side_t, unsigned long long *side_p,
+                                           unsigned &n, unsigned &wh, unsigned &wn, double &tmin, double &side_min,
+                                           const double h, WinEntry &head, WinEntry &nxt) {
     RPH_INIT();
-    for (unsigned s = 0; s < n; s += 2) {               // warm L2 with the table rows (2 x 128-byte lines per row and array)
-        prefetch_l2(rt_t + s * 32);
-        prefetch_l2(rt_p + s * 32);
-    }
-    for (unsigned j0 = wh; j0 < wn; j0 += 4) {          // leftover window entries (4 loads in flight)
-        WinEntry w[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) if (j0 + i < wn) w[i] = win_load(win + (j0 + i) * 32);
-#pragma unroll
-        for (int i = 0; i < 4; i++) if (j0 + i < wn) { rt_t[n * 32] = w[i].t; rt_p[n * 32] = w[i].p; n++; }
+    for (unsigned j = wh; j < wn; j++) {                // leftover window entries
+        const WinEntry w = win_load(win + j * 32);
+        rt_t[n * 32] = w.t; rt_p[n * 32] = w.p; n++;
     }
 #pragma unroll
     for (int s = 0; s < RO_SIDE; s++) {                 // side buffer
@@ -186,64 +179,24 @@ __device__ __forceinline__ void ro_rebuild_scan(double *__restrict__ rt_t, unsig
     }
     n = k;
     tmin = mn;
-    wh = 0; wn = c;
     RPH_MARK(12);                                       // rebuild: streaming pass
-}
-
-// Second half: the c candidates of the scratch list, sorted by release time into the window.  Ranks are computed on float
-// keys held in shared memory (`tile`: one pool tile per warp, taken only for this half): rounding down is monotone, so
-// key_a < key_b implies t_a < t_b, and equal keys (about one pair in a million) are ordered by the exact times.  The
-// inverse permutation then drives a batched gather of the exact entries.
-__device__ __forceinline__ void ro_rebuild_sort(const double *__restrict__ sc_t, const unsigned long long *__restrict__ sc_p,
-                                                WinEntry *__restrict__ win, unsigned char *tile, const int lane, const unsigned c,
-                                                const double h, WinEntry &head, WinEntry &nxt) {
-    RPH_INIT();
-    float *keys = reinterpret_cast<float *>(tile) + lane;                   // keys[q * 32]
-    unsigned char *inv = tile + RO_WCAP * 128 + lane;                       // inv[rank * 32] = candidate index
     head.t = ORLG_INF; nxt.t = ORLG_INF;
-    for (unsigned j0 = 0; j0 < c; j0 += 8) {
-        double tt[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) tt[i] = j0 + i < c ? sc_t[(j0 + i) * 32] : 0.0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) if (j0 + i < c) keys[(j0 + i) * 32] = __double2float_rd(tt[i] - h);
-    }
-    for (unsigned j = 0; j < c; j++) {
-        const float kj = keys[j * 32];
-        unsigned rank = 0, ties = 0;
+    for (unsigned j = 0; j < c; j++) {                  // rank sort (c is ~15: quadratic is fine, the loads coalesce)
+        const double tj = sc_t[j * 32];
+        unsigned rank = 0;
 #pragma unroll 4
         for (unsigned q = 0; q < c; q++) {
-            const float kq = keys[q * 32];
-            rank += kq < kj ? 1u : 0u;
-            ties += kq == kj ? 1u : 0u;
+            const double tq = sc_t[q * 32];
+            rank += (tq < tj || (tq == tj && q < j)) ? 1u : 0u;
         }
-        if (ties > 1) {                                 // exact order among equal keys
-            const double tj = sc_t[j * 32];
-            rank = 0;
-            for (unsigned q = 0; q < c; q++) {
-                const double tq = sc_t[q * 32];
-                rank += (tq < tj || (tq == tj && q < j)) ? 1u : 0u;
-            }
-        }
-        inv[rank * 32] = (unsigned char)j;
+        WinEntry w;
+        w.t = tj; w.p = sc_p[j * 32];
+        win[rank * 32] = w;
+        if (rank == 0) head = w;
+        if (rank == 1) nxt = w;
     }
-    for (unsigned r0 = 0; r0 < c; r0 += 4) {            // gather in window order, 8 loads in flight
-        WinEntry w[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (r0 + i < c) {
-                const unsigned j = inv[(r0 + i) * 32];
-                w[i].t = sc_t[j * 32]; w[i].p = sc_p[j * 32];
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) if (r0 + i < c) win[(r0 + i) * 32] = w[i];
-        if (r0 == 0) {
-            head = w[0];
-            if (c > 1) nxt = w[1];
-        }
-    }
-    RPH_MARK(13);                                       // rebuild: sort
+    wh = 0; wn = c;
+    RPH_MARK(13);                                       // rebuild: rank sort
 }
 
 // packed integer pre-image of one path's features: start (7, 127 = no block) | length (7) | total free (7) | free runs (6) | slots (5)
@@ -374,11 +327,8 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                     rt_p[(s0 + 2 * i) * 32] = b[i].x; rt_p[(s0 + 2 * i + 1) * 32] = b[i].y;
                 }
             }
-            ro_rebuild_scan(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn);
+            ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt);
         }
-        const unsigned tile = ro_tile_acquire(pool_free, lane);
-        if (live) ro_rebuild_sort(sc_t, sc_p, win, pool + (size_t)tile * ra.tile_bytes, lane, wn, hzn, head, nxt);
-        ro_tile_release(pool_free, tile, lane);
     }
     int npaths_cur = min((int)s_pair_count[src * p.N + dst], KM);       // candidate paths of the pending request
 
@@ -537,11 +487,10 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             RPH_COUNT(15);
             // a retry means the window filled up before every due service was reached: shorter horizon, down to the clock itself
             hzn = tries < 60 ? __dadd_rn(now, __dmul_rn(ra.span, __longlong_as_double((long long)(1023 - tries) << 52))) : now;
-            if (live) ro_rebuild_scan(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn);
-            const unsigned tile = ro_tile_acquire(pool_free, lane);
-            if (live) ro_rebuild_sort(sc_t, sc_p, win, pool + (size_t)tile * ra.tile_bytes, lane, wn, hzn, head, nxt);
-            ro_tile_release(pool_free, tile, lane);
-            if (live) { RO_POP_DUE(); }
+            if (live) {
+                ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt);
+                RO_POP_DUE();
+            }
         }
         RPH_MARK(3);                 // rebuild
         if (live) {
