@@ -304,6 +304,50 @@ def main():
                       "steps": k_e2e, "n_gpus": world,
                       "note": "VecEnv.step with pinned host buffers on every rank concurrently, synchronised every step"}
 
+    # ---- the same K steps with the results delivered to the HOST as packed 32-byte records (orlg_rollout_packed: the
+    # integer pre-image of the observation + request + action / accepted / done; orlg_expand_packed decodes them).  The
+    # device policy needs no per-step input, so there is no H2D; chunks of 4 steps are double-buffered: the D2H copy of
+    # chunk c (side stream) overlaps the kernel of chunk c + 1.
+    e2e_packed = None
+    if not args.no_e2e:
+        ck = 4
+        k_pk = max(20, min(K, 200)) // ck * ck
+        d_pk = [torch.empty((ck, n, 8), dtype=torch.int32, device=dev) for _ in range(2)]
+        h_pk = [torch.empty((ck, n, 8), dtype=torch.int32).pin_memory() for _ in range(2)]
+        s_copy = torch.cuda.Stream(device=dev)
+        ev_k = [torch.cuda.Event() for _ in range(2)]
+        ev_c = [torch.cuda.Event() for _ in range(2)]
+
+        def packed_block(k):
+            cur = torch.cuda.current_stream(dev)
+            for c in range(k // ck):
+                b = c & 1
+                if c >= 2:
+                    cur.wait_event(ev_c[b])                 # the copy that last read d_pk[b] has finished
+                env.rollout_packed(ck, "random", out=d_pk[b])
+                ev_k[b].record(cur)
+                s_copy.wait_event(ev_k[b])
+                with torch.cuda.stream(s_copy):
+                    h_pk[b].copy_(d_pk[b], non_blocking=True)
+                    ev_c[b].record(s_copy)
+                if c >= 1:
+                    ev_c[1 - b].synchronize()               # the consumer now owns chunk c - 1 in h_pk[1 - b]
+            ev_c[(k // ck - 1) & 1].synchronize()
+            torch.cuda.synchronize()
+
+        packed_block(2 * ck)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        packed_block(k_pk)
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_packed = {"value": n * world * k_pk / float(dt.item()), "unit": "env-steps/s", "h2d_bytes_per_step": 0,
+                      "d2h_bytes_per_step": n * 32 * world, "steps": k_pk, "n_gpus": world,
+                      "note": "orlg_rollout_packed (device policy) + pinned D2H of 32-byte step records, double-buffered in chunks "
+                              "of %d steps; wall clock, max over ranks; decoding to float32 rows (orlg_expand_packed) is left to the consumer" % ck}
+
     out = None
     if rank == 0:
         # ---- roofline of the dominant kernel: the timed region IS that kernel (one launch per <= 256 steps)
@@ -350,7 +394,8 @@ def main():
                                                                             env.state_bytes / 1e6),
                        "parallelism": "env-sharded x%d, no data-path collective" % world},
             "timing": {"reps": args.reps, "rep_ms": rep_ms, "stat": "median of the repetitions (each: max over ranks)"},
-            "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_python": cpu_py, "e2e": e2e_result, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_python": cpu_py, "e2e": e2e_result, "e2e_packed": e2e_packed,
+            "gpu_launches": launches,
             "clocks": sampler.summary(), "step_path_ms_per_step": step_path_ms,
             "accept_rate": 1.0 - stats["service_blocking_rate"], "envs_with_errors": stats["envs_with_errors"],
         }
