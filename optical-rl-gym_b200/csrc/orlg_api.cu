@@ -35,6 +35,7 @@ struct orlg_env {
     int km;                       // KM template instance (5 or 8)
     bool fast;                    // DeepRMSA fast kernel applicable (NSFNET-class: 22 links, k <= 5)
     bool hot;                     // ... and its steady-state specialisation (deeprmsa_fast_kernel<.., HOT = true>)
+    bool ro_ok;                   // the persistent rollout kernel applies (DeepRMSA / RMSA / RWA on NSFNET-class topologies)
     CUtensorMap mask_map;         // TMA view of the mask tensor: [C*E rows][n x 16 bytes], box = E rows x 512 bytes
     bool wide;                    // beyond 32 links / 128 slots / 8 paths: CSR link lists, multi-word masks
     size_t fast_smem;
@@ -270,7 +271,7 @@ bool rollout_plan(const orlg_env *env, int *wpc_out, RolloutArgs *ra, size_t *sm
     for (; wpc >= 1; wpc--) {
         const size_t fixed = (size_t)p.tab_vec * 16 + (size_t)wpc * warp_bytes + 16;
         if (fixed + tile > budget) continue;
-        int tiles = (int)((budget - fixed) / tile);
+        int tiles = tile > 0 ? (int)((budget - fixed) / tile) : 0;       // kinds without a tensor observation need no tile
         if (tiles > wpc) tiles = wpc;
         if (tiles > 32) tiles = 32;
         if (const char *v = std::getenv("ORLG_RO_TILES")) { int w = std::atoi(v); if (w >= 1 && w <= tiles) tiles = w; }
@@ -282,29 +283,39 @@ bool rollout_plan(const orlg_env *env, int *wpc_out, RolloutArgs *ra, size_t *sm
     return false;
 }
 
-template <int ET>
-cudaError_t launch_rollout(const orlg_env *env, const RolloutArgs &ra, int policy, int wpc, size_t smem, cudaStream_t s) {
+template <int ET, int KIND>
+cudaError_t launch_rollout_kind(const orlg_env *env, const RolloutArgs &ra, int policy, int wpc, size_t smem, cudaStream_t s) {
     const int threads = wpc * 32, blocks = (env->p.n + threads - 1) / threads;
     cudaLaunchConfig_t cfg = pdl_config(blocks, threads, smem, s);
-    cudaError_t e;
-#define ORLG_RO_LAUNCH(POL)                                                                                          \
-    do {                                                                                                             \
-        e = cudaFuncSetAttribute(deeprmsa_rollout_kernel<ET, POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, deeprmsa_rollout_kernel<ET, POL>, env->p, ra);            \
-    } while (0)
+    cudaError_t e = cudaErrorInvalidValue;
     const bool trace = env->p.traffic == ORLG_TRAFFIC_TRACE;
+#define ORLG_RO_LAUNCH(POL, TR)                                                                                          \
+    do {                                                                                                                 \
+        e = cudaFuncSetAttribute(deeprmsa_rollout_kernel<ET, POL, TR, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, deeprmsa_rollout_kernel<ET, POL, TR, KIND>, env->p, ra);     \
+    } while (0)
     if (policy == ORLG_POLICY_REPLAY) {
-        if (trace) {
-            e = cudaFuncSetAttribute(deeprmsa_rollout_kernel<ET, RO_POLICY_REPLAY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, deeprmsa_rollout_kernel<ET, RO_POLICY_REPLAY, true>, env->p, ra);
-        } else ORLG_RO_LAUNCH(RO_POLICY_REPLAY);
-    } else if (policy == ORLG_POLICY_RANDOM) ORLG_RO_LAUNCH(RO_POLICY_RANDOM);
-    else if (policy == ORLG_HEUR_SP_FF) ORLG_RO_LAUNCH(RO_POLICY_SP_FF);
-    else ORLG_RO_LAUNCH(RO_POLICY_SAP_FF);
+        if (trace) ORLG_RO_LAUNCH(RO_POLICY_REPLAY, true); else ORLG_RO_LAUNCH(RO_POLICY_REPLAY, false);
+    } else if (trace) {
+        return cudaErrorInvalidValue;                          // (filtered by the caller: trace traffic is replay-only here)
+    } else if (policy == ORLG_POLICY_RANDOM) ORLG_RO_LAUNCH(RO_POLICY_RANDOM, false);
+    else if (policy == ORLG_HEUR_SP_FF) ORLG_RO_LAUNCH(RO_POLICY_SP_FF, false);
+    else if (policy == ORLG_HEUR_SAP_FF) ORLG_RO_LAUNCH(RO_POLICY_SAP_FF, false);
+    else if (policy == ORLG_HEUR_LLP_FF) { if (KIND != ORLG_DEEPRMSA) ORLG_RO_LAUNCH(RO_POLICY_LLP_FF, false); }
+    else if (policy == ORLG_HEUR_SAP_LF) { if (KIND == ORLG_RWA) ORLG_RO_LAUNCH(RO_POLICY_SAP_LF, false); }
 #undef ORLG_RO_LAUNCH
     return e;
 }
 
+template <int ET>
+cudaError_t launch_rollout(const orlg_env *env, const RolloutArgs &ra, int policy, int wpc, size_t smem, cudaStream_t s) {
+    switch (env->p.kind) {
+    case ORLG_DEEPRMSA: return launch_rollout_kind<ET, ORLG_DEEPRMSA>(env, ra, policy, wpc, smem, s);
+    case ORLG_RMSA: return launch_rollout_kind<ET, ORLG_RMSA>(env, ra, policy, wpc, smem, s);
+    case ORLG_RWA: return launch_rollout_kind<ET, ORLG_RWA>(env, ra, policy, wpc, smem, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
 }  // namespace
 
 extern "C" {
@@ -481,7 +492,8 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     // ---- fast DeepRMSA kernel: small tables packed for shared-memory staging
     env->fast = false;
     env->hot = false;
-    if (!wide && cfg->kind == ORLG_DEEPRMSA && p.k <= 5 && P <= 65535 && se_max <= 15 && !std::getenv("ORLG_FORCE_GENERIC")) {
+    env->ro_ok = false;
+    if (!wide && cfg->kind != ORLG_RMCSA && p.k <= 5 && P <= 65535 && se_max <= 15 && !std::getenv("ORLG_FORCE_GENERIC")) {
         std::vector<unsigned char> blob;
         auto put = [&blob](const void *src, size_t bytes) {
             size_t off = (blob.size() + 15) / 16 * 16;
@@ -538,7 +550,7 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
             rc = dev_upload(env, &p.tab_blob, blob4);
             if (rc) { orlg_destroy(env); return rc; }
             p.tab_vec = (int)blob4.size();
-            env->fast = true;
+            env->fast = cfg->kind == ORLG_DEEPRMSA;
             size_t per_thread = (size_t)p.obs_dim * (p.obs_f64 ? 8 : 4);      // observation tile overlays the mask area
             if (per_thread < (size_t)p.E * 16) per_thread = (size_t)p.E * 16;
             p.warp_area_bytes = (int)((per_thread * 32 + 127) / 128 * 128);
@@ -570,6 +582,11 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
             env->hot = env->fast && J == 1 && p.k == 5 && p.cand_stride == 8 && t->num_bit_rates == 0 && cfg->bit_rate_hi < 128 &&
                        cfg->bit_rate_lo >= 0 && n_hi <= 16 && (p.obs_dim & 1) == 0 && p.E <= 256 && !std::getenv("ORLG_NO_HOT");
             if (env->hot && !encode_mask_map(env)) env->hot = false;
+            // the persistent rollout kernel (orlg_rollout.cuh): DeepRMSA-v0 under the HOT conditions; RMSA-v0 with continuous
+            // bit rates below 128 Gb/s whose slot counts fit the 4-round shift-AND; RWA-v0 (one wavelength per lightpath)
+            const bool small_n = t->num_bit_rates == 0 && cfg->bit_rate_hi < 128 && cfg->bit_rate_lo >= 0 && n_hi <= 16;
+            env->ro_ok = cfg->kind == ORLG_DEEPRMSA ? env->hot
+                         : (ea == cudaSuccess && p.E <= 32 && (cfg->kind == ORLG_RWA || small_n) && !std::getenv("ORLG_NO_HOT"));
         }
     }
 
@@ -865,11 +882,12 @@ static int rollout_impl(orlg_env *env, int steps, int policy, void *obs_dev, flo
     if (steps == 0) return ORLG_OK;
     Params &p = env->p;
     cudaStream_t s = (cudaStream_t)stream;
-    const bool persistent = env->hot && !p.stats && !p.obs_f64 &&
-                            (p.traffic == ORLG_TRAFFIC_PHILOX ? (policy == ORLG_POLICY_RANDOM || policy == ORLG_POLICY_REPLAY ||
-                                                                 policy == ORLG_HEUR_SP_FF || policy == ORLG_HEUR_SAP_FF)
-                                                              : policy == ORLG_POLICY_REPLAY) &&
-                            !std::getenv("ORLG_NO_ROLLOUT_KERNEL");
+    bool policy_ok;
+    if (p.traffic == ORLG_TRAFFIC_TRACE) policy_ok = policy == ORLG_POLICY_REPLAY;
+    else if (p.kind == ORLG_DEEPRMSA) policy_ok = policy == ORLG_POLICY_RANDOM || policy == ORLG_POLICY_REPLAY || policy == ORLG_HEUR_SP_FF || policy == ORLG_HEUR_SAP_FF;
+    else if (p.kind == ORLG_RMSA) policy_ok = policy != ORLG_HEUR_SAP_LF;
+    else policy_ok = true;
+    const bool persistent = env->ro_ok && !p.stats && !p.obs_f64 && !p.br_hist && policy_ok && !std::getenv("ORLG_NO_ROLLOUT_KERNEL");
     RolloutArgs ra;
     std::memset(&ra, 0, sizeof(ra));
     int wpc = 0;
@@ -895,6 +913,7 @@ static int rollout_impl(orlg_env *env, int steps, int policy, void *obs_dev, flo
         ra.obs = reinterpret_cast<float *>(obs_dev);
         ra.reward = reward_dev; ra.done = done_dev; ra.actions = actions_dev;
         ra.packed = reinterpret_cast<uint4 *>(packed_dev);
+        if (packed_dev && p.kind != ORLG_DEEPRMSA) return fail(ORLG_E_UNSUPPORTED, "packed records describe the DeepRMSA observation");
         rollout_state_args(env, &ra);
         ra.resume = env->ro_valid ? 1 : 0;
         cudaError_t e = p.E == 22 ? launch_rollout<22>(env, ra, policy, wpc, smem, s) : launch_rollout<0>(env, ra, policy, wpc, smem, s);

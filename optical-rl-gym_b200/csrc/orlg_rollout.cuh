@@ -36,7 +36,7 @@ namespace orlg {
 constexpr int RO_WCAP = 64;            // window entries per env
 constexpr int RO_SIDE = 3;             // side-buffer entries per env (shared memory)
 constexpr int RO_MAX_THREADS = 448;    // 14 warps x 148 SMs >= 65536 envs in one wave
-enum { RO_POLICY_RANDOM = 0, RO_POLICY_SP_FF = 1, RO_POLICY_SAP_FF = 2, RO_POLICY_REPLAY = 3 };
+enum { RO_POLICY_RANDOM = 0, RO_POLICY_SP_FF = 1, RO_POLICY_SAP_FF = 2, RO_POLICY_REPLAY = 3, RO_POLICY_LLP_FF = 4, RO_POLICY_SAP_LF = 5 };
 
 // optional cycle accounting per warp (instrumented builds: -DORLG_PHASE_TIMING, tools/rollout_phases.py)
 #ifdef ORLG_PHASE_TIMING
@@ -206,7 +206,9 @@ __device__ __forceinline__ unsigned feat_pack(int st, int len, int total, int ru
 
 // TRACE: the requests come from the recorded trace (orlg_set_trace) instead of the Philox generator; with
 // RO_POLICY_REPLAY (actions given up front) this replays a reference run through the persistent kernel.
-template <int ET, int POLICY, bool TRACE = false>
+// KIND: DeepRMSA-v0 (block-feature observation, path action), RMSA-v0 or RWA-v0 (no tensor observation, (path, slot) action,
+// the reference's first-fit heuristics evaluated on the cached free-slot masks of the candidate paths).
+template <int ET, int POLICY, bool TRACE = false, int KIND = ORLG_DEEPRMSA>
 __global__ void __launch_bounds__(RO_MAX_THREADS, 1)
 deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     constexpr int KM = 5;
@@ -244,6 +246,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     const unsigned char *s_pair_count = smem + p.off_pair_count;
     const unsigned *s_path_lm = reinterpret_cast<const unsigned *>(smem + p.off_path_lm);
     const unsigned char *s_path_se = smem + p.off_path_se;
+    const unsigned long long *s_path_ll = reinterpret_cast<const unsigned long long *>(smem + p.off_path_ll);
     const unsigned char *s_nslots = smem + p.off_nslots;
     const unsigned *s_node_thr = reinterpret_cast<const unsigned *>(smem + p.off_node_thr);
     const float *s_pos = reinterpret_cast<const float *>(smem + p.off_pos);
@@ -274,7 +277,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     unsigned nlive = p.nheap[e];                              // live services = table + window + side
     unsigned n_tab = nlive;
     unsigned err = p.errors[e];
-    unsigned long long candw = *reinterpret_cast<const unsigned long long *>(p.cand + (size_t)e * 8);
+    unsigned long long candw = KIND == ORLG_DEEPRMSA ? *reinterpret_cast<const unsigned long long *>(p.cand + (size_t)e * 8) : 0xFFFFFFFFFFFFFFFFULL;
     const size_t gw = (size_t)(env0 >> 5);                       // this warp's slice of the launch-private event storage
     double *const rt_t = ra.rt_t + gw * p.heap_cap * 32 + lane;
     unsigned long long *const rt_p = ra.rt_p + gw * p.heap_cap * 32 + lane;
@@ -334,7 +337,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
 
     const unsigned long long gid = (unsigned long long)(p.env_id_base + e);
     const unsigned k0 = (unsigned)p.seed, k1 = (unsigned)(p.seed >> 32);
-    const unsigned n_act = (unsigned)(p.k) + (p.allow_rejection ? 1u : 0u);     // j = 1
+    const unsigned n_act = (unsigned)(p.k) + (p.allow_rejection ? 1u : 0u);     // path actions (DeepRMSA: j = 1)
 
     // release of the window head; the entry after it was requested one pop earlier
 #define RO_POP_DUE()                                                                                              \
@@ -347,29 +350,48 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     }
 
     RPH_MARK(8);                     // entry: state in + first window build
-    for (int t = 0; t < ra.T; t++) {
+    // cached per candidate path of the PENDING request: first-fit start as the policy defines it (candw, one byte per path,
+    // CAND_NONE = none), free slots (candt) and hop count (candh) for the least-loaded / fewest-hops heuristics.
+    // DeepRMSA-v0 handles keep candw in the canonical state; the other kinds compute it in an extra phase-C pass (t = -1).
+    unsigned long long candt = 0;
+    unsigned candh = 0;
+    for (int t = (KIND == ORLG_DEEPRMSA ? 0 : -1); t < ra.T; t++) {
         bool done = false;
         int npaths = 0;
         unsigned pm[KM];
         int ns[KM];
         unsigned rec_flags = 0;          // action (low 16 bits) | accepted << 28, for the packed record
-        if (live) {
+        if (t < 0) {
+            // ---- first pass of a non-DeepRMSA launch: only the candidate cache of the pending request is built
+            if (live) {
+                const int pair = src * p.N + dst;
+                const int first = s_pair_first[pair];
+                npaths = min((int)s_pair_count[pair], KM);
+#pragma unroll
+                for (int q = 0; q < KM; q++) {
+                    const bool have = q < npaths;
+                    const int row = have ? first + q : first;
+                    ns[q] = KIND == ORLG_RWA ? 1 : s_nslots[s_path_se[row] * 128 + br];
+                    pm[q] = have ? s_path_lm[row] : 0u;
+                }
+                npaths_cur = npaths;
+            }
+        } else if (live) {
             // ---- the next request (rmsa_env.py:545-561): a pure function of (seed, global env id, request index)
             double e_iat = 0.0, e_hold = 0.0, t_arrival = now;
-            int p_src = 0, p_dst = 1, p_br = p.br_lo;
+            int p_src = 0, p_dst = 1, p_br = KIND == ORLG_RWA ? 0 : p.br_lo;
             if (TRACE) {
                 if ((long long)ridx < p.trace_len) {
                     const orlg_request r = p.trace[(size_t)e * p.trace_len + ridx];
                     t_arrival = r.arrival; e_hold = r.holding; p_src = r.src; p_dst = r.dst;
-                    p_br = min(max(r.bit_rate, 0), 127);
-                    if (r.bit_rate > 127) err |= ORLG_ERR_TRACE_RANGE;        // beyond the slot-count table of this kernel
+                    p_br = KIND == ORLG_RWA ? 0 : min(max(r.bit_rate, 0), 127);
+                    if (KIND != ORLG_RWA && r.bit_rate > 127) err |= ORLG_ERR_TRACE_RANGE;       // beyond the slot-count table of this kernel
                 } else {
                     err |= ORLG_ERR_TRACE_EXHAUSTED;
                 }
             } else {
-                uint32_t rc_[4] = {ridx, 0u, (uint32_t)gid, 0u}, rd_[4] = {ridx, 0u, (uint32_t)gid, 1u};
+                uint32_t rc_[4] = {ridx, 0u, (uint32_t)gid, 0u};
                 philox4x32_10(rc_, k0, k1);
-                philox4x32_10(rd_, k0, k1);
                 e_iat = __dmul_rn(neg_log_u32(rc_[0]), p.mean_iat);
                 e_hold = __dmul_rn(neg_log_u32(rc_[1]), p.mean_holding);
                 const int nn = p.N;
@@ -381,7 +403,11 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                 if (tt >= lo) tt += mass;
                 p_dst = pick_thr_bsearch(s_node_thr, nn, p.node_top_step, (unsigned)tt);
                 if (p_dst == p_src) p_dst = (p_src + 1) % nn;
-                p_br = p.br_lo + (int)__umulhi(rd_[0], (unsigned)p.br_span);
+                if (KIND != ORLG_RWA) {
+                    uint32_t rd_[4] = {ridx, 0u, (uint32_t)gid, 1u};
+                    philox4x32_10(rd_, k0, k1);
+                    p_br = p.br_lo + (int)__umulhi(rd_[0], (unsigned)p.br_span);
+                }
             }
             const int npair = p_src * p.N + p_dst;
             const int p_first = s_pair_first[npair];
@@ -390,44 +416,108 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             for (int q = 0; q < KM; q++) {
                 const bool have = q < npaths;
                 const int row = have ? p_first + q : p_first;
-                ns[q] = s_nslots[s_path_se[row] * 128 + p_br];
+                ns[q] = KIND == ORLG_RWA ? 1 : s_nslots[s_path_se[row] * 128 + p_br];
                 pm[q] = have ? s_path_lm[row] : 0u;
             }
 
             RPH_MARK(0);             // request draw
-            // ---- the policy's action on the pending request
-            int act;
+            // ---- the policy's action on the pending request: DeepRMSA a path index (j = 1), RMSA / RWA (path, slot)
+            const int pair = src * p.N + dst;
+            const int np_cur = (int)s_pair_count[pair];
+            int act = p.k, act_slot = p.S;                       // the reject action
+            bool checked = false;                                // the action came with a first-fit start that is known to be free
             if (POLICY == RO_POLICY_RANDOM) {                    // orlg_random_actions: Philox stream 2, same counter
                 uint32_t ra_[4] = {ridx, 0u, (uint32_t)gid, 2u};
                 philox4x32_10(ra_, k0, k1);
                 act = (int)__umulhi(ra_[0], n_act);
+                if (KIND != ORLG_DEEPRMSA) act_slot = (int)__umulhi(ra_[1], (unsigned)p.S + (p.allow_rejection ? 1u : 0u));
             } else if (POLICY == RO_POLICY_REPLAY) {             // a recorded action sequence
-                act = ra.actions[(size_t)t * p.n + env];
-            } else if (POLICY == RO_POLICY_SP_FF) {              // deeprmsa_env.py:135-143
-                act = (!p.allow_rejection || (candw & 0xffu) != CAND_NONE) ? 0 : p.k;
-            } else {                                             // deeprmsa_env.py:146-155
-                act = p.k;
-                for (int q = npaths_cur - 1; q >= 0; q--)
-                    if (((candw >> (8 * q)) & 0xffu) != CAND_NONE) act = q;
+                if (KIND == ORLG_DEEPRMSA) act = ra.actions[(size_t)t * p.n + env];
+                else { act = ra.actions[((size_t)t * p.n + env) * 2]; act_slot = ra.actions[((size_t)t * p.n + env) * 2 + 1]; }
+            } else if (KIND == ORLG_DEEPRMSA) {
+                if (POLICY == RO_POLICY_SP_FF) {                 // deeprmsa_env.py:135-143
+                    act = (!p.allow_rejection || (candw & 0xffu) != CAND_NONE) ? 0 : p.k;
+                } else {                                         // deeprmsa_env.py:146-155
+                    for (int q = npaths_cur - 1; q >= 0; q--)
+                        if (((candw >> (8 * q)) & 0xffu) != CAND_NONE) act = q;
+                }
+            } else {
+                // rmsa_env.py:747-803 / rwa_env.py:425-502 on the cached first-fit starts (which already honour the
+                // reference's range(0, S - n) / range(W - 1, 0, -1) scans)
+                checked = true;
+                if (POLICY == RO_POLICY_SP_FF) {
+                    if (npaths_cur > 0 && (candw & 0xffu) != CAND_NONE) { act = 0; act_slot = (int)(candw & 0xffu); }
+                } else if (POLICY == RO_POLICY_LLP_FF) {         // most free slots among the paths that fit (first wins ties)
+                    int best = KIND == ORLG_RWA ? -1 : 0;
+                    for (int q = 0; q < npaths_cur; q++) {
+                        const unsigned st = (unsigned)((candw >> (8 * q)) & 0xffu);
+                        const int fr = (int)((candt >> (8 * q)) & 0xffu);
+                        if (st != CAND_NONE && fr > best) { best = fr; act = q; act_slot = (int)st; }
+                    }
+                } else if (KIND == ORLG_RWA) {                   // SAP-FF / SAP-LF: fewest hops among the paths with a free wavelength
+                    int best_hops = 0x7fffffff;
+                    for (int q = 0; q < npaths_cur; q++) {
+                        const unsigned st = (unsigned)((candw >> (8 * q)) & 0xffu);
+                        const int hops = (int)((candh >> (4 * q)) & 0xfu);
+                        if (hops < best_hops && st != CAND_NONE) { best_hops = hops; act = q; act_slot = (int)st; }
+                    }
+                } else {                                         // RMSA SAP-FF: first path (k order) that fits
+                    for (int q = npaths_cur - 1; q >= 0; q--) {
+                        const unsigned st = (unsigned)((candw >> (8 * q)) & 0xffu);
+                        if (st != CAND_NONE) { act = q; act_slot = (int)st; }
+                    }
+                }
             }
-            if (POLICY != RO_POLICY_REPLAY && ra.actions) ra.actions[(size_t)t * p.n + env] = act;
+            if (POLICY != RO_POLICY_REPLAY && ra.actions) {
+                if (KIND == ORLG_DEEPRMSA) ra.actions[(size_t)t * p.n + env] = act;
+                else *reinterpret_cast<int2 *>(ra.actions + ((size_t)t * p.n + env) * 2) = make_int2(act, act_slot);
+            }
 
-            // ---- Phase A (deeprmsa_env.py:48-58 -> rmsa_env.py:163-209): the cached block start decides
+            // ---- Phase A (rmsa_env.py:163-209, deeprmsa_env.py:48-58, rwa_env.py:101-136)
             bool accepted = false;
-            if (act >= 0 && act < p.k) {
-                const int pair = src * p.N + dst;
-                if (act < (int)s_pair_count[pair]) {
-                    const unsigned st = (unsigned)((candw >> (8 * act)) & 0xffu);
-                    if (st != CAND_NONE) {
+            int a_start = 0;
+            if (KIND == ORLG_RWA && p.act_hist) {                // self.actions_output[path, wavelength] += 1 (rwa_env.py:103)
+                const int R = p.k + p.allow_rejection, Cn = p.S + p.allow_rejection;
+                if (act >= 0 && act < R && act_slot >= 0 && act_slot < Cn) {
+                    atomicAdd(p.act_hist + (size_t)act * p.n + env, 1);               // fire-and-forget (RED): nothing waits for it
+                    atomicAdd(p.act_hist + (size_t)(R + act_slot) * p.n + env, 1);
+                } else {
+                    err |= ORLG_ERR_NO_SUCH_PATH;
+                }
+            }
+            if (act >= 0 && act < p.k && (KIND == ORLG_DEEPRMSA || (act_slot >= 0 && act_slot < p.S))) {
+                if (act < np_cur) {
+                    const int a_row = s_pair_first[pair] + act;
+                    const int a_n = KIND == ORLG_RWA ? 1 : s_nslots[s_path_se[a_row] * 128 + br];
+                    const unsigned a_lm = s_path_lm[a_row];
+                    bool fits;
+                    if (KIND == ORLG_DEEPRMSA) {                 // the cached block start decides
+                        const unsigned st = (unsigned)((candw >> (8 * act)) & 0xffu);
+                        fits = st != CAND_NONE;
+                        a_start = (int)st;
+                    } else if (checked) {
+                        fits = true; a_start = act_slot;
+                    } else {                                     // is_path_free (rmsa_env.py:623-636, rwa_env.py:385-400) on the shared-memory masks
+                        a_start = act_slot;
+                        fits = a_start + a_n <= p.S;
+                        if (fits) {
+                            Bits F = bits_ones();
+                            unsigned m = a_lm;
+                            while (m) {
+                                const int l = __ffs(m) - 1;
+                                m &= m - 1;
+                                F = bits_and(F, bits_from(sm[l * 32]));
+                            }
+                            fits = bits_contains(F, bits_range_short(a_start, a_n));
+                        }
+                    }
+                    if (fits) {
                         if (nlive + 1 > (unsigned)p.heap_cap) {
                             err |= ORLG_ERR_HEAP_OVERFLOW;
                         } else {
-                            const int a_row = s_pair_first[pair] + act;
-                            const int a_n = s_nslots[s_path_se[a_row] * 128 + br];
-                            const unsigned a_lm = s_path_lm[a_row];
-                            ro_path_update<false>(sm, a_lm, bits_range_short((int)st, a_n));      // _provision_path
+                            ro_path_update<false>(sm, a_lm, bits_range_short(a_start, a_n));      // _provision_path
                             const double rel = __dadd_rn(now, hold);
-                            const unsigned long long pl = pack_service(a_row, (int)st, a_n, 0, sid);
+                            const unsigned long long pl = pack_service(a_row, a_start, a_n, 0, sid);
                             bool in_side = false;
                             if (rel <= hzn) {                    // expires inside the window: side buffer
 #pragma unroll
@@ -443,7 +533,8 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                                 tmin_tab = dmin(tmin_tab, rel);
                             }
                             nlive++;
-                            d_acc += 1; ep_acc += 1; d_prov += br; ep_prov += br;
+                            d_acc += 1; ep_acc += 1;
+                            if (KIND != ORLG_RWA) { d_prov += br; ep_prov += br; }
                             accepted = true;
                         }
                     }
@@ -451,16 +542,17 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                     err |= ORLG_ERR_NO_SUCH_PATH;
                 }
             }
-            if (ra.reward) ra.reward[(size_t)t * p.n + env] = accepted ? 1.0f : -1.0f;
+            if (KIND == ORLG_RWA) { d_proc += 1; ep_proc += 1; }             // rwa_env.py:135-136: counted in step
+            if (ra.reward) ra.reward[(size_t)t * p.n + env] = accepted ? 1.0f : (KIND == ORLG_DEEPRMSA ? -1.0f : 0.0f);
             rec_flags = ((unsigned)act & 0xffffu) | (accepted ? (1u << 28) : 0u);
 
             RPH_MARK(1);             // action + phase A
-            // ---- Phase B: _next_service (rmsa_env.py:545-597)
+            // ---- Phase B: _next_service (rmsa_env.py:545-597, rwa_env.py:258-288)
             now = TRACE ? t_arrival : __dadd_rn(now, e_iat);
             hold = e_hold; src = p_src; dst = p_dst; br = p_br;
             ridx++;
             sid = ep_proc;
-            d_proc += 1; ep_proc += 1; d_req += br; ep_req += br;
+            if (KIND != ORLG_RWA) { d_proc += 1; ep_proc += 1; d_req += br; ep_req += br; }
             npaths_cur = npaths;
             RO_POP_DUE();
             if (side_min <= now) {
@@ -483,7 +575,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
         }
         RPH_MARK(2);                 // phase B + window / side releases
         // ---- a table entry is due somewhere in the warp: every lane re-centres its window (~1 step in 30)
-        for (int tries = 0; __any_sync(0xffffffffu, live && tmin_tab <= now); tries++) {
+        for (int tries = 0; t >= 0 && __any_sync(0xffffffffu, live && tmin_tab <= now); tries++) {
             RPH_COUNT(15);
             // a retry means the window filled up before every due service was reached: shorter horizon, down to the clock itself
             hzn = tries < 60 ? __dadd_rn(now, __dmul_rn(ra.span, __longlong_as_double((long long)(1023 - tries) << 52))) : now;
@@ -493,13 +585,17 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             }
         }
         RPH_MARK(3);                 // rebuild
-        if (live) {
+        if (live && t >= 0) {
             done = (ep_proc == p.episode_length);
-            if (done && p.auto_reset) { ep_proc = 1; ep_acc = 0; ep_req = br; ep_prov = 0; }      // rmsa_env.py:285-330
+            if (done && p.auto_reset) {                          // rmsa_env.py:285-330, rwa_env.py:164-179
+                ep_acc = 0; ep_prov = 0;
+                if (KIND == ORLG_RWA) { ep_proc = 0; ep_req = 0; } else { ep_proc = 1; ep_req = br; }
+            }
             if (ra.done) ra.done[(size_t)t * p.n + env] = done ? 1 : 0;
         }
 
-        // ---- Phase C (deeprmsa_env.py:60-121): free-slot mask of every candidate path, then the block features
+        // ---- Phase C: free-slot mask of every candidate path of the pending request (get_available_slots,
+        // rmsa_env.py:638-649), then DeepRMSA's block features (deeprmsa_env.py:60-121) / the heuristics' first-fit starts
         unsigned feat[KM];
 #pragma unroll
         for (int q = 0; q < KM; q++) feat[q] = 0;
@@ -530,28 +626,51 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             }
             RPH_MARK(10);            // candidate-path AND
             unsigned long long cand_out = 0xFFFFFFFFFFFFFFFFULL;
+            if (KIND == ORLG_DEEPRMSA) {
 #pragma unroll
-            for (int q = 0; q < KM; q++) {
-                const int n = ns[q];
-                const Bits B = bits_runs_ge_sched(A[q], s_dbl[n]);
-                const int st = bits_ffs_flat(B);
-                const int fe = bits_ffs_flat(bits_andnot(B, bits_shr1(B)));
-                const int total = bits_popc(A[q]);
-                const int runs = bits_popc(bits_andnot(A[q], bits_shl1(A[q])));
-                cand_out = st >= 0 ? ((cand_out & ~(0xFFULL << (8 * q))) | ((unsigned long long)st << (8 * q))) : cand_out;
-                feat[q] = feat_pack(st, fe - st + n, total, runs, n);
+                for (int q = 0; q < KM; q++) {
+                    const int n = ns[q];
+                    const Bits B = bits_runs_ge_sched(A[q], s_dbl[n]);
+                    const int st = bits_ffs_flat(B);
+                    const int fe = bits_ffs_flat(bits_andnot(B, bits_shr1(B)));
+                    const int total = bits_popc(A[q]);
+                    const int runs = bits_popc(bits_andnot(A[q], bits_shl1(A[q])));
+                    cand_out = st >= 0 ? ((cand_out & ~(0xFFULL << (8 * q))) | ((unsigned long long)st << (8 * q))) : cand_out;
+                    feat[q] = feat_pack(st, fe - st + n, total, runs, n);
+                }
+            } else {
+                unsigned long long tot_out = 0;
+                unsigned hops_out = 0;
+                const int first = s_pair_first[src * p.N + dst];
+#pragma unroll
+                for (int q = 0; q < KM; q++) {
+                    int st;
+                    if (KIND == ORLG_RWA) {
+                        if (POLICY == RO_POLICY_SAP_LF) { Bits L = A[q]; L.w[0] &= ~1u; st = bits_fls(L); }     // range(W - 1, 0, -1): never wavelength 0
+                        else st = bits_ffs_flat(A[q]);
+                    } else {                                     // first fit over range(0, S - n): the last feasible start is never tried
+                        const int n = ns[q];
+                        const Bits B = bits_and(bits_runs_ge_sched(A[q], s_dbl[n]), bits_range(0, max(p.S - n, 0)));
+                        st = bits_ffs_flat(B);
+                    }
+                    cand_out = st >= 0 ? ((cand_out & ~(0xFFULL << (8 * q))) | ((unsigned long long)st << (8 * q))) : cand_out;
+                    tot_out |= (unsigned long long)(bits_popc(A[q]) & 0xff) << (8 * q);
+                    if (KIND == ORLG_RWA && q < npaths) hops_out |= (unsigned)(s_path_ll[first + q] >> 60) << (4 * q);
+                }
+                candt = tot_out; candh = hops_out;
             }
             candw = cand_out;
         }
         RPH_MARK(5);                 // features
-        if (ra.packed && live) {         // 32 bytes per env-step, 1 KB contiguous per warp
+        if (t < 0) continue;
+        if (KIND == ORLG_DEEPRMSA && ra.packed && live) {        // 32 bytes per env-step, 1 KB contiguous per warp
             uint4 *rec = ra.packed + ((size_t)t * p.n + env) * 2;
             rec[0] = make_uint4(feat[0], feat[1], feat[2], feat[3]);
             rec[1] = make_uint4(feat[4], (unsigned)br | ((unsigned)src << 8) | ((unsigned)dst << 16) | ((unsigned)npaths << 24) |
                                              (rec_flags & (1u << 28)) | (done ? (1u << 29) : 0u),
                                 rec_flags & 0xffffu, 0u);
         }
-        if (ra.obs) {
+        if (KIND == ORLG_DEEPRMSA && ra.obs) {
             // ---- the warp's 32 rows = one contiguous run of obs[t]: written to a pool tile, copied out with coalesced 16-byte stores
             const unsigned tile = ro_tile_acquire(pool_free, lane);
             unsigned char *stage = pool + (size_t)tile * ra.tile_bytes;
@@ -647,7 +766,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
         p.req_index[env] = ridx;
         p.nheap[env] = nlive;
         p.errors[env] = err;
-        *reinterpret_cast<unsigned long long *>(p.cand + (size_t)env * 8) = candw;
+        if (KIND == ORLG_DEEPRMSA) *reinterpret_cast<unsigned long long *>(p.cand + (size_t)env * 8) = candw;
     }
     RPH_MARK(9);                     // exit: state out
 }

@@ -114,10 +114,21 @@ def test_rollout_without_outputs_and_partial_outputs():
     a.close(); b.close()
 
 
+_RMSA = dict(episode_length=50, load=250, mean_service_holding_time=25, allow_rejection=True)
+_RWA = dict(episode_length=64, load=450, mean_service_holding_time=25)
+
+
 @pytest.mark.parametrize("kind,env_args,policy", [
-    ("RMSA-v0", dict(episode_length=50, load=250, mean_service_holding_time=25, allow_rejection=True), "sap_ff"),
-    ("RWA-v0", dict(episode_length=64, load=450, mean_service_holding_time=25), "random"),
-    ("DeepRMSA-v0", dict(episode_length=40, j=2), "sap"),          # j = 2: outside the persistent kernel's limits
+    # RMSA-v0 / RWA-v0 on NSFNET: the persistent kernel with the reference's heuristics evaluated in-kernel
+    ("RMSA-v0", _RMSA, "sap_ff"), ("RMSA-v0", _RMSA, "sp_ff"), ("RMSA-v0", _RMSA, "llp_ff"), ("RMSA-v0", _RMSA, "random"),
+    ("RMSA-v0", dict(_RMSA, load=600, num_spectrum_resources=64), "sap_ff"),
+    ("RWA-v0", _RWA, "random"), ("RWA-v0", _RWA, "sap_ff"), ("RWA-v0", _RWA, "sap_lf"), ("RWA-v0", _RWA, "llp_ff"),
+    ("RWA-v0", dict(_RWA, load=900), "sp_ff"),
+    # outside the persistent kernel's limits: the same entry point on the per-step kernels
+    ("DeepRMSA-v0", dict(episode_length=40, j=2), "sap"),
+    ("RMSA-v0", dict(_RMSA, bit_rate_selection="discrete"), "sap_ff"),
+    ("RMCSA-v0", dict(episode_length=50, load=400, mean_service_holding_time=25, num_spectrum_resources=100,
+                      num_spatial_resources=3, worst_xt=-84.7, allow_rejection=True), "heuristic"),
 ])
 def test_generic_rollout_equals_step_loop(kind, env_args, policy):
     from optical_rl_gym_b200 import OpticalVecEnv
@@ -126,15 +137,21 @@ def test_generic_rollout_equals_step_loop(kind, env_args, policy):
     kw = dict(traffic="philox", seed=9, **env_args)
     ro = OpticalVecEnv(kind, 80, tables, **kw)
     st = OpticalVecEnv(kind, 80, tables, **kw)
-    T = 60
-    o1, r1, d1, a1 = ro.rollout(T, policy)
-    for t in range(T):
-        a = st.sample_actions() if policy == "random" else st.heuristic(policy)
-        o, r, d, _ = st.step(a)
-        assert torch.equal(a1[t], a) and torch.equal(r1[t], r) and torch.equal(d1[t], d), t
-        if o is not None:
-            assert torch.equal(o1[t], o), t
-    _final_state_equal(ro, st)
+    for T in (60, 1, 130):
+        o1, r1, d1, a1 = ro.rollout(T, policy)
+        for t in range(T):
+            a = st.sample_actions() if policy == "random" else st.heuristic(policy)
+            o, r, d, _ = st.step(a)
+            assert torch.equal(a1[t], a), ("actions", t, a1[t][:8], a[:8])
+            assert torch.equal(r1[t], r) and torch.equal(d1[t], d), t
+            if o is not None:
+                assert torch.equal(o1[t], o), t
+        _final_state_equal(ro, st)
+    if kind == "RWA-v0":          # the action histogram behind info["path_action_probability"] (rwa_env.py:103, 148-151)
+        a = ro.sample_actions()
+        ia, ib = ro.step(a)[3], st.step(a)[3]
+        assert torch.equal(ia["path_action_probability"], ib["path_action_probability"])
+        assert torch.equal(ia["wavelength_action_probability"], ib["wavelength_action_probability"])
     ro.close(); st.close()
 
 
