@@ -128,7 +128,7 @@ _RWA = dict(episode_length=64, load=450, mean_service_holding_time=25)
     ("DeepRMSA-v0", dict(episode_length=40, j=2), "sap"),
     ("RMSA-v0", dict(_RMSA, bit_rate_selection="discrete"), "sap_ff"),
     ("RMCSA-v0", dict(episode_length=50, load=400, mean_service_holding_time=25, num_spectrum_resources=100,
-                      num_spatial_resources=3, worst_xt=-84.7, allow_rejection=True), "heuristic"),
+                      num_spatial_resources=3, worst_xt=-84.7, allow_rejection=True), "sap_ff"),
 ])
 def test_generic_rollout_equals_step_loop(kind, env_args, policy):
     from optical_rl_gym_b200 import OpticalVecEnv
