@@ -174,6 +174,93 @@ def run_reference(args, rank, world):
     }))
 
 
+# The other BASELINE.json configs: secondary lines (`--config c0|c1|c3|c4`); the headline stays configs[2].
+# B_step = SURVEY.md 8(d) algorithmic bytes per env-step of each config.
+SECONDARY = {
+    "c0": dict(kind="RWA-v0", topo="nsfnet", envs=65536, policy="sap_ff", b_step=930, fill=1800,
+               args=dict(episode_length=1000, load=450, mean_service_holding_time=25),
+               workload="RWA-v0 NSFNET k=5 W=80 450E, %d envs/GPU, device shortest-available-path first-fit (configs[0] batched)"),
+    "c1": dict(kind="RMSA-v0", topo="nsfnet", envs=4096, policy="sap_ff", b_step=800, fill=1000,
+               args=dict(episode_length=1000, load=250, mean_service_holding_time=25),
+               workload="RMSA-v0 NSFNET k=5 S=100 250E, %d envs/GPU, device SAP-FF (configs[1])"),
+    "c1x": dict(kind="RMSA-v0", topo="nsfnet", envs=65536, policy="sap_ff", b_step=800, fill=1000,
+                args=dict(episode_length=1000, load=250, mean_service_holding_time=25),
+                workload="RMSA-v0 NSFNET k=5 S=100 250E, %d envs/GPU, device SAP-FF (configs[1] at 65536 envs)"),
+    "c3": dict(kind="RMSA-v0", topo="c3", envs=131072, policy="sap_ff", b_step=1700, fill=600,
+               args=dict(episode_length=1000, load=600, mean_service_holding_time=25, num_spectrum_resources=320),
+               workload="RMSA-v0 synthetic 100 nodes / 300 links, S=320, k=10, 600E, %d envs/GPU, device SAP-FF (configs[3])"),
+    "c4": dict(kind="RMCSA-v0", topo="nsfnet", envs=262144, policy="sap_ff", b_step=1000, fill=600,
+               args=dict(episode_length=1000, load=700, mean_service_holding_time=25, num_spectrum_resources=320,
+                         num_spatial_resources=7, worst_xt=-84.7),
+               workload="RMCSA-v0 NSFNET 7 cores x 320 slots, 700E, %d envs/GPU, device first-core first-fit (configs[4])"),
+}
+
+
+def run_secondary(args):
+    """One JSON line for another BASELINE config: K steps = orlg_rollout launches (persistent kernel for RMSA / RWA on
+    NSFNET, per-step kernels for the wide layouts), R repetitions, CUDA events; single GPU."""
+    import torch
+
+    from optical_rl_gym_b200 import OpticalVecEnv, nsfnet
+    from optical_rl_gym_b200.topology import TopologyTables
+
+    c = SECONDARY[args.config]
+    tables = nsfnet() if c["topo"] == "nsfnet" else TopologyTables.load(
+        os.path.join(ROOT, "tests", "golden", "topo_c3_ring100_chords200_k10.npz"))
+    torch.cuda.set_device(0)
+    n, K = (args.envs if args.envs != ENVS_PER_GPU else c["envs"]), args.steps
+    env = OpticalVecEnv(c["kind"], n, tables, seed=1, collect_info=False, **c["args"])
+    chunk = min(K, 64)
+    rew = torch.empty((chunk, n), dtype=torch.float32, device="cuda")
+    done = torch.empty((chunk, n), dtype=torch.uint8, device="cuda")
+    act = torch.empty((chunk, n, env.action_dim), dtype=torch.int32, device="cuda")
+
+    def k_steps(k):
+        left = k
+        while left > 0:
+            t = min(left, chunk)
+            env.rollout(t, c["policy"], reward=rew[:t], done=done[:t], actions=act[:t], want_obs=False)
+            left -= t
+
+    k_steps(c["fill"])
+    k_steps(max(args.warmup, 3))
+    sampler = ClockSampler(0)
+    rep_ms = []
+    with sampler:
+        for _ in range(args.reps):
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(400000)
+            ev0.record()
+            k_steps(K)
+            ev1.record()
+            torch.cuda.synchronize()
+            rep_ms.append(ev0.elapsed_time(ev1))
+        t_end = time.perf_counter() + 0.25
+        while time.perf_counter() < t_end:
+            k_steps(chunk)
+            torch.cuda.synchronize()
+    ms = sorted(rep_ms)[len(rep_ms) // 2]
+    peak, peak_src = read_peaks()
+    achieved = c["b_step"] * n * K / (ms * 1e-3) / 1e9
+    cnt = env.counters().sum(0).cpu().numpy()
+    persistent = c["topo"] == "nsfnet" and c["kind"] in ("RMSA-v0", "RWA-v0")
+    print(json.dumps({
+        "metric": "env_steps_per_sec", "value": n * K / (ms * 1e-3), "unit": "env-steps/s", "n_gpus": 1, "steps": K,
+        "warmup": args.warmup, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": c["workload"] % n, "secondary": args.config, "envs_per_gpu": n, "fill_steps": c["fill"],
+                   "call": "orlg_rollout, %d steps per call (%s)" % (chunk, "persistent kernel" if persistent else
+                                                                      "heuristic + step kernel per step")},
+        "timing": {"reps": args.reps, "rep_ms": rep_ms, "stat": "median"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "algorithmic_bytes_per_env_step": c["b_step"], "peak_source": peak_src,
+                     "note": "B_step of this config from SURVEY.md 8(d) (an estimate from the formula there)"},
+        "cpu_baseline": None, "e2e": None, "gpu_launches": (K + chunk - 1) // chunk * (1 if persistent else 2 * chunk),
+        "clocks": sampler.summary(), "accept_rate": float(cnt[1]) / float(cnt[0]),
+        "envs_with_errors": int((env.error_flags() != 0).sum()), "state_MB": env.state_bytes / 1e6}))
+
+
 ROLLOUT_CHUNK = 256      # steps per orlg_rollout launch (bounds the [chunk, N, 54] float32 output buffer: 3.6 GB)
 
 
@@ -185,6 +272,8 @@ def main():
     ap.add_argument("--reps", type=int, default=7, help="repetitions of the --steps block (median reported)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU (default: BASELINE config)")
+    ap.add_argument("--config", default="c2", choices=["c2"] + sorted(SECONDARY),
+                    help="c2 = the headline (BASELINE configs[2]); the others print a secondary line for that config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -195,6 +284,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.config != "c2":
+        if rank == 0:
+            run_secondary(args)
         return
 
     # The CPU baseline runs FIRST, on rank 0, while the other ranks are still blocked in the rendezvous of
