@@ -171,6 +171,19 @@ int orlg_expand_packed(const uint32_t *packed_host, int64_t rows, int num_nodes,
 int orlg_rollout_host(orlg_env *env, int steps, int policy, float *obs_host, float *reward_host, uint8_t *done_host,
                       int32_t *actions_host, int chunk_steps, int threads, orlg_stream stream);
 
+/* ---- the PPO agent of the reference's notebook, evaluated on the device ------------------------------------------ */
+/* model.predict(obs, deterministic=True) of the agent the reference trains and ships (examples/stable_baselines3/
+ * DeepRMSA.ipynb cell 13: PPO(MlpPolicy, env, policy_kwargs=dict(net_arch=5*[128])); bkp/deeprmsa-ppo-trained/best_model.zip):
+ * obs -> 5 x (Linear 128 + tanh) -> action_net / value_net -> argmax.  One fused kernel on the tensor cores (bf16 operands,
+ * fp32 accumulation).  weights: HOST float32, the nn.Linear matrices [out, in] row-major one after the other (5 trunk layers,
+ * action_net, value_net); biases likewise. */
+typedef struct orlg_policy orlg_policy;
+int orlg_policy_create(int device, int obs_dim, int hidden, int n_hidden_layers, int n_actions, const float *weights,
+                       const float *biases, orlg_policy **out);
+/* actions_dev int32 [n]; logits_dev float32 [n, n_actions + 1] = logits then value (NULL: skip) */
+int orlg_policy_act(orlg_policy *pol, const float *obs_dev, int n, int32_t *actions_dev, float *logits_dev, orlg_stream stream);
+int orlg_policy_destroy(orlg_policy *pol);
+
 /* Float statistics of `info` (rmsa_env.py:229-264, 439-543, 699-744; RMSA-v0 / DeepRMSA-v0, <= 32 links,
  * <= 128 slots): after this call every orlg_step also writes, per env, float64
  *   stats_dev[env][0..3] = network_compactness, network_compactness_difference,

@@ -9,6 +9,7 @@
 
 #include "orlg_deeprmsa_fast.cuh"
 #include "orlg_rollout.cuh"
+#include "orlg_policy.cuh"
 #include "orlg_step_wide.cuh"
 #include "orlg_wrappers.cuh"
 
@@ -1048,6 +1049,89 @@ int orlg_rollout_host(orlg_env *env, int steps, int policy, float *obs_host, flo
             if (rc) return rc;
         }
     }
+    return ORLG_OK;
+}
+
+// ---------------------------------------------------------------- the shipped PPO agent (orlg_policy.cuh)
+struct orlg_policy {
+    PolicyParams pp;
+    int device;
+    size_t smem;
+    void *w_dev, *b_dev;
+};
+
+static unsigned short f32_to_bf16(float f) {          // round to nearest even
+    unsigned u;
+    std::memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (unsigned short)((u >> 16) | 0x40u);      // NaN
+    return (unsigned short)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+
+int orlg_policy_create(int device, int obs_dim, int hidden, int n_hidden_layers, int n_actions, const float *weights,
+                       const float *biases, orlg_policy **out) {
+    if (!weights || !biases || !out) return fail(ORLG_E_INVALID, "null argument");
+    *out = nullptr;
+    if (hidden != PL_H || n_hidden_layers != PL_LAYERS || obs_dim < 2 || obs_dim > PL_K0 || (obs_dim & 1) || n_actions < 1 ||
+        n_actions + 1 > PL_NOUT)
+        return fail(ORLG_E_UNSUPPORTED, "the fused policy kernel is built for obs_dim <= 64 (even), 5 hidden layers of 128, <= 15 actions");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) return fail(ORLG_E_CUDA, "no such CUDA device");
+    DeviceGuard guard(device);
+    // bf16 weights in the shared-memory operand layout of the kernel: layer l is an [N x K] K-major operand
+    size_t bytes = (size_t)PL_H * PL_K0 * 2 + (size_t)(PL_LAYERS - 1) * PL_H * PL_H * 2 + (size_t)PL_NOUT * PL_H * 2;
+    std::vector<unsigned short> blob(bytes / 2, 0);
+    std::vector<float> bias(PL_LAYERS * PL_H + PL_NOUT, 0.0f);
+    const float *w = weights, *b = biases;
+    size_t off = 0;
+    for (int l = 0; l < PL_LAYERS; l++) {
+        const int K = l == 0 ? obs_dim : PL_H, Kp = l == 0 ? PL_K0 : PL_H;
+        for (int r = 0; r < PL_H; r++)
+            for (int k = 0; k < K; k++) blob[(off + pl_operand_offset(PL_H, r, k)) / 2] = f32_to_bf16(w[(size_t)r * K + k]);
+        for (int r = 0; r < PL_H; r++) bias[l * PL_H + r] = b[r];
+        w += (size_t)PL_H * K; b += PL_H; off += (size_t)PL_H * Kp * 2;
+    }
+    for (int r = 0; r < n_actions + 1; r++)                     // action_net rows, then value_net
+        for (int k = 0; k < PL_H; k++) blob[(off + pl_operand_offset(PL_NOUT, r, k)) / 2] = f32_to_bf16(w[(size_t)r * PL_H + k]);
+    for (int r = 0; r < n_actions + 1; r++) bias[PL_LAYERS * PL_H + r] = b[r];
+    orlg_policy *pol = new orlg_policy();
+    pol->device = device; pol->w_dev = nullptr; pol->b_dev = nullptr;
+    if (cudaMalloc(&pol->w_dev, bytes) != cudaSuccess || cudaMalloc(&pol->b_dev, bias.size() * 4) != cudaSuccess ||
+        cudaMemcpy(pol->w_dev, blob.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(pol->b_dev, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(pol->w_dev); cudaFree(pol->b_dev); delete pol;
+        return fail(ORLG_E_NOMEM, "policy weight upload failed");
+    }
+    pol->pp.w_blob = reinterpret_cast<const uint4 *>(pol->w_dev);
+    pol->pp.w_bytes = (int)bytes;
+    pol->pp.bias = reinterpret_cast<const float *>(pol->b_dev);
+    pol->pp.obs_dim = obs_dim; pol->pp.n_actions = n_actions;
+    pol->smem = bytes + (size_t)PL_TILE * PL_H * 2 + bias.size() * 4 + 32;
+    if (cudaFuncSetAttribute(mlp_policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pol->smem) != cudaSuccess) {
+        cudaFree(pol->w_dev); cudaFree(pol->b_dev); delete pol;
+        return fail(ORLG_E_CUDA, "cudaFuncSetAttribute(policy kernel shared memory) failed");
+    }
+    *out = pol;
+    return ORLG_OK;
+}
+
+int orlg_policy_act(orlg_policy *pol, const float *obs_dev, int n, int32_t *actions_dev, float *logits_dev, orlg_stream stream) {
+    if (!pol || !obs_dev || !actions_dev || n < 0) return fail(ORLG_E_INVALID, "null policy or buffer");
+    if (n == 0) return ORLG_OK;
+    DeviceGuard guard(pol->device);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pol->device);
+    const int tiles = (n + PL_TILE - 1) / PL_TILE;
+    cudaLaunchConfig_t cfg = pdl_config(tiles < sms ? tiles : sms, 128, pol->smem, (cudaStream_t)stream);
+    int *actions = actions_dev;
+    CUDA_OK(cudaLaunchKernelEx(&cfg, mlp_policy_kernel, pol->pp, obs_dev, n, actions, logits_dev));
+    return ORLG_OK;
+}
+
+int orlg_policy_destroy(orlg_policy *pol) {
+    if (!pol) return ORLG_OK;
+    DeviceGuard guard(pol->device);
+    cudaFree(pol->w_dev); cudaFree(pol->b_dev);
+    delete pol;
     return ORLG_OK;
 }
 

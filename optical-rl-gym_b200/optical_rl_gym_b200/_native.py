@@ -89,6 +89,9 @@ def lib():
     L.orlg_action_hist_dim.argtypes = [vp]
     L.orlg_action_probability.argtypes = [vp, vp, vp]
     L.orlg_rollout.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    L.orlg_policy_create.argtypes = [i32, i32, i32, i32, i32, vp, vp, C.POINTER(vp)]
+    L.orlg_policy_act.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.orlg_policy_destroy.argtypes = [vp]
     L.orlg_rollout_packed.argtypes = [vp, i32, i32, vp, vp, vp]
     L.orlg_expand_packed.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, i32]
     L.orlg_rollout_host.argtypes = [vp, i32, i32, vp, vp, vp, vp, i32, i32, vp]
@@ -106,4 +109,4 @@ EXPORTED = ["orlg_create", "orlg_destroy", "orlg_last_error", "orlg_version", "o
             "orlg_observation", "orlg_observation_int", "orlg_heuristic", "orlg_random_actions", "orlg_get_counters",
             "orlg_get_requests", "orlg_export_state", "orlg_error_flags", "orlg_reduce_counters", "orlg_enable_stats",
             "orlg_num_bit_rates", "orlg_bit_rate_blocking", "orlg_matrix_obs_dim", "orlg_matrix_observation",
-            "orlg_path_only_first_fit", "orlg_rollout", "orlg_rollout_packed", "orlg_expand_packed", "orlg_rollout_host", "orlg_action_hist_dim", "orlg_action_probability"]
+            "orlg_path_only_first_fit", "orlg_rollout", "orlg_policy_create", "orlg_policy_act", "orlg_policy_destroy", "orlg_rollout_packed", "orlg_expand_packed", "orlg_rollout_host", "orlg_action_hist_dim", "orlg_action_probability"]

@@ -7,7 +7,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(PKG), "csrc")
 LIB = os.path.join(PKG, "liborlg.so")
 SOURCES = ["orlg_api.cu"]
-HEADERS = ["orlg_kernels.cuh", "orlg_device.cuh", "orlg_deeprmsa_fast.cuh", "orlg_rollout.cuh", "orlg_step_wide.cuh", "orlg_wrappers.cuh", os.path.join("..", "..", "include", "orlg.h")]
+HEADERS = ["orlg_kernels.cuh", "orlg_device.cuh", "orlg_deeprmsa_fast.cuh", "orlg_rollout.cuh", "orlg_policy.cuh", "orlg_step_wide.cuh", "orlg_wrappers.cuh", os.path.join("..", "..", "include", "orlg.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xptxas=-v", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared", "-cudart", "shared"]
 

@@ -4,8 +4,11 @@ Architecture of the agent the reference trains and ships
 (examples/stable_baselines3/DeepRMSA.ipynb: ``PPO(MlpPolicy, env, policy_kwargs=dict(net_arch=5*[128]))``;
 examples/stable_baselines3/bkp/deeprmsa-ppo-trained/best_model.zip): observation 54 -> 5 x (Linear 128 + tanh)
 shared trunk -> ``action_net`` (5 logits) and ``value_net`` (1).  ``from_sb3_zip`` reads ``policy.pth`` out of
-such an archive (a plain ``state_dict``; Stable-Baselines3 itself is not needed).  The forward pass is five
-small GEMMs on whatever device the observations live on (library GEMMs: this is plumbing next to the env).
+such an archive (a plain ``state_dict``; Stable-Baselines3 itself is not needed).
+
+Two forward paths: :meth:`forward` (plain torch float32, the numerics reference) and :meth:`act_native` -- the whole
+``model.predict(obs, deterministic=True)`` as ONE fused sm_100a kernel of liborlg.so (``orlg_policy_act``: bf16
+``tcgen05.mma`` with TMEM accumulators, weights resident in shared memory, tanh + argmax epilogue, int32 actions out).
 """
 from __future__ import annotations
 
@@ -52,6 +55,46 @@ class MlpPolicy(torch.nn.Module):
             sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu", weights_only=True)
         pol = cls.from_state_dict(sd)
         return pol.to(device) if device is not None else pol
+
+    # ------------------------------------------------------------------ fused native kernel (csrc/orlg_policy.cuh)
+    def _native_handle(self, device_index: int):
+        import ctypes as C
+
+        import numpy as np
+
+        from . import _native as nat
+
+        key = ("h", device_index)
+        cache = self.__dict__.setdefault("_native_cache", {})
+        if key not in cache:
+            lins = [m for m in self.shared_net if isinstance(m, torch.nn.Linear)]
+            mats = lins + [self.action_net, self.value_net]
+            w = np.concatenate([m.weight.detach().float().cpu().numpy().reshape(-1) for m in mats]).astype(np.float32)
+            b = np.concatenate([m.bias.detach().float().cpu().numpy().reshape(-1) for m in mats]).astype(np.float32)
+            h = C.c_void_p()
+            nat.check(nat.lib().orlg_policy_create(device_index, lins[0].in_features, lins[0].out_features, len(lins),
+                                                   self.action_net.out_features, w.ctypes.data_as(C.c_void_p),
+                                                   b.ctypes.data_as(C.c_void_p), C.byref(h)))
+            cache[key] = h
+        return cache[key]
+
+    @torch.no_grad()
+    def act_native(self, obs: torch.Tensor, out: torch.Tensor = None, logits: torch.Tensor = None) -> torch.Tensor:
+        """Deterministic actions int32 ``[N, 1]`` from float32 CUDA observations ``[N, obs_dim]`` through the fused tensor-core
+        kernel; ``logits`` (optional float32 ``[N, n_actions + 1]``) receives the logits and the value estimate."""
+        import ctypes as C
+
+        from . import _native as nat
+
+        assert obs.is_cuda and obs.dtype == torch.float32 and obs.is_contiguous()
+        n = obs.shape[0]
+        if out is None:
+            out = torch.empty((n, 1), dtype=torch.int32, device=obs.device)
+        h = self._native_handle(obs.device.index)
+        stream = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
+        nat.check(nat.lib().orlg_policy_act(h, C.c_void_p(obs.data_ptr()), n, C.c_void_p(out.data_ptr()),
+                                            None if logits is None else C.c_void_p(logits.data_ptr()), stream))
+        return out
 
     def forward(self, obs: torch.Tensor):
         """(logits [N, n_actions], value [N]) -- observations are used as they are (SB3 ``preprocess_obs`` of a
