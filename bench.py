@@ -475,6 +475,44 @@ def main():
         torch.cuda.synchronize()
         step_path_ms = a.elapsed_time(b) / 200
 
+        # ---- the "PPO-policy actions" variant of this config (DeepRMSA.ipynb cell 13): obs -> shipped agent's MLP
+        # (54 -> 5 x 128 tanh -> 5 logits, random-init weights of that architecture) -> env.step, all on the device
+        ppo = None
+        try:
+            from optical_rl_gym_b200.policy import MlpPolicy
+
+            torch.manual_seed(0)
+            pol = MlpPolicy(env.obs_dim, 5, (128,) * 5).to(dev)
+            env.observation()
+
+            def ppo_step():
+                pol.act_native(env._obs, out=actions)
+                env.step_raw(actions)
+
+            for _ in range(20):
+                ppo_step()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(400000)
+            a.record()
+            for _ in range(200):
+                ppo_step()
+            b.record()
+            torch.cuda.synchronize()
+            ppo_ms = a.elapsed_time(b) / 200
+            a.record()
+            for _ in range(200):
+                pol.act_native(env._obs, out=actions)
+            b.record()
+            torch.cuda.synchronize()
+            pol_ms = a.elapsed_time(b) / 200
+            flop = 2.0 * n * (env.obs_dim * 128 + 4 * 128 * 128 + 6 * 128)
+            ppo = {"value": n / (ppo_ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ppo_ms, "policy_kernel_ms": pol_ms,
+                   "policy_tflops": flop / (pol_ms * 1e-3) / 1e12, "policy_kernel": "mlp_policy_kernel (bf16 tcgen05.mma, TMEM accumulators)",
+                   "note": "per step: fused policy kernel + per-step env kernel, chained by programmatic dependent launch; 1 GPU"}
+        except Exception as exc:  # noqa: BLE001
+            ppo = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+
         out = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": K, "warmup": args.warmup, "ms_per_step": elapsed_ms / K,
@@ -489,7 +527,7 @@ def main():
             "timing": {"reps": args.reps, "rep_ms": rep_ms, "stat": "median of the repetitions (each: max over ranks)"},
             "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_python": cpu_py, "e2e": e2e_result, "e2e_packed": e2e_packed,
             "gpu_launches": launches,
-            "clocks": sampler.summary(), "step_path_ms_per_step": step_path_ms,
+            "clocks": sampler.summary(), "step_path_ms_per_step": step_path_ms, "ppo_policy_variant": ppo,
             "accept_rate": 1.0 - stats["service_blocking_rate"], "envs_with_errors": stats["envs_with_errors"],
         }
     if world > 1:
