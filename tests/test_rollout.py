@@ -267,3 +267,33 @@ def test_packed_records_and_host_rollout_equal_the_device_rollout():
     _final_state_equal(a, b)
     _final_state_equal(a, c)
     a.close(); b.close(); c.close()
+
+
+@pytest.mark.parametrize("kind,env_args,heuristic,pol_id", [
+    ("DeepRMSA-v0", dict(episode_length=50), "shortest_available_path_first_fit", 11),
+    ("RMSA-v0", dict(episode_length=60, load=250, mean_service_holding_time=25, allow_rejection=True), "least_loaded_path_first_fit", 12),
+    ("RWA-v0", dict(episode_length=40, load=450, mean_service_holding_time=25), "shortest_available_path_first_fit", 11),
+])
+def test_evaluate_heuristic_matches_the_reference_loop(kind, env_args, heuristic, pol_id):
+    """utils.evaluate_heuristic (utils.py:103-141) batched: per-episode rewards / lengths of every env equal the oracle's
+    (which restates the reference loop: reset(), then heuristic + step until done)."""
+    from optical_rl_gym_b200 import OpticalVecEnv
+    from optical_rl_gym_b200.utils import evaluate_heuristic
+
+    tables = helpers.golden_tables()
+    n, episodes, seed = 40, 4, 6
+    env = OpticalVecEnv(kind, n, tables, traffic="philox", seed=seed, **env_args)
+    rewards, lengths = evaluate_heuristic(env, heuristic, n_eval_episodes=episodes, return_episode_rewards=True, chunk=37)
+    okw = helpers.sim_kwargs(dict(kind=kind, env_args=env_args))
+    L = env_args["episode_length"] if kind == "RWA-v0" else env_args["episode_length"] - 1
+    for i, o in enumerate(_oracles(kind, tables, n, seed, **okw)):
+        o.reset(full=False)
+        r = o.rollout(episodes * L, policy=pol_id)
+        ends = np.nonzero(r["dones"])[0]
+        assert list(ends) == [L * (e + 1) - 1 for e in range(episodes)]
+        want = [r["rewards"][e * L:(e + 1) * L].sum() for e in range(episodes)]
+        assert np.array_equal(rewards[:, i].cpu().numpy(), np.array(want)), i
+        assert (lengths[:, i] == L).all()
+    mean, std = evaluate_heuristic(OpticalVecEnv(kind, n, tables, traffic="philox", seed=seed, **env_args), heuristic, n_eval_episodes=episodes)
+    assert abs(mean - rewards.mean().item()) < 1e-9 and abs(std - rewards.std(unbiased=False).item()) < 1e-9
+    env.close()
