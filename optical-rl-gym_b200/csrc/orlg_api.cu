@@ -1105,7 +1105,7 @@ int orlg_policy_create(int device, int obs_dim, int hidden, int n_hidden_layers,
     pol->pp.w_bytes = (int)bytes;
     pol->pp.bias = reinterpret_cast<const float *>(pol->b_dev);
     pol->pp.obs_dim = obs_dim; pol->pp.n_actions = n_actions;
-    pol->smem = bytes + (size_t)PL_TILE * PL_H * 2 + bias.size() * 4 + 32;
+    pol->smem = bytes + (size_t)PL_GROUPS * PL_TILE * PL_H * 2 + bias.size() * 4 + 64;
     if (cudaFuncSetAttribute(mlp_policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pol->smem) != cudaSuccess) {
         cudaFree(pol->w_dev); cudaFree(pol->b_dev); delete pol;
         return fail(ORLG_E_CUDA, "cudaFuncSetAttribute(policy kernel shared memory) failed");
@@ -1120,8 +1120,8 @@ int orlg_policy_act(orlg_policy *pol, const float *obs_dev, int n, int32_t *acti
     DeviceGuard guard(pol->device);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pol->device);
-    const int tiles = (n + PL_TILE - 1) / PL_TILE;
-    cudaLaunchConfig_t cfg = pdl_config(tiles < sms ? tiles : sms, 128, pol->smem, (cudaStream_t)stream);
+    const int pairs = ((n + PL_TILE - 1) / PL_TILE + PL_GROUPS - 1) / PL_GROUPS;       // each CTA walks PL_GROUPS tile streams
+    cudaLaunchConfig_t cfg = pdl_config(pairs < sms ? pairs : sms, 128 * PL_GROUPS, pol->smem, (cudaStream_t)stream);
     int *actions = actions_dev;
     CUDA_OK(cudaLaunchKernelEx(&cfg, mlp_policy_kernel, pol->pp, obs_dev, n, actions, logits_dev));
     return ORLG_OK;

@@ -88,22 +88,29 @@ __device__ __forceinline__ void pl_tmem_ld16(unsigned taddr, float (&v)[16]) {
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
-// smem: [weights w_bytes][A tile 128 x 128 bf16 = 32 KB][bias floats][mbarrier][tmem base]
-__global__ void __launch_bounds__(128, 1)
+// Two warpgroups per CTA, each walking its own stream of 128-environment tiles with its own A buffer, TMEM accumulator and
+// mbarrier (they only share the weights): one warpgroup's tensor-core work and TMEM reads overlap the other's epilogue math.
+// smem: [weights w_bytes][2 x A tile 128 x 128 bf16 = 64 KB][bias floats][mbarriers][tmem base]
+constexpr int PL_GROUPS = 2;
+__device__ __forceinline__ void pl_group_sync(int group) {          // named barrier of one warpgroup (ids 1, 2; 0 = __syncthreads)
+    asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+}
+
+__global__ void __launch_bounds__(128 * PL_GROUPS, 1)
 mlp_policy_kernel(const PolicyParams pp, const float *__restrict__ obs, const int n, int *__restrict__ actions,
                   float *__restrict__ logits_out /* [n, 6] = 5 logits + value, or NULL */) {
     extern __shared__ __align__(128) unsigned char psm[];
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int group = threadIdx.x >> 7, tid = threadIdx.x & 127, warp = tid >> 5;      // warp = index inside the warpgroup: its TMEM lane quarter
     unsigned char *s_w = psm;
-    unsigned char *s_a = psm + pp.w_bytes;
-    float *s_bias = reinterpret_cast<float *>(s_a + PL_TILE * PL_H * 2);
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(s_bias + PL_LAYERS * PL_H + PL_NOUT);   // [0] weights, [1] mma
-    unsigned *s_tmem = reinterpret_cast<unsigned *>(bars + 2);
+    unsigned char *s_a = psm + pp.w_bytes + (size_t)group * PL_TILE * PL_H * 2;
+    float *s_bias = reinterpret_cast<float *>(psm + pp.w_bytes + (size_t)PL_GROUPS * PL_TILE * PL_H * 2);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(s_bias + PL_LAYERS * PL_H + PL_NOUT);   // [0] weights, [1 + g] mma of group g
+    unsigned *s_tmem = reinterpret_cast<unsigned *>(bars + 1 + PL_GROUPS);
 
     pdl_launch_dependents();
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        for (int g = 0; g < PL_GROUPS; g++) mbar_init(&bars[1 + g], 1);
         mbar_expect_tx(&bars[0], (unsigned)pp.w_bytes);
         // the weights do not depend on the previous kernel of the stream: requested before the dependency wait
         const unsigned chunk = 32768u;
@@ -114,16 +121,17 @@ mlp_policy_kernel(const PolicyParams pp, const float *__restrict__ obs, const in
                            "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(&bars[0])) : "memory");
         }
     }
-    for (int i = tid; i < PL_LAYERS * PL_H + PL_NOUT; i += 128) s_bias[i] = pp.bias[i];
-    if (warp == 0) {     // TMEM: 128 columns (one 128 x 128 fp32 accumulator tile)
+    for (int i = threadIdx.x; i < PL_LAYERS * PL_H + PL_NOUT; i += 128 * PL_GROUPS) s_bias[i] = pp.bias[i];
+    if (threadIdx.x < 32) {     // TMEM: 128 columns (one 128 x 128 fp32 accumulator tile) per warpgroup
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"((unsigned)__cvta_generic_to_shared(s_tmem)), "r"(128u) : "memory");
+                     ::"r"((unsigned)__cvta_generic_to_shared(s_tmem)), "r"(128u * PL_GROUPS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const unsigned tmem = *s_tmem;
+    const unsigned tmem_base = *s_tmem;
+    const unsigned tmem = tmem_base + (unsigned)group * 128u;           // this warpgroup's accumulator columns
     const unsigned t_lane = tmem + ((unsigned)(warp * 32) << 16);       // this warp's 32 TMEM lanes
     mbar_wait(&bars[0], 0);           // weights have landed
     pdl_wait();                       // the observations come from the previous kernel of the stream
@@ -134,7 +142,8 @@ mlp_policy_kernel(const PolicyParams pp, const float *__restrict__ obs, const in
     const int row = tid;              // thread t owns row t of the tile: TMEM lane t, A-operand row t
     unsigned char *a_row = s_a + (row >> 3) * 128 + (row & 7) * 16;        // + (k >> 3) * 2048 + (k & 7) * 2
 
-    for (int tile = blockIdx.x; tile * PL_TILE < n; tile += gridDim.x) {
+    unsigned long long *bar = &bars[1 + group];
+    for (int tile = blockIdx.x * PL_GROUPS + group; tile * PL_TILE < n; tile += gridDim.x * PL_GROUPS) {
         const int env = tile * PL_TILE + row;
         // ---- layer-0 input: this row's observation as bf16, K padded to 64 with zeros
         {
@@ -164,7 +173,7 @@ mlp_policy_kernel(const PolicyParams pp, const float *__restrict__ obs, const in
             // activations written by the generic proxy -> visible to the tensor core (async proxy); previous TMEM reads done
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncthreads();
+            pl_group_sync(group);
             if (tid == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const unsigned idesc = pl_instr_desc(PL_TILE, N);
@@ -175,9 +184,9 @@ mlp_policy_kernel(const PolicyParams pp, const float *__restrict__ obs, const in
                     const unsigned long long bd = pl_smem_desc(w_addr + (unsigned)w_off + (unsigned)kk * 2u * b_lbo, b_lbo, 128u);
                     pl_mma(tmem, ad, bd, idesc, kk > 0 ? 1u : 0u);
                 }
-                pl_commit(&bars[1]);
+                pl_commit(bar);
             }
-            mbar_wait(&bars[1], phase);
+            mbar_wait(bar, phase);
             phase ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const float *b = s_bias + layer * PL_H;
@@ -192,9 +201,10 @@ mlp_policy_kernel(const PolicyParams pp, const float *__restrict__ obs, const in
                         uint4 pk;
                         unsigned w4[4];
 #pragma unroll
+                        const float4 b0 = *reinterpret_cast<const float4 *>(b + c0 + 8 * j), b1 = *reinterpret_cast<const float4 *>(b + c0 + 8 * j + 4);
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                         for (int q = 0; q < 4; q++) {
-                            const int c = c0 + 8 * j + 2 * q;
-                            __nv_bfloat162 h = __floats2bfloat162_rn(pl_tanh(v[8 * j + 2 * q] + b[c]), pl_tanh(v[8 * j + 2 * q + 1] + b[c + 1]));
+                            __nv_bfloat162 h = __floats2bfloat162_rn(pl_tanh(v[8 * j + 2 * q] + bb[2 * q]), pl_tanh(v[8 * j + 2 * q + 1] + bb[2 * q + 1]));
                             w4[q] = *reinterpret_cast<unsigned *>(&h);
                         }
                         pk.x = w4[0]; pk.y = w4[1]; pk.z = w4[2]; pk.w = w4[3];
@@ -222,7 +232,7 @@ mlp_policy_kernel(const PolicyParams pp, const float *__restrict__ obs, const in
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u * PL_GROUPS) : "memory");
 }
 
 }  // namespace orlg
