@@ -455,8 +455,10 @@ def main():
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 tj = json.load(f)
-            roofline["traffic"] = tj.get("rollout_kernel_dram_bytes_per_launch")
-            roofline["traffic_steps_per_launch"] = tj.get("rollout_kernel_steps_per_launch")
+            # per launch like `achieved`: the ncu capture (65536 envs x 20 steps per launch) scaled to this launch's env-steps
+            roofline["traffic"] = tj.get("rollout_kernel_bytes_per_env_step") * n * chunk
+            roofline["traffic_source"] = "ncu --set full capture of a %s-step launch (profiles/r2_rollout_ncu_full.csv), %.0f B per env-step" % (
+                tj.get("rollout_kernel_steps_per_launch"), tj.get("rollout_kernel_bytes_per_env_step"))
         except Exception:  # noqa: BLE001
             pass
 
