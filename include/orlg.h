@@ -228,6 +228,14 @@ int orlg_matrix_observation(orlg_env *env, uint8_t *out_dev, orlg_stream stream)
  * RMSA-v0 scans range(0, S - n) like the reference (never the last feasible start), RWA-v0 range(W). */
 int orlg_path_only_first_fit(orlg_env *env, const int32_t *path_actions_dev, int32_t *actions_dev, orlg_stream stream);
 
+/* ---- checkpoint / resume ------------------------------------------------------------------ */
+/* Every per-environment state array of the handle (masks, clocks, pending requests, counters, release-event tables, ...) as one
+ * opaque device buffer of orlg_state_save_bytes(env) bytes; orlg_state_load restores it into a handle created with the same
+ * configuration (seed and trace are configuration, not state).  Stream-ordered except for one 16-byte header copy. */
+int64_t orlg_state_save_bytes(const orlg_env *env);
+int orlg_state_save(orlg_env *env, void *buf_dev, orlg_stream stream);
+int orlg_state_load(orlg_env *env, const void *buf_dev, orlg_stream stream);
+
 /* ---- introspection (what heuristics / tests read from the reference env object) -------- */
 /* counters after the last step: int64 [num_envs, 8], same order as info_dev */
 int orlg_get_counters(orlg_env *env, int64_t *counters_dev, orlg_stream stream);

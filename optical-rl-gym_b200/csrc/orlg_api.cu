@@ -43,6 +43,9 @@ struct orlg_env {
     size_t obs_smem;
     int64_t state_bytes;
     std::vector<void *> allocs;
+    // the per-environment STATE arrays among them (orlg_state_save / orlg_state_load), in allocation order
+    std::vector<std::pair<void *, size_t>> state_allocs;
+    bool alloc_is_state = false;
     // T-steps-per-launch rollout path (orlg_rollout.cuh): window / scratch buffers, allocated by the first call
     WinEntry *ro_win = nullptr;
     double *ro_sc_t = nullptr, *ro_rt_t = nullptr;
@@ -78,6 +81,7 @@ int dev_alloc(orlg_env *env, T **out, size_t count, bool zero = true) {
     if (cudaMalloc(&ptr, bytes) != cudaSuccess) return fail(ORLG_E_NOMEM, "cudaMalloc failed for " + std::to_string(bytes) + " bytes");
     if (zero && cudaMemset(ptr, 0, bytes) != cudaSuccess) return fail(ORLG_E_CUDA, "cudaMemset failed");
     env->allocs.push_back(ptr);
+    if (env->alloc_is_state) env->state_allocs.emplace_back(ptr, bytes);
     env->state_bytes += (int64_t)bytes;
     *out = reinterpret_cast<T *>(ptr);
     return ORLG_OK;
@@ -470,6 +474,7 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     if (!rc) rc = dev_upload(env, &p.bit_rates, bit_rates);
     if (!rc) rc = dev_upload(env, &p.link_order, link_order);
     // ---- state
+    env->alloc_is_state = true;
     const size_t n = (size_t)p.n;
     if (!rc) rc = dev_alloc(env, &p.masks, (size_t)C * p.E * p.nwv * n);
     if (!rc) rc = dev_alloc(env, &p.now, n);
@@ -488,6 +493,7 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     if (!rc) rc = dev_alloc(env, &p.errors, n);
     if (!rc && cfg->kind == ORLG_RMSA && t->num_bit_rates > 0) rc = dev_alloc(env, &p.br_hist, 2 * (size_t)t->num_bit_rates * n);
     if (!rc && cfg->kind == ORLG_RWA) rc = dev_alloc(env, &p.act_hist, (size_t)(p.k + p.S + 2 * p.allow_rejection) * n);
+    env->alloc_is_state = false;
     if (rc) { orlg_destroy(env); return rc; }
 
     // ---- fast DeepRMSA kernel: small tables packed for shared-memory staging
@@ -809,10 +815,12 @@ int orlg_enable_stats(orlg_env *env, double *stats_dev) {
     if (env->wide || p.E > 128) return fail(ORLG_E_UNSUPPORTED, "statistics path handles <= 32 links and <= 128 slots");
     if (!p.link_util) {
         const size_t n = (size_t)p.n;
+        env->alloc_is_state = true;
         int rc = dev_alloc(env, &p.link_util, (size_t)p.E * n);
         if (!rc) rc = dev_alloc(env, &p.link_comp, (size_t)p.E * n);
         if (!rc) rc = dev_alloc(env, &p.link_last, (size_t)p.E * n);
         if (!rc) rc = dev_alloc(env, &p.sum_nh, n);
+        env->alloc_is_state = false;
         if (rc) return rc;
     }
     p.stats = 1;
@@ -1132,6 +1140,48 @@ int orlg_policy_destroy(orlg_policy *pol) {
     DeviceGuard guard(pol->device);
     cudaFree(pol->w_dev); cudaFree(pol->b_dev);
     delete pol;
+    return ORLG_OK;
+}
+
+// ---------------------------------------------------------------- checkpoint / resume
+int64_t orlg_state_save_bytes(const orlg_env *env) {
+    int64_t b = 16;                                   // header: lockstep request index, number of arrays
+    for (const auto &a : env->state_allocs) b += (int64_t)((a.second + 15) / 16 * 16);
+    return b;
+}
+
+int orlg_state_save(orlg_env *env, void *buf_dev, orlg_stream stream) {
+    if (!env || !buf_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
+    DeviceGuard guard(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = ensure_canonical(env, s);               // the saved form is the canonical one
+    if (rc) return rc;
+    const unsigned long long hdr[2] = {env->p.lockstep_ridx, (unsigned long long)env->state_allocs.size()};
+    CUDA_OK(cudaMemcpyAsync(buf_dev, hdr, 16, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaStreamSynchronize(s));               // hdr lives on this stack frame
+    size_t off = 16;
+    for (const auto &a : env->state_allocs) {
+        CUDA_OK(cudaMemcpyAsync(reinterpret_cast<unsigned char *>(buf_dev) + off, a.first, a.second, cudaMemcpyDeviceToDevice, s));
+        off += (a.second + 15) / 16 * 16;
+    }
+    return ORLG_OK;
+}
+
+int orlg_state_load(orlg_env *env, const void *buf_dev, orlg_stream stream) {
+    if (!env || !buf_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
+    DeviceGuard guard(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long hdr[2] = {0, 0};
+    CUDA_OK(cudaMemcpyAsync(hdr, buf_dev, 16, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    if (hdr[1] != env->state_allocs.size()) return fail(ORLG_E_INVALID, "checkpoint does not match this handle (different configuration)");
+    size_t off = 16;
+    for (const auto &a : env->state_allocs) {
+        CUDA_OK(cudaMemcpyAsync(a.first, reinterpret_cast<const unsigned char *>(buf_dev) + off, a.second, cudaMemcpyDeviceToDevice, s));
+        off += (a.second + 15) / 16 * 16;
+    }
+    env->p.lockstep_ridx = (unsigned)hdr[0];
+    env->ro_valid = false;                           // the loaded tables are canonical
     return ORLG_OK;
 }
 

@@ -89,6 +89,10 @@ def lib():
     L.orlg_action_hist_dim.argtypes = [vp]
     L.orlg_action_probability.argtypes = [vp, vp, vp]
     L.orlg_rollout.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    L.orlg_state_save_bytes.argtypes = [vp]
+    L.orlg_state_save_bytes.restype = i64
+    L.orlg_state_save.argtypes = [vp, vp, vp]
+    L.orlg_state_load.argtypes = [vp, vp, vp]
     L.orlg_policy_create.argtypes = [i32, i32, i32, i32, i32, vp, vp, C.POINTER(vp)]
     L.orlg_policy_act.argtypes = [vp, vp, i32, vp, vp, vp]
     L.orlg_policy_destroy.argtypes = [vp]
@@ -109,4 +113,4 @@ EXPORTED = ["orlg_create", "orlg_destroy", "orlg_last_error", "orlg_version", "o
             "orlg_observation", "orlg_observation_int", "orlg_heuristic", "orlg_random_actions", "orlg_get_counters",
             "orlg_get_requests", "orlg_export_state", "orlg_error_flags", "orlg_reduce_counters", "orlg_enable_stats",
             "orlg_num_bit_rates", "orlg_bit_rate_blocking", "orlg_matrix_obs_dim", "orlg_matrix_observation",
-            "orlg_path_only_first_fit", "orlg_rollout", "orlg_policy_create", "orlg_policy_act", "orlg_policy_destroy", "orlg_rollout_packed", "orlg_expand_packed", "orlg_rollout_host", "orlg_action_hist_dim", "orlg_action_probability"]
+            "orlg_path_only_first_fit", "orlg_rollout", "orlg_state_save_bytes", "orlg_state_save", "orlg_state_load", "orlg_policy_create", "orlg_policy_act", "orlg_policy_destroy", "orlg_rollout_packed", "orlg_expand_packed", "orlg_rollout_host", "orlg_action_hist_dim", "orlg_action_probability"]

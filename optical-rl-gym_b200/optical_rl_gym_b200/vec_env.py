@@ -471,6 +471,26 @@ class OpticalVecEnv:
             nat.check(rc)
         return out
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self):
+        """Everything needed to continue this batch later: the native state (one opaque uint8 CUDA tensor) + the request-stream
+        key.  ``load_state_dict`` restores it into an env constructed with the same arguments."""
+        nbytes = int(self._lib.orlg_state_save_bytes(self._h))
+        blob = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self._dev_index):
+            nat.check(self._lib.orlg_state_save(self._h, _ptr(blob), self._stream()))
+        return {"native": blob, "seed": self.rand_seed, "env_id": self.env_id, "num_envs": self.num_envs}
+
+    def load_state_dict(self, sd):
+        if sd["env_id"] != self.env_id or sd["num_envs"] != self.num_envs:
+            raise ValueError("checkpoint of %s x %d does not fit %s x %d" % (sd["env_id"], sd["num_envs"], self.env_id, self.num_envs))
+        blob = sd["native"].to(self.device).contiguous()
+        if blob.numel() != int(self._lib.orlg_state_save_bytes(self._h)):
+            raise ValueError("checkpoint was written by a differently configured env")
+        with torch.cuda.device(self._dev_index):
+            nat.check(self._lib.orlg_state_load(self._h, _ptr(blob), self._stream()))
+        self.seed(sd["seed"])
+
     # ------------------------------------------------------------------ introspection
     @property
     def decisions(self):

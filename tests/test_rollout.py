@@ -297,3 +297,29 @@ def test_evaluate_heuristic_matches_the_reference_loop(kind, env_args, heuristic
     mean, std = evaluate_heuristic(OpticalVecEnv(kind, n, tables, traffic="philox", seed=seed, **env_args), heuristic, n_eval_episodes=episodes)
     assert abs(mean - rewards.mean().item()) < 1e-9 and abs(std - rewards.std(unbiased=False).item()) < 1e-9
     env.close()
+
+
+@pytest.mark.parametrize("kind,env_args,policy", [("DeepRMSA-v0", dict(episode_length=40), "random"),
+                                                  ("RMSA-v0", _RMSA, "sap_ff"), ("RWA-v0", _RWA, "sap_ff")])
+def test_state_dict_round_trip_continues_bit_for_bit(kind, env_args, policy):
+    """state_dict() after a mix of rollouts and steps, load_state_dict() into a FRESH env (also through a CPU copy): both then
+    produce identical trajectories and end in the same state."""
+    from optical_rl_gym_b200 import OpticalVecEnv
+
+    tables = helpers.golden_tables()
+    kw = dict(traffic="philox", seed=5, **env_args)
+    a = OpticalVecEnv(kind, 300, tables, **kw)
+    a.rollout(70, policy)
+    for _ in range(3):
+        a.step(a.sample_actions())
+    a.rollout(11, policy)                       # the checkpoint is taken while the events sit in the rollout-private storage
+    sd = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in a.state_dict().items()}
+    b = OpticalVecEnv(kind, 300, tables, **dict(kw, seed=999))
+    b.rollout(5, policy)
+    b.load_state_dict(sd)
+    _final_state_equal(a, b)
+    ra, rb = a.rollout(90, policy), b.rollout(90, policy)
+    for x, y in zip(ra, rb):
+        assert (x is None and y is None) or torch.equal(x, y)
+    _final_state_equal(a, b)
+    a.close(); b.close()
