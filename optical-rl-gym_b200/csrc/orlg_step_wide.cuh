@@ -113,34 +113,67 @@ __device__ __forceinline__ int wb_run_length(const WBits<NWV> &a, int start) {
     return (pos < 0 ? 128 * NWV : pos) - start;
 }
 
-// get_available_slots (rmsa_env.py:638-649): AND of the path's link masks
+// get_available_slots (rmsa_env.py:638-649): AND of the path's link masks.  Four hops at a time: the four link indices are
+// fetched together, then all 4 x NWV mask words are requested before any is used (2 dependent round trips per 4 hops instead
+// of 2 per hop: the kernel is latency-bound, every lane walks its own path).
 template <int NWV>
 __device__ __forceinline__ WBits<NWV> wide_path_free(const Params &p, int env, int row, int core) {
     WBits<NWV> a = wb_fill<NWV>(0xFFFFFFFFu);
-    for (int h = p.path_link_ptr[row]; h < p.path_link_ptr[row + 1]; h++) {
-        const uint4 *m = p.masks + ((size_t)(core * p.E + p.path_links16[h]) * NWV) * p.n + env;
+    const int h0 = p.path_link_ptr[row], h1 = p.path_link_ptr[row + 1];
+    const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    for (int h = h0; h < h1; h += 4) {
+        int l[4];
 #pragma unroll
-        for (int v = 0; v < NWV; v++) {
-            const uint4 x = m[(size_t)v * p.n];
-            a.w[4 * v] &= x.x; a.w[4 * v + 1] &= x.y; a.w[4 * v + 2] &= x.z; a.w[4 * v + 3] &= x.w;
+        for (int i = 0; i < 4; i++) l[i] = h + i < h1 ? (int)p.path_links16[h + i] : -1;
+        uint4 x[4][NWV];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint4 *m = p.masks + ((size_t)(core * p.E + max(l[i], 0)) * NWV) * p.n + env;
+#pragma unroll
+            for (int v = 0; v < NWV; v++) x[i][v] = l[i] >= 0 ? m[(size_t)v * p.n] : ones;
         }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int v = 0; v < NWV; v++) {
+                a.w[4 * v] &= x[i][v].x; a.w[4 * v + 1] &= x[i][v].y; a.w[4 * v + 2] &= x[i][v].z; a.w[4 * v + 3] &= x[i][v].w;
+            }
     }
     return a;
 }
 
-// _provision_path / _release_path on the masks
+// _provision_path / _release_path on the masks (only the word groups the slot range touches; loads of 4 hops in flight)
 template <int NWV>
 __device__ __forceinline__ void wide_path_update(const Params &p, int env, int row, int core, int start, int n, bool set) {
     const WBits<NWV> rm = wb_range<NWV>(start, start + n);
-    for (int h = p.path_link_ptr[row]; h < p.path_link_ptr[row + 1]; h++) {
-        uint4 *m = p.masks + ((size_t)(core * p.E + p.path_links16[h]) * NWV) * p.n + env;
+    bool touch[NWV];
 #pragma unroll
-        for (int v = 0; v < NWV; v++) {
-            if ((rm.w[4 * v] | rm.w[4 * v + 1] | rm.w[4 * v + 2] | rm.w[4 * v + 3]) == 0u) continue;
-            uint4 x = m[(size_t)v * p.n];
-            if (set) { x.x |= rm.w[4 * v]; x.y |= rm.w[4 * v + 1]; x.z |= rm.w[4 * v + 2]; x.w |= rm.w[4 * v + 3]; }
-            else { x.x &= ~rm.w[4 * v]; x.y &= ~rm.w[4 * v + 1]; x.z &= ~rm.w[4 * v + 2]; x.w &= ~rm.w[4 * v + 3]; }
-            m[(size_t)v * p.n] = x;
+    for (int v = 0; v < NWV; v++) touch[v] = (rm.w[4 * v] | rm.w[4 * v + 1] | rm.w[4 * v + 2] | rm.w[4 * v + 3]) != 0u;
+    const int h0 = p.path_link_ptr[row], h1 = p.path_link_ptr[row + 1];
+    for (int h = h0; h < h1; h += 4) {
+        int l[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) l[i] = h + i < h1 ? (int)p.path_links16[h + i] : -1;
+        uint4 x[4][NWV];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint4 *m = p.masks + ((size_t)(core * p.E + max(l[i], 0)) * NWV) * p.n + env;
+#pragma unroll
+            for (int v = 0; v < NWV; v++)
+                if (l[i] >= 0 && touch[v]) x[i][v] = m[(size_t)v * p.n];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint4 *m = p.masks + ((size_t)(core * p.E + max(l[i], 0)) * NWV) * p.n + env;
+#pragma unroll
+            for (int v = 0; v < NWV; v++) {
+                if (l[i] >= 0 && touch[v]) {
+                    uint4 y = x[i][v];
+                    if (set) { y.x |= rm.w[4 * v]; y.y |= rm.w[4 * v + 1]; y.z |= rm.w[4 * v + 2]; y.w |= rm.w[4 * v + 3]; }
+                    else { y.x &= ~rm.w[4 * v]; y.y &= ~rm.w[4 * v + 1]; y.z &= ~rm.w[4 * v + 2]; y.w &= ~rm.w[4 * v + 3]; }
+                    m[(size_t)v * p.n] = y;
+                }
+            }
         }
     }
 }
