@@ -372,6 +372,8 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     p.seed = cfg->seed; p.env_id_base = cfg->env_id_base;
     p.mean_holding = cfg->mean_holding; p.mean_iat = cfg->mean_iat;
     p.obs_dim = cfg->kind == ORLG_DEEPRMSA ? 1 + 2 * p.N + (2 * J + 3) * p.k : 0;
+    p.node_top_step = 1;                   // highest power of two <= N - 1: binary search over the node CDF
+    while (p.node_top_step * 2 <= p.N - 1) p.node_top_step *= 2;
     p.cand_stride = ((p.k * J + 7) / 8) * 8;
     p.nwv = wide ? (p.S + 127) / 128 : 1;
     env->km = p.k <= 5 ? 5 : KMAX;
@@ -562,8 +564,6 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
             if (per_thread < (size_t)p.E * 16) per_thread = (size_t)p.E * 16;
             p.warp_area_bytes = (int)((per_thread * 32 + 127) / 128 * 128);
             env->fast_smem = blob.size() + (size_t)(FAST_THREADS / 32) * p.warp_area_bytes + 8 * (FAST_THREADS / 32 + 1);   // + per-warp mbarriers + the table barrier
-            p.node_top_step = 1;
-            while (p.node_top_step * 2 <= p.N - 1) p.node_top_step *= 2;
             cudaError_t ea = cudaSuccess;
             if (env->fast_smem > 48 * 1024) {
                 ea = cudaFuncSetAttribute(deeprmsa_fast_kernel<22, 5, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->fast_smem);

@@ -107,13 +107,6 @@ __device__ __forceinline__ Bits bits_shr1(const Bits &a) {
     return r;
 }
 
-// first i in [0, n-1] with r < thr[i] (n-1 if none): same result as the linear scan of pick_thr
-__device__ __forceinline__ int pick_thr_bsearch(const unsigned *thr, int n, int top_step, unsigned r) {
-    int i = 0;
-    for (int step = top_step; step > 0; step >>= 1)
-        if (i + step <= n - 1 && r >= thr[i + step - 1]) i += step;
-    return i;
-}
 
 // Optional per-phase cycle accounting (build with -DORLG_PHASE_TIMING; read with orlg_debug_phase_cycles):
 // sum over warps of the cycles between consecutive marks.  Not part of the product build.

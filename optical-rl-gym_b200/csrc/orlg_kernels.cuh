@@ -155,6 +155,14 @@ __device__ __forceinline__ int pick_thr(const unsigned *thr, int n, unsigned r) 
     return i;
 }
 
+// first i in [0, n-1] with r < thr[i] (n-1 if none): same result as the linear scan of pick_thr (thr is non-decreasing)
+__device__ __forceinline__ int pick_thr_bsearch(const unsigned *thr, int n, int top_step, unsigned r) {
+    int i = 0;
+    for (int step = top_step; step > 0; step >>= 1)
+        if (i + step <= n - 1 && r >= thr[i + step - 1]) i += step;
+    return i;
+}
+
 // _next_service's draws (rmsa_env.py:548-561) from the counter-based generator
 __device__ __forceinline__ void philox_request(const Params &p, const unsigned *node_thr, int env, unsigned ridx, double now,
                                                double &arrival, double &holding, int &src, int &dst, int &br) {
@@ -164,15 +172,13 @@ __device__ __forceinline__ void philox_request(const Params &p, const unsigned *
     arrival = __dadd_rn(now, __dmul_rn(neg_log_u32(c[0]), p.mean_iat));
     holding = __dmul_rn(neg_log_u32(c[1]), p.mean_holding);
     int n = p.N;
-    src = pick_thr(node_thr, n, c[2]);
+    src = pick_thr_bsearch(node_thr, n, p.node_top_step, c[2]);        // binary search: up to 255 nodes, every lane its own draw
     unsigned long long lo = src ? node_thr[src - 1] : 0u;
     unsigned long long hi = (src == n - 1) ? 4294967296ULL : (unsigned long long)node_thr[src];
     unsigned long long mass = hi - lo;
     unsigned long long tt = ((unsigned long long)c[3] * (4294967296ULL - mass)) >> 32;
     if (tt >= lo) tt += mass;
-    dst = n - 1;
-    for (int i = 0; i < n - 1; i++)
-        if (tt < (unsigned long long)node_thr[i]) { dst = i; break; }
+    dst = pick_thr_bsearch(node_thr, n, p.node_top_step, (unsigned)tt);
     if (dst == src) dst = (src + 1) % n;
     br = 0;
     if (p.kind != ORLG_RWA) {
