@@ -19,6 +19,8 @@ import sys
 import threading
 import time
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "optical-rl-gym_b200")):
     if p not in sys.path:
@@ -261,6 +263,7 @@ def run_secondary(args):
         "envs_with_errors": int((env.error_flags() != 0).sum()), "state_MB": env.state_bytes / 1e6}))
 
 
+E2E_CHUNK = int(os.environ.get("ORLG_E2E_CHUNK", "2"))   # steps per pipeline stage of the end-to-end leg (orlg_rollout_host)
 ROLLOUT_CHUNK = 256      # steps per orlg_rollout launch (bounds the [chunk, N, 54] float32 output buffer: 3.6 GB)
 
 
@@ -362,7 +365,7 @@ def main():
 
     # ---- end to end through the public API with HOST buffers (pinned): H2D actions, step, D2H obs/reward/done.
     # Every rank runs it at the same time (they share the host's PCIe / memory), max over ranks.
-    e2e_result = None
+    e2e_result = e2e_sync = None
     actions = torch.empty((n, 1), dtype=torch.int32, device=dev)
     env.sample_actions(out=actions)
     if not args.no_e2e:
@@ -391,11 +394,49 @@ def main():
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e_result = {"value": n * world * k_e2e / float(dt.item()), "unit": "env-steps/s",
-                      "h2d_bytes_per_step": h_act.numel() * 4 * world,
-                      "d2h_bytes_per_step": (h_obs.numel() * 4 + h_rew.numel() * 4 + h_done.numel()) * world,
-                      "steps": k_e2e, "n_gpus": world,
-                      "note": "VecEnv.step with pinned host buffers on every rank concurrently, synchronised every step"}
+        e2e_sync = {"value": n * world * k_e2e / float(dt.item()), "unit": "env-steps/s",
+                    "h2d_bytes_per_step": h_act.numel() * 4 * world,
+                    "d2h_bytes_per_step": (h_obs.numel() * 4 + h_rew.numel() * 4 + h_done.numel()) * world,
+                    "steps": k_e2e, "n_gpus": world,
+                    "note": "VecEnv.step with pinned host buffers on every rank concurrently, synchronised every step "
+                            "(float32 rows cross PCIe: 14.5 MB per step and GPU)"}
+        del h_obs, h_rew, h_done
+
+        # ---- the headline end-to-end number: the same K-step rollout through the C ABI with HOST buffers on both sides
+        # (orlg_rollout_host, ORLG_POLICY_REPLAY).  Input: the actions of every step, drawn beforehand on the host (the uniform
+        # random policy does not look at observations), in pinned memory, copied to the device chunk by chunk.  Output: every
+        # step's float32 observation row, reward and done in host memory.  Inside the call the device runs chunk c + 1 while
+        # chunk c's 32-byte step records cross PCIe and the host threads expand them to the float32 rows (bit-identical to
+        # what orlg_rollout writes on the device).  Wall clock around the calls, every rank at the same time, max over ranks.
+        k_h = max(20, min(K, 40))
+        threads = max(1, (os.cpu_count() or 1) // world)
+        rng = np.random.default_rng(1234 + rank)
+        ha_t = torch.from_numpy(rng.integers(0, env.k_paths * env.j + 1, size=(k_h, n), dtype=np.int32)).pin_memory()
+        ha = ha_t.numpy()
+        ho = np.zeros((k_h, n, env.obs_dim), np.float32)
+        hr = np.zeros((k_h, n), np.float32)
+        hd = np.zeros((k_h, n), np.uint8)
+        for _ in range(2):
+            env.rollout_host(k_h, "replay", obs=ho, reward=hr, done=hd, actions=ha, chunk=E2E_CHUNK, threads=threads)
+        if world > 1:
+            dist.barrier()
+        reps_h = 3
+        t0 = time.perf_counter()
+        for _ in range(reps_h):
+            env.rollout_host(k_h, "replay", obs=ho, reward=hr, done=hd, actions=ha, chunk=E2E_CHUNK, threads=threads)
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_result = {"value": n * world * k_h * reps_h / float(dt.item()), "unit": "env-steps/s",
+                      "h2d_bytes_per_step": n * 4 * world, "d2h_bytes_per_step": n * 32 * world,
+                      "host_bytes_delivered_per_step": n * (env.obs_dim * 4 + 5) * world,
+                      "steps": k_h * reps_h, "n_gpus": world, "host_threads_per_rank": threads, "chunk_steps": E2E_CHUNK,
+                      "accepted_in_sample": float((hr > 0).mean()),
+                      "note": "orlg_rollout_host(ORLG_POLICY_REPLAY): actions [steps, N] int32 from pinned host memory (H2D per "
+                              "chunk), float32 observation rows + reward + done of every step delivered in host memory; the step "
+                              "records cross PCIe packed (32 B per env-step) and are expanded by the library's host threads; "
+                              "wall clock, every rank concurrently, max over ranks"}
+        del ho, hr, hd
 
     # ---- the same K steps with the results delivered to the HOST as packed 32-byte records (orlg_rollout_packed: the
     # integer pre-image of the observation + request + action / accepted / done; orlg_expand_packed decodes them).  The
@@ -527,7 +568,7 @@ def main():
                                                                             env.state_bytes / 1e6),
                        "parallelism": "env-sharded x%d, no data-path collective" % world},
             "timing": {"reps": args.reps, "rep_ms": rep_ms, "stat": "median of the repetitions (each: max over ranks)"},
-            "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_python": cpu_py, "e2e": e2e_result, "e2e_packed": e2e_packed,
+            "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_python": cpu_py, "e2e": e2e_result, "e2e_step_sync": e2e_sync, "e2e_packed": e2e_packed,
             "gpu_launches": launches,
             "clocks": sampler.summary(), "step_path_ms_per_step": step_path_ms, "ppo_policy_variant": ppo,
             "accept_rate": 1.0 - stats["service_blocking_rate"], "envs_with_errors": stats["envs_with_errors"],

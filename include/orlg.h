@@ -166,8 +166,10 @@ int orlg_rollout_packed(orlg_env *env, int steps, int policy, uint32_t *packed_d
  * may be NULL) -- using `threads` host threads (<= 0: all cores). */
 int orlg_expand_packed(const uint32_t *packed_host, int64_t rows, int num_nodes, int num_slots, float *obs_host, float *reward_host,
                        uint8_t *done_host, int32_t *action_host, int threads);
-/* orlg_rollout with HOST result buffers (pageable or pinned): the steps run in chunks on the device while the previous chunk's
- * records cross PCIe and are expanded by the host threads.  obs_host f32 [steps, num_envs, obs_dim] etc.; any may be NULL. */
+/* orlg_rollout with HOST buffers (pageable or pinned): the steps run in chunks on the device while the previous chunk's
+ * records cross PCIe and are expanded by a persistent pool of `threads` host threads (<= 0: all cores).  obs_host f32
+ * [steps, num_envs, obs_dim] etc.; any output may be NULL.  With ORLG_POLICY_REPLAY actions_host is the INPUT: the action of
+ * every env at every step, copied to the device chunk by chunk ahead of the kernel that consumes it. */
 int orlg_rollout_host(orlg_env *env, int steps, int policy, float *obs_host, float *reward_host, uint8_t *done_host,
                       int32_t *actions_host, int chunk_steps, int threads, orlg_stream stream);
 

@@ -1,8 +1,14 @@
 // orlg_api.cu -- the C ABI (include/orlg.h) on top of the step kernels.  Links cudart only.
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <emmintrin.h>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -59,6 +65,8 @@ struct orlg_env {
     uint4 *ro_pk_host[2] = {nullptr, nullptr};
     size_t ro_pk_rows = 0;                     // rows (env-steps) each buffer holds
     cudaEvent_t ro_pk_ev[2] = {nullptr, nullptr};
+    int32_t *ro_act_dev[2] = {nullptr, nullptr};   // ORLG_POLICY_REPLAY: the host's action chunks on the device
+    size_t ro_act_rows = 0;
     int *ro_actions = nullptr;    // [n, action_dim] scratch of the generic (kernel-per-step) rollout
 };
 
@@ -192,12 +200,12 @@ void launch_fast(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s
 
 template <int KIND>
 void launch_wide_kind(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s) {
-    const int blocks = (env->p.n + 127) / 128;
+    const int blocks = (env->p.n + ORLG_WIDE_THREADS - 1) / ORLG_WIDE_THREADS;
     switch (env->p.nwv) {
-    case 1: step_wide_kernel<KIND, 1><<<blocks, 128, 0, s>>>(env->p, io, mode); break;
-    case 2: step_wide_kernel<KIND, 2><<<blocks, 128, 0, s>>>(env->p, io, mode); break;
-    case 3: step_wide_kernel<KIND, 3><<<blocks, 128, 0, s>>>(env->p, io, mode); break;
-    default: step_wide_kernel<KIND, 4><<<blocks, 128, 0, s>>>(env->p, io, mode); break;
+    case 1: step_wide_kernel<KIND, 1><<<blocks, ORLG_WIDE_THREADS, 0, s>>>(env->p, io, mode); break;
+    case 2: step_wide_kernel<KIND, 2><<<blocks, ORLG_WIDE_THREADS, 0, s>>>(env->p, io, mode); break;
+    case 3: step_wide_kernel<KIND, 3><<<blocks, ORLG_WIDE_THREADS, 0, s>>>(env->p, io, mode); break;
+    default: step_wide_kernel<KIND, 4><<<blocks, ORLG_WIDE_THREADS, 0, s>>>(env->p, io, mode); break;
     }
 }
 
@@ -376,6 +384,7 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     while (p.node_top_step * 2 <= p.N - 1) p.node_top_step *= 2;
     p.cand_stride = ((p.k * J + 7) / 8) * 8;
     p.nwv = wide ? (p.S + 127) / 128 : 1;
+    p.wstride = wide ? (p.nwv == 3 ? 4 : p.nwv) : 0;      // 3-word entries padded to 64 bytes: one DRAM burst per (env, core, link)
     env->km = p.k <= 5 ? 5 : KMAX;
     env->obs_smem = (size_t)STEP_THREADS * p.obs_dim * (p.obs_f64 ? 8 : 4);
     if (env->obs_smem > 200 * 1024) { delete env; return fail(ORLG_E_UNSUPPORTED, "observation too large for the staging tile"); }
@@ -478,7 +487,7 @@ int orlg_create(const orlg_config *cfg, const orlg_tables *t, int device, orlg_e
     // ---- state
     env->alloc_is_state = true;
     const size_t n = (size_t)p.n;
-    if (!rc) rc = dev_alloc(env, &p.masks, (size_t)C * p.E * p.nwv * n);
+    if (!rc) rc = dev_alloc(env, &p.masks, (size_t)C * p.E * (wide ? p.wstride : p.nwv) * n);
     if (!rc) rc = dev_alloc(env, &p.now, n);
     if (!rc) rc = dev_alloc(env, &p.cur_hold, n);
     if (!rc) rc = dev_alloc(env, &p.cur_req, n);
@@ -614,6 +623,7 @@ int orlg_destroy(orlg_env *env) {
         if (env->ro_pk_dev[i]) cudaFree(env->ro_pk_dev[i]);
         if (env->ro_pk_host[i]) cudaFreeHost(env->ro_pk_host[i]);
         if (env->ro_pk_ev[i]) cudaEventDestroy(env->ro_pk_ev[i]);
+        if (env->ro_act_dev[i]) cudaFree(env->ro_act_dev[i]);
     }
     delete env;
     return ORLG_OK;
@@ -647,6 +657,7 @@ int orlg_reset(orlg_env *env, int full, void *obs_dev, orlg_stream stream) {
     if (env->p.traffic == ORLG_TRAFFIC_TRACE && env->p.trace == nullptr) return fail(ORLG_E_INVALID, "trace traffic selected but orlg_set_trace was not called");
     StepIO io;
     std::memset(&io, 0, sizeof(io));
+    io.policy = -1;
     io.obs = env->p.obs_dim ? obs_dev : nullptr;
     if (full) env->ro_valid = false;           // everything is reset below: nothing to convert back
     else {
@@ -662,15 +673,16 @@ int orlg_reset(orlg_env *env, int full, void *obs_dev, orlg_stream stream) {
     return rc;
 }
 
-int orlg_step(orlg_env *env, const int32_t *actions_dev, void *obs_dev, float *reward_dev, uint8_t *done_dev,
-              int32_t *decision_dev, int64_t *info_dev, orlg_stream stream) {
-    if (!env || !actions_dev) return fail(ORLG_E_INVALID, "null handle or actions");
-    DeviceGuard guard(env->device);
+// orlg_step; fused_policy >= 0 (wide kernels only): the heuristic is evaluated inside the step kernel, actions_dev receives it
+static int step_impl(orlg_env *env, const int32_t *actions_dev, int fused_policy, int32_t *actions_out, void *obs_dev, float *reward_dev,
+                     uint8_t *done_dev, int32_t *decision_dev, int64_t *info_dev, orlg_stream stream) {
     {
         int rc0 = ensure_canonical(env, (cudaStream_t)stream);
         if (rc0) return rc0;
     }
     StepIO io;
+    io.policy = fused_policy;
+    io.actions_out = actions_out;
     io.actions = actions_dev;
     io.obs = env->p.obs_dim ? obs_dev : nullptr;
     io.reward = reward_dev;
@@ -683,12 +695,20 @@ int orlg_step(orlg_env *env, const int32_t *actions_dev, void *obs_dev, float *r
     return rc;
 }
 
+int orlg_step(orlg_env *env, const int32_t *actions_dev, void *obs_dev, float *reward_dev, uint8_t *done_dev,
+              int32_t *decision_dev, int64_t *info_dev, orlg_stream stream) {
+    if (!env || !actions_dev) return fail(ORLG_E_INVALID, "null handle or actions");
+    DeviceGuard guard(env->device);
+    return step_impl(env, actions_dev, -1, nullptr, obs_dev, reward_dev, done_dev, decision_dev, info_dev, stream);
+}
+
 int orlg_observation(orlg_env *env, void *obs_dev, orlg_stream stream) {
     if (!env || !obs_dev) return fail(ORLG_E_INVALID, "null handle or buffer");
     DeviceGuard guard(env->device);
     if (!env->p.obs_dim) return fail(ORLG_E_UNSUPPORTED, "this env kind has a dict observation (no tensor)");
     StepIO io;
     std::memset(&io, 0, sizeof(io));
+    io.policy = -1;
     io.obs = obs_dev;
     return launch_step(env, io, MODE_OBSERVE, (cudaStream_t)stream);
 }
@@ -699,6 +719,7 @@ int orlg_observation_int(orlg_env *env, int32_t *out_dev, orlg_stream stream) {
     if (!env->p.obs_dim) return fail(ORLG_E_UNSUPPORTED, "this env kind has a dict observation (no tensor)");
     StepIO io;
     std::memset(&io, 0, sizeof(io));
+    io.policy = -1;
     io.obs_int = out_dev;
     return launch_step(env, io, MODE_OBSERVE, (cudaStream_t)stream);
 }
@@ -943,8 +964,19 @@ static int rollout_impl(orlg_env *env, int steps, int policy, void *obs_dev, flo
         if (rc) return rc;
     }
     const size_t obs_row = (size_t)p.obs_dim * (p.obs_f64 ? 8 : 4);
+    // wide kernels: the heuristic runs in the step kernel's prologue (one launch per step; the chosen path's masks are read once)
+    bool fuse = env->wide && policy >= 0 && !std::getenv("ORLG_NO_FUSED_HEURISTIC");
+    if (fuse && ((p.kind == ORLG_RMSA && policy == ORLG_HEUR_SAP_LF) || (p.kind == ORLG_DEEPRMSA && policy > ORLG_HEUR_SAP_FF))) fuse = false;
     for (int t = 0; t < steps; t++) {
         int32_t *a = actions_dev ? actions_dev + (size_t)t * p.n * adim : env->ro_actions;
+        if (fuse) {
+            int rc = step_impl(env, nullptr, policy, actions_dev ? a : nullptr,
+                               (obs_dev && p.obs_dim) ? reinterpret_cast<unsigned char *>(obs_dev) + (size_t)t * p.n * obs_row : nullptr,
+                               reward_dev ? reward_dev + (size_t)t * p.n : nullptr, done_dev ? done_dev + (size_t)t * p.n : nullptr,
+                               nullptr, nullptr, stream);
+            if (rc) return rc;
+            continue;
+        }
         int rc = policy == ORLG_POLICY_REPLAY ? ORLG_OK
                  : (policy == ORLG_POLICY_RANDOM ? orlg_random_actions(env, a, stream) : orlg_heuristic(env, policy, a, stream));
         if (rc) return rc;
@@ -967,52 +999,154 @@ int orlg_rollout_packed(orlg_env *env, int steps, int policy, uint32_t *packed_d
     return rollout_impl(env, steps, policy, nullptr, nullptr, nullptr, actions_dev, packed_dev, stream);
 }
 
-// one packed record -> what env.step returned (same float expressions as the device tables built in orlg_create)
-static void expand_rows(const uint32_t *pk, int64_t r0, int64_t r1, int N, int S, float *obs, float *reward, uint8_t *done, int32_t *action) {
-    const int D = 1 + 2 * N + 25;
-    for (int64_t r = r0; r < r1; r++) {
-        const uint32_t *w = pk + r * 8;
-        const uint32_t q5 = w[5];
+// ---------------------------------------------------------------- host side of the packed records (no CUDA below this line)
+// A persistent pool of host threads: orlg_expand_packed is called once per chunk of a pipelined rollout (every ~0.3 ms),
+// so creating threads per call would cost more than the work.  Blocks of rows are handed out through an atomic counter
+// (the caller's thread works too), which also balances the load when several ranks share the host's cores.
+namespace {
+struct HostPool {
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::vector<std::thread> workers;
+    std::function<void(int64_t)> fn;
+    int64_t nblocks = 0;
+    std::atomic<int64_t> next{0};
+    int want = 0, active = 0;            // workers allowed into this job / still inside it
+    uint64_t generation = 0;
+    bool stop = false;
+
+    void drain() {
+        for (;;) {
+            const int64_t b = next.fetch_add(1, std::memory_order_relaxed);
+            if (b >= nblocks) return;
+            fn(b);
+        }
+    }
+    void worker(int id) {
+        uint64_t seen = 0;
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv_work.wait(lk, [&] { return stop || generation != seen; });
+            if (stop) return;
+            seen = generation;
+            if (id >= want) continue;
+            lk.unlock();
+            drain();
+            lk.lock();
+            if (--active == 0) cv_done.notify_one();
+        }
+    }
+    void run(int threads, int64_t blocks, std::function<void(int64_t)> f) {
+        if (threads <= 1 || blocks <= 1) { for (int64_t b = 0; b < blocks; b++) f(b); return; }
+        std::unique_lock<std::mutex> lk(mu);
+        while ((int)workers.size() < threads - 1) { const int id = (int)workers.size(); workers.emplace_back(&HostPool::worker, this, id); }
+        fn = std::move(f); nblocks = blocks; next.store(0); want = threads - 1; active = threads - 1; generation++;
+        lk.unlock();
+        cv_work.notify_all();
+        drain();
+        lk.lock();
+        cv_done.wait(lk, [&] { return active == 0; });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv_work.notify_all();
+        for (auto &t : workers) t.join();
+    }
+};
+HostPool g_pool;                         // one job at a time (g_pool_mu); handles on different threads serialise here
+std::mutex g_pool_mu;
+
+// Float tables of the observation features, indexed by PAIRS of packed fields so that a candidate path costs three look-ups:
+// the same float32 expressions as the device tables built in orlg_create (hence bit-identical rows).  192 KB, L2-resident.
+struct F2 { float a, b; };
+struct ExpandTables {
+    int S = -1;
+    std::vector<F2> sl;      // [start | length << 7] -> (start, length) features; (-1, -1) when start == 127 (no block)
+    std::vector<F2> tr;      // [free slots | free runs << 7] -> (free-slot feature, average-run feature or -1)
+    float need[32], rate[256];
+};
+const ExpandTables &expand_tables(int S) {
+    static std::mutex mu;
+    static std::vector<std::unique_ptr<ExpandTables>> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto &t : cache) if (t->S == S) return *t;
+    std::unique_ptr<ExpandTables> t(new ExpandTables);
+    t->S = S; t->sl.resize(1 << 14); t->tr.resize(1 << 13);
+    for (int st = 0; st < 128; st++)
+        for (int ln = 0; ln < 128; ln++)
+            t->sl[st | ln << 7] = st != 127 ? F2{(float)(2 * st - S) / (float)S, (float)(ln - 8) * 0.125f} : F2{-1.0f, -1.0f};
+    for (int total = 0; total < 128; total++)
+        for (int runs = 0; runs < 64; runs++)
+            t->tr[total | runs << 7] = F2{(float)(2 * total - S) / (float)S, runs > 0 ? (float)(total - 4 * runs) * (1.0f / (float)(4 * runs)) : -1.0f};
+    for (int n = 0; n < 32; n++) t->need[n] = (float)(2 * n - 11) / 7.0f;
+    for (int b = 0; b < 256; b++) t->rate[b] = (float)b / 100.0f;
+    cache.push_back(std::move(t));
+    return *cache.back();
+}
+
+constexpr int EXP_BLOCK = 64;            // rows per staging block: 64 x (4 D) bytes is a multiple of 64 for every D
+
+// rows [r0, r1) of the packed records -> float32 rows.  A block is assembled in a cache-resident staging buffer and leaves
+// with non-temporal 16-byte stores when the destination allows it (no read-for-ownership of 14 MB per step).
+void expand_rows(const ExpandTables &tb, const uint32_t *pk, int64_t r0, int64_t r1, int N, float *obs, float *reward, uint8_t *done,
+                 int32_t *action) {
+    const int D = 1 + 2 * N + 25, H = 1 + 2 * N;
+    alignas(64) float stage[EXP_BLOCK * (1 + 2 * 255 + 25)];
+    const F2 *sl = tb.sl.data(), *tr = tb.tr.data();
+    for (int64_t b0 = r0; b0 < r1; b0 += EXP_BLOCK) {
+        const int nb = (int)(r1 - b0 < EXP_BLOCK ? r1 - b0 : EXP_BLOCK);
         if (obs) {
-            float *o = obs + r * D;
-            const int br = (int)(q5 & 0xffu), src = (int)((q5 >> 8) & 0xffu), dst = (int)((q5 >> 16) & 0xffu), npaths = (int)((q5 >> 24) & 0xfu);
-            for (int i = 0; i < 1 + 2 * N; i++) o[i] = 0.0f;
-            o[0] = (float)br / 100.0f;
-            o[1 + (src < dst ? src : dst)] = 1.0f;
-            o[1 + N + (src < dst ? dst : src)] = 1.0f;
-            for (int q = 0; q < 5; q++) {
-                const uint32_t f = w[q];
-                const int st = (int)(f & 127u), len = (int)((f >> 7) & 127u), total = (int)((f >> 14) & 127u);
-                const int runs = (int)((f >> 21) & 63u), n = (int)(f >> 27);
-                float *v = o + 1 + 2 * N + 5 * q;
-                v[0] = st != 127 ? (float)(2 * st - S) / (float)S : -1.0f;
-                v[1] = st != 127 ? (float)(len - 8) * 0.125f : -1.0f;
-                v[2] = q < npaths ? (float)(2 * n - 11) / 7.0f : -1.0f;
-                v[3] = q < npaths ? (float)(2 * total - S) / (float)S : -1.0f;
-                v[4] = runs > 0 ? (float)(total - 4 * runs) * (1.0f / (float)(4 * runs)) : -1.0f;
+            float *dst = obs + b0 * D;
+            const bool stream_out = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && ((size_t)nb * D) % 4 == 0;
+            float *out = stream_out ? stage : dst;
+            std::memset(out, 0, sizeof(float) * (size_t)nb * D);
+            for (int i = 0; i < nb; i++) {
+                const uint32_t *w = pk + (b0 + i) * 8;
+                float *o = out + (size_t)i * D;
+                const uint32_t q5 = w[5];
+                const int src = (int)((q5 >> 8) & 0xffu), dst_n = (int)((q5 >> 16) & 0xffu), npaths = (int)((q5 >> 24) & 0xfu);
+                o[0] = tb.rate[q5 & 0xffu];
+                o[1 + (src < dst_n ? src : dst_n)] = 1.0f;
+                o[1 + N + (src < dst_n ? dst_n : src)] = 1.0f;
+                float *v = o + H;
+                for (int q = 0; q < 5; q++, v += 5) {
+                    const uint32_t f = w[q];
+                    const F2 a = sl[f & 0x3fffu], b = tr[(f >> 14) & 0x1fffu];
+                    const bool path = q < npaths;
+                    v[0] = a.a; v[1] = a.b; v[2] = path ? tb.need[f >> 27] : -1.0f; v[3] = path ? b.a : -1.0f; v[4] = b.b;
+                }
+            }
+            if (stream_out) {
+                const __m128i *sv = reinterpret_cast<const __m128i *>(stage);
+                __m128i *dv = reinterpret_cast<__m128i *>(dst);
+                const size_t nv = (size_t)nb * D / 4;
+                for (size_t i = 0; i < nv; i++) _mm_stream_si128(dv + i, _mm_load_si128(sv + i));
             }
         }
-        if (reward) reward[r] = (q5 >> 28) & 1u ? 1.0f : -1.0f;
-        if (done) done[r] = (uint8_t)((q5 >> 29) & 1u);
-        if (action) action[r] = (int32_t)w[6];
+        if (reward) for (int i = 0; i < nb; i++) reward[b0 + i] = (pk[(b0 + i) * 8 + 5] >> 28) & 1u ? 1.0f : -1.0f;
+        if (done) for (int i = 0; i < nb; i++) done[b0 + i] = (uint8_t)((pk[(b0 + i) * 8 + 5] >> 29) & 1u);
+        if (action) for (int i = 0; i < nb; i++) action[b0 + i] = (int32_t)pk[(b0 + i) * 8 + 6];
     }
+    _mm_sfence();
 }
+}  // namespace
 
 int orlg_expand_packed(const uint32_t *packed_host, int64_t rows, int num_nodes, int num_slots, float *obs_host, float *reward_host,
                        uint8_t *done_host, int32_t *action_host, int threads) {
-    if (!packed_host || rows < 0 || num_nodes < 2 || num_slots < 1) return fail(ORLG_E_INVALID, "bad arguments");
+    if (!packed_host || rows < 0 || num_nodes < 2 || num_nodes > 255 || num_slots < 1) return fail(ORLG_E_INVALID, "bad arguments");
     int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
     if (nt < 1) nt = 1;
-    if ((int64_t)nt > rows / 4096 + 1) nt = (int)(rows / 4096 + 1);
-    if (nt == 1) { expand_rows(packed_host, 0, rows, num_nodes, num_slots, obs_host, reward_host, done_host, action_host); return ORLG_OK; }
-    std::vector<std::thread> pool;
-    const int64_t per = (rows + nt - 1) / nt;
-    for (int i = 0; i < nt; i++) {
-        const int64_t r0 = i * per, r1 = r0 + per < rows ? r0 + per : rows;
-        if (r0 >= r1) break;
-        pool.emplace_back(expand_rows, packed_host, r0, r1, num_nodes, num_slots, obs_host, reward_host, done_host, action_host);
-    }
-    for (auto &t : pool) t.join();
+    const ExpandTables &tb = expand_tables(num_slots);
+    constexpr int64_t JOB = 2048;          // rows per hand-out (a multiple of EXP_BLOCK)
+    const int64_t blocks = (rows + JOB - 1) / JOB;
+    if ((int64_t)nt > blocks) nt = (int)blocks;
+    auto job = [&](int64_t b) {
+        const int64_t r0 = b * JOB, r1 = r0 + JOB < rows ? r0 + JOB : rows;
+        expand_rows(tb, packed_host, r0, r1, num_nodes, obs_host, reward_host, done_host, action_host);
+    };
+    if (nt <= 1) { for (int64_t b = 0; b < blocks; b++) job(b); return ORLG_OK; }
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool.run(nt, blocks, job);
     return ORLG_OK;
 }
 
@@ -1020,7 +1154,8 @@ int orlg_rollout_host(orlg_env *env, int steps, int policy, float *obs_host, flo
                       int32_t *actions_host, int chunk_steps, int threads, orlg_stream stream) {
     if (!env) return fail(ORLG_E_INVALID, "null handle");
     if (steps <= 0) return steps == 0 ? ORLG_OK : fail(ORLG_E_INVALID, "steps must be >= 0");
-    if (policy == ORLG_POLICY_REPLAY) return fail(ORLG_E_UNSUPPORTED, "orlg_rollout_host takes device-side policies (random / heuristics)");
+    const bool replay = policy == ORLG_POLICY_REPLAY;       // actions_host is then the INPUT [steps, num_envs, action_dim]
+    if (replay && !actions_host) return fail(ORLG_E_INVALID, "ORLG_POLICY_REPLAY needs the actions");
     DeviceGuard guard(env->device);
     Params &p = env->p;
     cudaStream_t s = (cudaStream_t)stream;
@@ -1037,12 +1172,25 @@ int orlg_rollout_host(orlg_env *env, int steps, int policy, float *obs_host, flo
         }
         env->ro_pk_rows = rows;
     }
+    const size_t adim = (size_t)orlg_action_dim(env);
+    if (replay && env->ro_act_rows < rows) {             // device copies of the action chunks, double-buffered like the records
+        for (int i = 0; i < 2; i++) {
+            if (env->ro_act_dev[i]) cudaFree(env->ro_act_dev[i]);
+            env->ro_act_dev[i] = nullptr;
+            if (cudaMalloc(&env->ro_act_dev[i], rows * adim * sizeof(int32_t)) != cudaSuccess) return fail(ORLG_E_NOMEM, "cudaMalloc (action chunks) failed");
+        }
+        env->ro_act_rows = rows;
+    }
     const int nchunks = (steps + chunk - 1) / chunk;
     const size_t D = (size_t)p.obs_dim;
     for (int c = 0; c <= nchunks; c++) {
         if (c < nchunks) {                              // chunk c: device rollout, then its records start crossing PCIe
             const int t0 = c * chunk, tc = steps - t0 < chunk ? steps - t0 : chunk;
-            int rc = rollout_impl(env, tc, policy, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<uint32_t *>(env->ro_pk_dev[c & 1]), stream);
+            if (replay)
+                CUDA_OK(cudaMemcpyAsync(env->ro_act_dev[c & 1], actions_host + (size_t)t0 * p.n * adim, (size_t)tc * p.n * adim * sizeof(int32_t),
+                                        cudaMemcpyHostToDevice, s));
+            int rc = rollout_impl(env, tc, policy, nullptr, nullptr, nullptr, replay ? env->ro_act_dev[c & 1] : nullptr,
+                                  reinterpret_cast<uint32_t *>(env->ro_pk_dev[c & 1]), stream);
             if (rc) return rc;
             CUDA_OK(cudaMemcpyAsync(env->ro_pk_host[c & 1], env->ro_pk_dev[c & 1], (size_t)tc * p.n * 32, cudaMemcpyDeviceToHost, s));
             CUDA_OK(cudaEventRecord(env->ro_pk_ev[c & 1], s));
@@ -1053,7 +1201,7 @@ int orlg_rollout_host(orlg_env *env, int steps, int policy, float *obs_host, flo
             const size_t off = (size_t)t0 * p.n;
             int rc = orlg_expand_packed(reinterpret_cast<const uint32_t *>(env->ro_pk_host[(c - 1) & 1]), (int64_t)tc * p.n, p.N, p.S,
                                         obs_host ? obs_host + off * D : nullptr, reward_host ? reward_host + off : nullptr,
-                                        done_host ? done_host + off : nullptr, actions_host ? actions_host + off : nullptr, threads);
+                                        done_host ? done_host + off : nullptr, (actions_host && !replay) ? actions_host + off : nullptr, threads);
             if (rc) return rc;
         }
     }

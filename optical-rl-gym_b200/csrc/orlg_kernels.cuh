@@ -65,6 +65,7 @@ struct Params {
     unsigned char *cand;               // [n][cand_stride] first-fit block starts of the pending request
     unsigned short *cand16;            // same for the wide layout (S > 128)
     int nwv;                           // 128-bit word groups per (core, link): 1 unless wide
+    int wstride;                       // wide layout (env-major): 128-bit words between consecutive (core, link) entries of one env; 0 = [link][env] layout
     unsigned *errors;                  // [n]
     // ---- float statistics of `info` (row f1: rmsa_env.py:439-543, 699-744); allocated by orlg_enable_stats
     int stats;
@@ -77,6 +78,13 @@ struct Params {
     // ---- RWA actions_output (rwa_env.py:52-58, 103): only its marginals reach `info` (rwa_env.py:148-151)
     int *act_hist;                     // [(k + rej) + (S + rej)][n] row sums, then column sums (NULL unless RWA-v0)
 };
+
+// index of the 128-bit word group v of (core, link) entry cl of env e in p.masks: [entry][word][env] (a warp's 32 envs read one
+// entry as one 512-byte run: the NSFNET-class kernels), or env-major [env][entry][wstride] for the wide kernels (each thread
+// walks its own path, so an entry's words should share a DRAM burst and an env's entries a page)
+__device__ __forceinline__ size_t mask_index(const Params &p, int cl, int v, int e) {
+    return p.wstride ? ((size_t)e * (p.C * p.E) + cl) * p.wstride + v : ((size_t)cl * p.nwv + v) * p.n + e;
+}
 
 // position of a bit rate in the discrete list (-1: not one of them, e.g. a foreign trace)
 __device__ __forceinline__ int br_index(const Params &p, int br) {
@@ -119,6 +127,8 @@ struct StepIO {
     int *decision;
     long long *info;
     int *obs_int;
+    int policy;          // wide kernels, MODE_STEP: >= 0 = this ORLG_HEUR_* is evaluated in the step kernel's prologue (fused), else -1
+    int *actions_out;    // ... and the action it took is stored here (may be null)
 };
 
 __device__ __forceinline__ int meta_hops(unsigned m) { return m & 0xff; }

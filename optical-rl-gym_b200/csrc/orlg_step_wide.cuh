@@ -4,7 +4,9 @@
 // Covers BASELINE.json configs[3] (RMSA-v0, 100 nodes / 300 links, 320 slots, k = 10) and configs[4]
 // (RMCSA-v0, 7 cores x 320 slots).  Same semantics, same state arrays and the same release-event table as
 // step_kernel (orlg_kernels.cuh); one thread per environment, masks accessed in place:
-//     masks[((core * E + link) * NWV + v) * n_envs + env]   (uint4)
+//     masks[(env * C * E + core * E + link) * wstride + v]   (uint4; env-major: an entry's words share one DRAM burst,
+//     an env's entries one page -- every thread walks its OWN path, so the [link][env] layout of the NSFNET-class kernels
+//     would put each of its accesses on a different 2 MB page)
 #pragma once
 #include "orlg_kernels.cuh"
 
@@ -120,6 +122,7 @@ template <int NWV>
 __device__ __forceinline__ WBits<NWV> wide_path_free(const Params &p, int env, int row, int core) {
     WBits<NWV> a = wb_fill<NWV>(0xFFFFFFFFu);
     const int h0 = p.path_link_ptr[row], h1 = p.path_link_ptr[row + 1];
+    const size_t vs = p.wstride ? 1 : (size_t)p.n;          // distance between the word groups of one entry (mask_index)
     const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
     for (int h = h0; h < h1; h += 4) {
         int l[4];
@@ -128,9 +131,9 @@ __device__ __forceinline__ WBits<NWV> wide_path_free(const Params &p, int env, i
         uint4 x[4][NWV];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const uint4 *m = p.masks + ((size_t)(core * p.E + max(l[i], 0)) * NWV) * p.n + env;
+            const uint4 *m = p.masks + mask_index(p, core * p.E + max(l[i], 0), 0, env);
 #pragma unroll
-            for (int v = 0; v < NWV; v++) x[i][v] = l[i] >= 0 ? m[(size_t)v * p.n] : ones;
+            for (int v = 0; v < NWV; v++) x[i][v] = l[i] >= 0 ? m[v * vs] : ones;
         }
 #pragma unroll
         for (int i = 0; i < 4; i++)
@@ -150,6 +153,7 @@ __device__ __forceinline__ void wide_path_update(const Params &p, int env, int r
 #pragma unroll
     for (int v = 0; v < NWV; v++) touch[v] = (rm.w[4 * v] | rm.w[4 * v + 1] | rm.w[4 * v + 2] | rm.w[4 * v + 3]) != 0u;
     const int h0 = p.path_link_ptr[row], h1 = p.path_link_ptr[row + 1];
+    const size_t vs = p.wstride ? 1 : (size_t)p.n;
     for (int h = h0; h < h1; h += 4) {
         int l[4];
 #pragma unroll
@@ -157,21 +161,21 @@ __device__ __forceinline__ void wide_path_update(const Params &p, int env, int r
         uint4 x[4][NWV];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const uint4 *m = p.masks + ((size_t)(core * p.E + max(l[i], 0)) * NWV) * p.n + env;
+            const uint4 *m = p.masks + mask_index(p, core * p.E + max(l[i], 0), 0, env);
 #pragma unroll
             for (int v = 0; v < NWV; v++)
-                if (l[i] >= 0 && touch[v]) x[i][v] = m[(size_t)v * p.n];
+                if (l[i] >= 0 && touch[v]) x[i][v] = m[v * vs];
         }
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            uint4 *m = p.masks + ((size_t)(core * p.E + max(l[i], 0)) * NWV) * p.n + env;
+            uint4 *m = p.masks + mask_index(p, core * p.E + max(l[i], 0), 0, env);
 #pragma unroll
             for (int v = 0; v < NWV; v++) {
                 if (l[i] >= 0 && touch[v]) {
                     uint4 y = x[i][v];
                     if (set) { y.x |= rm.w[4 * v]; y.y |= rm.w[4 * v + 1]; y.z |= rm.w[4 * v + 2]; y.w |= rm.w[4 * v + 3]; }
                     else { y.x &= ~rm.w[4 * v]; y.y &= ~rm.w[4 * v + 1]; y.z &= ~rm.w[4 * v + 2]; y.w &= ~rm.w[4 * v + 3]; }
-                    m[(size_t)v * p.n] = y;
+                    m[v * vs] = y;
                 }
             }
         }
@@ -180,8 +184,108 @@ __device__ __forceinline__ void wide_path_update(const Params &p, int env, int r
 
 __device__ __forceinline__ int wide_nslots(const Params &p, int se, int br) { return p.nslots[se * (p.br_max + 1) + br]; }
 
+// heuristic action sources for the wide layout: the action of env's pending request (src, dst, br) into a[0..3]
 template <int KIND, int NWV>
-__global__ void __launch_bounds__(128) step_wide_kernel(const Params p, const StepIO io, const int mode) {
+__device__ __forceinline__ void wide_heuristic(const Params &p, const int env, const int which, const int src, const int dst, const int br, int *a) {
+    const int pair = src * p.N + dst;
+    const int first = p.pair_first[pair];
+    const int npaths = min((int)p.pair_count[pair], p.k);
+    if (KIND == ORLG_DEEPRMSA) {
+        int act = p.k * p.J;
+        if (which == ORLG_HEUR_SP_FF) act = (!p.allow_rejection || p.cand16[(size_t)env * p.cand_stride] != 0xFFFFu) ? 0 : p.k * p.J;
+        else
+            for (int q = 0; q < npaths; q++)
+                if (p.cand16[(size_t)env * p.cand_stride + q * p.J] != 0xFFFFu) { act = q * p.J; break; }
+        a[0] = act;
+    } else if (KIND == ORLG_RMSA) {
+        int ap = p.k, as = p.S, max_free = 0;
+        const int np_ = (which == ORLG_HEUR_SP_FF) ? min(npaths, 1) : npaths;
+        for (int q = 0; q < np_; q++) {
+            const int n = wide_nslots(p, meta_se(p.path_meta[first + q]), br);
+            const WBits<NWV> A = wide_path_free<NWV>(p, env, first + q, 0);
+            WBits<NWV> B = wb_runs_ge(A, n);
+            const WBits<NWV> lim = wb_range<NWV>(0, max(p.S - n, 0));          // range(0, S - n): App. B-5
+#pragma unroll
+            for (int i = 0; i < 4 * NWV; i++) B.w[i] &= lim.w[i];
+            const int s = wb_ffs(B);
+            if (s >= 0) {
+                if (which == ORLG_HEUR_LLP_FF) {
+                    const int fr = wb_popc(A);
+                    if (fr > max_free) { ap = q; as = s; max_free = fr; }
+                } else { ap = q; as = s; break; }
+            }
+        }
+        a[0] = ap; a[1] = as;
+    } else if (KIND == ORLG_RWA) {
+        int ap = p.k, as = p.S;
+        if (which == ORLG_HEUR_SP_FF) {
+            if (npaths > 0) {
+                const int s = wb_ffs(wide_path_free<NWV>(p, env, first, 0));
+                if (s >= 0) { ap = 0; as = s; }
+            }
+        } else if (which == ORLG_HEUR_SAP_FF || which == ORLG_HEUR_SAP_LF) {
+            int best_hops = 0x7fffffff;
+            for (int q = 0; q < npaths; q++) {
+                const int hops = p.path_link_ptr[first + q + 1] - p.path_link_ptr[first + q];
+                if (hops < best_hops) {
+                    WBits<NWV> A = wide_path_free<NWV>(p, env, first + q, 0);
+                    int s;
+                    if (which == ORLG_HEUR_SAP_FF) s = wb_ffs(A);
+                    else { A.w[0] &= ~1u; s = wb_fls(A); }
+                    if (s >= 0) { best_hops = hops; ap = q; as = s; }
+                }
+            }
+        } else {
+            int best = -1;
+            for (int q = 0; q < npaths; q++) {
+                const WBits<NWV> A = wide_path_free<NWV>(p, env, first + q, 0);
+                const int cap = wb_popc(A);
+                if (cap > best) {
+                    const int s = wb_ffs(A);
+                    if (s >= 0) { best = cap; ap = q; as = s; }
+                }
+            }
+        }
+        a[0] = ap; a[1] = as;
+    } else {
+        int a0 = p.k, a1 = p.M, a2 = p.C, a3 = p.S;
+        bool found = false;
+        for (int q = 0; q < npaths && !found; q++) {
+            const int mod = meta_mod(p.path_meta[first + q]);
+            const int n = wide_nslots(p, p.mod_se[mod], br);
+            const WBits<NWV> lim = wb_range<NWV>(0, max(p.S - n, 0));
+            for (int c = 0; c < p.C && !found; c++) {
+                WBits<NWV> B = wb_runs_ge(wide_path_free<NWV>(p, env, first + q, c), n);
+#pragma unroll
+                for (int i = 0; i < 4 * NWV; i++) B.w[i] &= lim.w[i];
+                const int s = wb_ffs(B);
+                if (s >= 0) { a0 = q; a1 = mod; a2 = c; a3 = s; found = true; }
+            }
+        }
+        a[0] = a0; a[1] = a1; a[2] = a2; a[3] = a3;
+    }
+}
+
+template <int KIND, int NWV>
+__global__ void heuristic_wide_kernel(const Params p, const int which, int *actions) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.n) return;
+    const uint2 rq = p.cur_req[env];
+    constexpr int AD = KIND == ORLG_DEEPRMSA ? 1 : (KIND == ORLG_RMCSA ? 4 : 2);
+    int a[4];
+    wide_heuristic<KIND, NWV>(p, env, which, rq.x & 0xff, (rq.x >> 8) & 0xff, (int)(rq.x >> 16), a);
+#pragma unroll
+    for (int i = 0; i < AD; i++) actions[AD * env + i] = a[i];
+}
+
+#ifndef ORLG_WIDE_THREADS
+#define ORLG_WIDE_THREADS 128
+#endif
+#ifndef ORLG_WIDE_MIN_BLOCKS
+#define ORLG_WIDE_MIN_BLOCKS 4        // 128 registers per thread: 16 warps per SM instead of 12 (the kernel is latency-bound)
+#endif
+template <int KIND, int NWV>
+__global__ void __launch_bounds__(ORLG_WIDE_THREADS, ORLG_WIDE_MIN_BLOCKS) step_wide_kernel(const Params p, const StepIO io, const int mode) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.n) return;
     double now = p.now[env];
@@ -204,7 +308,7 @@ __global__ void __launch_bounds__(128) step_wide_kernel(const Params p, const St
         for (int l = 0; l < p.C * p.E; l++)
 #pragma unroll
             for (int v = 0; v < NWV; v++)
-                p.masks[((size_t)l * NWV + v) * p.n + env] = make_uint4(full.w[4 * v], full.w[4 * v + 1], full.w[4 * v + 2], full.w[4 * v + 3]);
+                p.masks[mask_index(p, l, v, env)] = make_uint4(full.w[4 * v], full.w[4 * v + 1], full.w[4 * v + 2], full.w[4 * v + 3]);
         now = 0.0; nheap = 0; hmin = ORLG_INF; tailmin = ORLG_INF; ridx = 0; err = 0;
 #pragma unroll
         for (int q = 0; q < 8; q++) cnt[q] = 0;
@@ -217,8 +321,20 @@ __global__ void __launch_bounds__(128) step_wide_kernel(const Params p, const St
         const int first = p.pair_first[pair];
         const int npaths = p.pair_count[pair];
         int row = -1, start = 0, n = 0, core = 0, mod = -1;
+        constexpr int AD = KIND == ORLG_DEEPRMSA ? 1 : (KIND == ORLG_RMCSA ? 4 : 2);
+        int act[4];
+        if (io.policy >= 0) {                                // fused rollout step: action = heuristic(env), no second launch, and
+            wide_heuristic<KIND, NWV>(p, env, io.policy, src, dst, br, act);      // the path's masks are in L1 / L2 for what follows
+            if (io.actions_out) {
+#pragma unroll
+                for (int i = 0; i < AD; i++) io.actions_out[AD * env + i] = act[i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < AD; i++) act[i] = io.actions[AD * env + i];
+        }
         if (KIND == ORLG_DEEPRMSA) {
-            const int a = io.actions[env];
+            const int a = act[0];
             if (a >= 0 && a < p.k * p.J) {
                 const int route = a / p.J;
                 if (route < npaths) {
@@ -232,7 +348,7 @@ __global__ void __launch_bounds__(128) step_wide_kernel(const Params p, const St
                 } else err |= ORLG_ERR_NO_SUCH_PATH;
             }
         } else if (KIND == ORLG_RMSA || KIND == ORLG_RWA) {
-            const int path = io.actions[2 * env], slot = io.actions[2 * env + 1];
+            const int path = act[0], slot = act[1];
             if (KIND == ORLG_RWA) act_hist_bump(p, env, path, slot, err);
             if (path >= 0 && path < p.k && slot >= 0 && slot < p.S) {
                 if (path < npaths) {
@@ -243,7 +359,7 @@ __global__ void __launch_bounds__(128) step_wide_kernel(const Params p, const St
                 } else err |= ORLG_ERR_NO_SUCH_PATH;
             }
         } else {
-            const int path = io.actions[4 * env], am = io.actions[4 * env + 1], ac = io.actions[4 * env + 2], slot = io.actions[4 * env + 3];
+            const int path = act[0], am = act[1], ac = act[2], slot = act[3];
             if (path >= 0 && path < p.k && am >= 0 && am < p.M && ac >= 0 && ac < p.C && slot >= 0 && slot < p.S) {
                 if (path < npaths) {
                     row = first + path;
@@ -390,92 +506,6 @@ __global__ void __launch_bounds__(128) step_wide_kernel(const Params p, const St
     }
 }
 
-// heuristic action sources for the wide layout
-template <int KIND, int NWV>
-__global__ void heuristic_wide_kernel(const Params p, const int which, int *actions) {
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= p.n) return;
-    const uint2 rq = p.cur_req[env];
-    const int src = rq.x & 0xff, dst = (rq.x >> 8) & 0xff, br = (int)(rq.x >> 16);
-    const int pair = src * p.N + dst;
-    const int first = p.pair_first[pair];
-    const int npaths = min((int)p.pair_count[pair], p.k);
-    if (KIND == ORLG_DEEPRMSA) {
-        int a = p.k * p.J;
-        if (which == ORLG_HEUR_SP_FF) a = (!p.allow_rejection || p.cand16[(size_t)env * p.cand_stride] != 0xFFFFu) ? 0 : p.k * p.J;
-        else
-            for (int q = 0; q < npaths; q++)
-                if (p.cand16[(size_t)env * p.cand_stride + q * p.J] != 0xFFFFu) { a = q * p.J; break; }
-        actions[env] = a;
-    } else if (KIND == ORLG_RMSA) {
-        int ap = p.k, as = p.S, max_free = 0;
-        const int np_ = (which == ORLG_HEUR_SP_FF) ? min(npaths, 1) : npaths;
-        for (int q = 0; q < np_; q++) {
-            const int n = wide_nslots(p, meta_se(p.path_meta[first + q]), br);
-            const WBits<NWV> A = wide_path_free<NWV>(p, env, first + q, 0);
-            WBits<NWV> B = wb_runs_ge(A, n);
-            const WBits<NWV> lim = wb_range<NWV>(0, max(p.S - n, 0));          // range(0, S - n): App. B-5
-#pragma unroll
-            for (int i = 0; i < 4 * NWV; i++) B.w[i] &= lim.w[i];
-            const int s = wb_ffs(B);
-            if (s >= 0) {
-                if (which == ORLG_HEUR_LLP_FF) {
-                    const int fr = wb_popc(A);
-                    if (fr > max_free) { ap = q; as = s; max_free = fr; }
-                } else { ap = q; as = s; break; }
-            }
-        }
-        actions[2 * env] = ap; actions[2 * env + 1] = as;
-    } else if (KIND == ORLG_RWA) {
-        int ap = p.k, as = p.S;
-        if (which == ORLG_HEUR_SP_FF) {
-            if (npaths > 0) {
-                const int s = wb_ffs(wide_path_free<NWV>(p, env, first, 0));
-                if (s >= 0) { ap = 0; as = s; }
-            }
-        } else if (which == ORLG_HEUR_SAP_FF || which == ORLG_HEUR_SAP_LF) {
-            int best_hops = 0x7fffffff;
-            for (int q = 0; q < npaths; q++) {
-                const int hops = p.path_link_ptr[first + q + 1] - p.path_link_ptr[first + q];
-                if (hops < best_hops) {
-                    WBits<NWV> A = wide_path_free<NWV>(p, env, first + q, 0);
-                    int s;
-                    if (which == ORLG_HEUR_SAP_FF) s = wb_ffs(A);
-                    else { A.w[0] &= ~1u; s = wb_fls(A); }
-                    if (s >= 0) { best_hops = hops; ap = q; as = s; }
-                }
-            }
-        } else {
-            int best = -1;
-            for (int q = 0; q < npaths; q++) {
-                const WBits<NWV> A = wide_path_free<NWV>(p, env, first + q, 0);
-                const int cap = wb_popc(A);
-                if (cap > best) {
-                    const int s = wb_ffs(A);
-                    if (s >= 0) { best = cap; ap = q; as = s; }
-                }
-            }
-        }
-        actions[2 * env] = ap; actions[2 * env + 1] = as;
-    } else {
-        int a0 = p.k, a1 = p.M, a2 = p.C, a3 = p.S;
-        bool found = false;
-        for (int q = 0; q < npaths && !found; q++) {
-            const int mod = meta_mod(p.path_meta[first + q]);
-            const int n = wide_nslots(p, p.mod_se[mod], br);
-            const WBits<NWV> lim = wb_range<NWV>(0, max(p.S - n, 0));
-            for (int c = 0; c < p.C && !found; c++) {
-                WBits<NWV> B = wb_runs_ge(wide_path_free<NWV>(p, env, first + q, c), n);
-#pragma unroll
-                for (int i = 0; i < 4 * NWV; i++) B.w[i] &= lim.w[i];
-                const int s = wb_ffs(B);
-                if (s >= 0) { a0 = q; a1 = mod; a2 = c; a3 = s; found = true; }
-            }
-        }
-        actions[4 * env] = a0; actions[4 * env + 1] = a1; actions[4 * env + 2] = a2; actions[4 * env + 3] = a3;
-    }
-}
-
 // state export for the wide layout: masks uint32 [n][C*E][4*NWV], allocation int32 [n][C][E][S]
 __global__ void export_wide_kernel(const Params p, unsigned *masks_out, int *alloc_out) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
@@ -484,7 +514,7 @@ __global__ void export_wide_kernel(const Params p, unsigned *masks_out, int *all
     if (masks_out)
         for (int l = 0; l < CE; l++)
             for (int v = 0; v < NWV; v++) {
-                const uint4 m = p.masks[((size_t)l * NWV + v) * p.n + env];
+                const uint4 m = p.masks[mask_index(p, l, v, env)];
                 unsigned *o = masks_out + ((size_t)env * CE + l) * (4 * NWV) + 4 * v;
                 o[0] = m.x; o[1] = m.y; o[2] = m.z; o[3] = m.w;
             }

@@ -59,7 +59,7 @@ __global__ void matrix_observation_kernel(const Params p, unsigned char *out) {
         } else {
             const int cell = pos - 2 * p.N;
             const int l = cell / p.S, s = cell - l * p.S;
-            const uint4 m = p.masks[((size_t)l * p.nwv + (s >> 7)) * p.n + env];
+            const uint4 m = p.masks[mask_index(p, l, s >> 7, env)];
             const int w = (s >> 5) & 3;
             const unsigned word = w == 0 ? m.x : (w == 1 ? m.y : (w == 2 ? m.z : m.w));
             v = (word >> (s & 31)) & 1u;

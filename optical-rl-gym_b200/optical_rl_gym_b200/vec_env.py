@@ -409,9 +409,14 @@ class OpticalVecEnv:
     def rollout_host(self, steps: int, policy="random", *, obs=None, reward=None, done=None, actions=None, chunk: int = 8,
                      threads: int = 0):
         """:meth:`rollout` with the results delivered in HOST memory (numpy arrays, pageable is fine): the device runs chunk
-        c + 1 while chunk c's packed records cross PCIe and the host threads expand them (``orlg_rollout_host``)."""
+        c + 1 while chunk c's packed records cross PCIe and the host threads expand them (``orlg_rollout_host``).
+        ``policy="replay"``: ``actions`` (int32 ``[steps, num_envs]``, host) is the input action sequence."""
         T, n = int(steps), self.num_envs
-        pol = -1 if policy in ("random", None) else (nat.HEURISTICS[policy] if isinstance(policy, str) else int(policy))
+        if policy == "replay":
+            assert actions is not None, "policy='replay' needs the actions"
+            pol = -2
+        else:
+            pol = -1 if policy in ("random", None) else (nat.HEURISTICS[policy] if isinstance(policy, str) else int(policy))
         obs = np.empty((T, n, self.obs_dim), np.float32) if obs is None else obs
         reward = np.empty((T, n), np.float32) if reward is None else reward
         done = np.empty((T, n), np.uint8) if done is None else done

@@ -327,6 +327,17 @@ def test_wide_layout_matches_oracle(kind, topo, env_args, policy, n_envs, T):
         assert now[i].item() == onow and nheap[i].item() == onh
         assert np.array_equal(cnt[i], o.counters())
     assert int(env.error_flags().abs().sum()) == 0
+    # the same T steps as ONE orlg_rollout call on a fresh handle: for heuristic policies the wide kernels evaluate the heuristic
+    # inside the step kernel (fused); actions, rewards, dones and the final state must not change
+    twin = OpticalVecEnv(kind, n_envs, tables, traffic="philox", obs_dtype=torch.float64, env_id_base=base, seed=seed, **env_args)
+    pname = {"heuristic": "sap_ff"}.get(policy, policy)
+    _, r_ro, d_ro, a_ro = twin.rollout(T, pname)
+    assert np.array_equal(a_ro.cpu().numpy(), np.stack([np.stack([np.atleast_1d(r["actions"][t]) for r in ref]) for t in range(T)]))
+    assert np.array_equal(d_ro.cpu().numpy().astype(bool), np.stack([[bool(r["dones"][t]) for r in ref] for t in range(T)]))
+    assert torch.equal(twin.export_state(allocation=True)[0], m) and torch.equal(twin.counters(), env.counters())
+    assert torch.equal(twin.export_state(allocation=True)[1], alloc)
+    assert int(twin.error_flags().abs().sum()) == 0
+    twin.close()
     env.close()
 
 

@@ -266,6 +266,15 @@ def test_packed_records_and_host_rollout_equal_the_device_rollout():
         assert np.array_equal(o2, o3) and np.array_equal(r2, r3) and np.array_equal(d2, d3) and np.array_equal(a2, a3), T
     _final_state_equal(a, b)
     _final_state_equal(a, c)
+    # host-provided actions (ORLG_POLICY_REPLAY): the same trajectory as stepping with them one call at a time
+    T = 29
+    acts = np.random.default_rng(3).integers(0, 6, size=(T, 1000)).astype(np.int32)
+    o3, r3, d3, _ = c.rollout_host(T, "replay", actions=acts.copy(), chunk=4, threads=2)
+    for t in range(T):
+        o, r, d, _ = a.step(torch.from_numpy(acts[t]).cuda())
+        assert np.array_equal(o.cpu().numpy(), o3[t]) and np.array_equal(r.cpu().numpy(), r3[t]), t
+        assert np.array_equal(d.cpu().numpy().astype(np.uint8), d3[t]), t
+    _final_state_equal(a, c)
     a.close(); b.close(); c.close()
 
 
