@@ -408,7 +408,7 @@ def main():
         # step's float32 observation row, reward and done in host memory.  Inside the call the device runs chunk c + 1 while
         # chunk c's 32-byte step records cross PCIe and the host threads expand them to the float32 rows (bit-identical to
         # what orlg_rollout writes on the device).  Wall clock around the calls, every rank at the same time, max over ranks.
-        k_h = max(20, min(K, 40))
+        k_h = 40                               # steps per call (580 MB of float32 rows in host memory per rank)
         threads = max(1, (os.cpu_count() or 1) // world)
         rng = np.random.default_rng(1234 + rank)
         ha_t = torch.from_numpy(rng.integers(0, env.k_paths * env.j + 1, size=(k_h, n), dtype=np.int32)).pin_memory()

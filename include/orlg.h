@@ -194,6 +194,16 @@ int orlg_policy_destroy(orlg_policy *pol);
  * pairwise mean).  Call before orlg_reset(full = 1).  stats_dev = NULL disables it again.  The statistics
  * path uses the generic kernel (slower than the default path). */
 int orlg_enable_stats(orlg_env *env, double *stats_dev);
+/* The time-averaged statistics the reference keeps ON the topology graph while it provisions and releases (never returned by
+ * step, read by users through env.topology): per link `utilization`, `external_fragmentation`, `compactness`
+ * (_update_link_stats: rmsa_env.py:464-543, rmcsa_env.py:591-688 -- one set per link, fed by the core being touched --,
+ * rwa_env.py:365-383 -- utilization only) and the graph's `throughput` / `compactness` (_update_network_stats:
+ * rmsa_env.py:439-462, rmcsa_env.py:560-589; a no-op in rwa_env.py:351-363).  orlg_enable_link_stats(on = 1) before
+ * orlg_reset(full = 1) turns them on for ANY env kind (orlg_enable_stats implies it); orlg_link_stats reads them as of the last
+ * step: link_dev f64 [num_envs, links, 3] by link index, graph_dev f64 [num_envs, 2] (either may be NULL).  Bit-identical to
+ * the reference (same float64 operation order, releases applied in time order).  Same limits and cost as orlg_enable_stats. */
+int orlg_enable_link_stats(orlg_env *env, int on);
+int orlg_link_stats(orlg_env *env, double *link_dev, double *graph_dev, orlg_stream stream);
 
 /* env.observation() of the pending request (deeprmsa_env.py:60-121) */
 int orlg_observation(orlg_env *env, void *obs_dev, orlg_stream stream);

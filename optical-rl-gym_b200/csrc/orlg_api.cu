@@ -35,6 +35,8 @@ static int fail(int code, const std::string &msg) {
             return fail(ORLG_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
     } while (0)
 
+constexpr int RO_HOST_BUFFERS = 3;       // orlg_rollout_host: record buffers in flight (device runs two chunks ahead of the decoder)
+
 struct orlg_env {
     Params p;
     orlg_config cfg;
@@ -61,11 +63,13 @@ struct orlg_env {
     unsigned long long *ro_st_u64 = nullptr;   // [RO_SIDE][n] side-buffer payloads
     bool ro_valid = false;                     // the events live in the rollout-private storage (canonical tables are stale)
     // orlg_rollout_host: double-buffered packed records on the device and in pinned host memory
-    uint4 *ro_pk_dev[2] = {nullptr, nullptr};
-    uint4 *ro_pk_host[2] = {nullptr, nullptr};
+    uint4 *ro_pk_dev[RO_HOST_BUFFERS] = {};
+    uint4 *ro_pk_host[RO_HOST_BUFFERS] = {};
     size_t ro_pk_rows = 0;                     // rows (env-steps) each buffer holds
-    cudaEvent_t ro_pk_ev[2] = {nullptr, nullptr};
-    int32_t *ro_act_dev[2] = {nullptr, nullptr};   // ORLG_POLICY_REPLAY: the host's action chunks on the device
+    cudaEvent_t ro_pk_ev[RO_HOST_BUFFERS] = {};    // records of the chunk are in pinned host memory (copy stream)
+    cudaEvent_t ro_k_ev[RO_HOST_BUFFERS] = {};     // the chunk's kernel is done (user stream)
+    cudaStream_t ro_copy_stream = nullptr;         // D2H of chunk c overlaps the kernel of chunk c + 1
+    int32_t *ro_act_dev[RO_HOST_BUFFERS] = {};     // ORLG_POLICY_REPLAY: the host's action chunks on the device
     size_t ro_act_rows = 0;
     int *ro_actions = nullptr;    // [n, action_dim] scratch of the generic (kernel-per-step) rollout
 };
@@ -619,12 +623,14 @@ int orlg_destroy(orlg_env *env) {
     if (!env) return ORLG_OK;
     DeviceGuard guard(env->device);
     for (void *ptr : env->allocs) cudaFree(ptr);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < RO_HOST_BUFFERS; i++) {
         if (env->ro_pk_dev[i]) cudaFree(env->ro_pk_dev[i]);
         if (env->ro_pk_host[i]) cudaFreeHost(env->ro_pk_host[i]);
         if (env->ro_pk_ev[i]) cudaEventDestroy(env->ro_pk_ev[i]);
+        if (env->ro_k_ev[i]) cudaEventDestroy(env->ro_k_ev[i]);
         if (env->ro_act_dev[i]) cudaFree(env->ro_act_dev[i]);
     }
+    if (env->ro_copy_stream) cudaStreamDestroy(env->ro_copy_stream);
     delete env;
     return ORLG_OK;
 }
@@ -827,25 +833,57 @@ int orlg_debug_warp_timeline(unsigned long long *out, int n_warps) {
 #endif
 }
 
-int orlg_enable_stats(orlg_env *env, double *stats_dev) {
-    if (!env) return fail(ORLG_E_INVALID, "null handle");
-    DeviceGuard guard(env->device);
+static int stats_alloc(orlg_env *env) {
     Params &p = env->p;
-    if (!stats_dev) { p.stats = 0; p.stats_out = nullptr; return ORLG_OK; }
-    if (p.kind != ORLG_RMSA && p.kind != ORLG_DEEPRMSA) return fail(ORLG_E_UNSUPPORTED, "info has float statistics for RMSA-v0 / DeepRMSA-v0 only");
     if (env->wide || p.E > 128) return fail(ORLG_E_UNSUPPORTED, "statistics path handles <= 32 links and <= 128 slots");
+    if (p.br_max > 65535) return fail(ORLG_E_UNSUPPORTED, "statistics path keeps bit rates in 16 bits");
     if (!p.link_util) {
         const size_t n = (size_t)p.n;
         env->alloc_is_state = true;
         int rc = dev_alloc(env, &p.link_util, (size_t)p.E * n);
         if (!rc) rc = dev_alloc(env, &p.link_comp, (size_t)p.E * n);
         if (!rc) rc = dev_alloc(env, &p.link_last, (size_t)p.E * n);
+        if (!rc) rc = dev_alloc(env, &p.link_frag, (size_t)p.E * n);
+        if (!rc) rc = dev_alloc(env, &p.graph_stats, 3 * n);
+        if (!rc) rc = dev_alloc(env, &p.run_br, n);
+        if (!rc) rc = dev_alloc(env, &p.ev_br, n * (size_t)p.heap_cap);
         if (!rc) rc = dev_alloc(env, &p.sum_nh, n);
         env->alloc_is_state = false;
         if (rc) return rc;
     }
+    return ORLG_OK;
+}
+
+int orlg_enable_stats(orlg_env *env, double *stats_dev) {
+    if (!env) return fail(ORLG_E_INVALID, "null handle");
+    DeviceGuard guard(env->device);
+    Params &p = env->p;
+    if (!stats_dev) { p.stats = 0; p.stats_out = nullptr; return ORLG_OK; }
+    if (p.kind != ORLG_RMSA && p.kind != ORLG_DEEPRMSA) return fail(ORLG_E_UNSUPPORTED, "info has float statistics for RMSA-v0 / DeepRMSA-v0 only (orlg_enable_link_stats covers every kind)");
+    int rc = stats_alloc(env);
+    if (rc) return rc;
     p.stats = 1;
     p.stats_out = stats_dev;
+    return ORLG_OK;
+}
+
+int orlg_enable_link_stats(orlg_env *env, int on) {
+    if (!env) return fail(ORLG_E_INVALID, "null handle");
+    DeviceGuard guard(env->device);
+    Params &p = env->p;
+    if (!on) { if (!p.stats_out) p.stats = 0; return ORLG_OK; }
+    int rc = stats_alloc(env);
+    if (rc) return rc;
+    p.stats = 1;
+    return ORLG_OK;
+}
+
+int orlg_link_stats(orlg_env *env, double *link_dev, double *graph_dev, orlg_stream stream) {
+    if (!env || (!link_dev && !graph_dev)) return fail(ORLG_E_INVALID, "null handle or buffers");
+    if (!env->p.stats) return fail(ORLG_E_INVALID, "statistics are off (orlg_enable_stats / orlg_enable_link_stats before the full reset)");
+    DeviceGuard guard(env->device);
+    link_stats_kernel<<<(env->p.n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->p, link_dev, graph_dev);
+    CUDA_OK(cudaGetLastError());
     return ORLG_OK;
 }
 
@@ -1006,14 +1044,16 @@ int orlg_rollout_packed(orlg_env *env, int steps, int policy, uint32_t *packed_d
 namespace {
 struct HostPool {
     std::mutex mu;
-    std::condition_variable cv_work, cv_done;
+    std::condition_variable cv_work;
     std::vector<std::thread> workers;
     std::function<void(int64_t)> fn;
     int64_t nblocks = 0;
     std::atomic<int64_t> next{0};
-    int want = 0, active = 0;            // workers allowed into this job / still inside it
-    uint64_t generation = 0;
+    std::atomic<int> active{0};          // workers still inside the current job
+    std::atomic<uint64_t> generation{0};
     bool stop = false;
+    static constexpr int SPIN = 20000;   // polls of the generation counter (~0.3 ms) before a worker sleeps on the condition variable:
+                                         // the chunks of a pipelined rollout follow each other within that time
 
     void drain() {
         for (;;) {
@@ -1024,28 +1064,35 @@ struct HostPool {
     }
     void worker(int id) {
         uint64_t seen = 0;
-        std::unique_lock<std::mutex> lk(mu);
         for (;;) {
-            cv_work.wait(lk, [&] { return stop || generation != seen; });
-            if (stop) return;
-            seen = generation;
-            if (id >= want) continue;
-            lk.unlock();
-            drain();
-            lk.lock();
-            if (--active == 0) cv_done.notify_one();
+            int spins = 0;
+            while (generation.load(std::memory_order_acquire) == seen && spins < SPIN) { _mm_pause(); spins++; }
+            if (generation.load(std::memory_order_acquire) == seen) {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&] { return stop || generation.load(std::memory_order_acquire) != seen; });
+                if (stop) return;
+            }
+            seen = generation.load(std::memory_order_acquire);
+            // the low byte of the generation is the number of workers wanted by THAT job: a worker below it is waited for by
+            // run() (so fn / nblocks / next are the job's own); one at or above it touches nothing
+            if (id < (int)(seen & 0xffu)) {
+                drain();
+                active.fetch_sub(1, std::memory_order_acq_rel);
+            }
         }
     }
     void run(int threads, int64_t blocks, std::function<void(int64_t)> f) {
         if (threads <= 1 || blocks <= 1) { for (int64_t b = 0; b < blocks; b++) f(b); return; }
-        std::unique_lock<std::mutex> lk(mu);
-        while ((int)workers.size() < threads - 1) { const int id = (int)workers.size(); workers.emplace_back(&HostPool::worker, this, id); }
-        fn = std::move(f); nblocks = blocks; next.store(0); want = threads - 1; active = threads - 1; generation++;
-        lk.unlock();
+        if (threads > 200) threads = 200;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            while ((int)workers.size() < threads - 1) { const int id = (int)workers.size(); workers.emplace_back(&HostPool::worker, this, id); }
+            fn = std::move(f); nblocks = blocks; next.store(0); active.store(threads - 1);
+            generation.store((((generation.load(std::memory_order_relaxed) >> 8) + 1) << 8) | (uint64_t)(threads - 1), std::memory_order_release);
+        }
         cv_work.notify_all();
         drain();
-        lk.lock();
-        cv_done.wait(lk, [&] { return active == 0; });
+        while (active.load(std::memory_order_acquire) != 0) _mm_pause();     // the stragglers finish their last block
     }
     ~HostPool() {
         { std::lock_guard<std::mutex> lk(mu); stop = true; }
@@ -1159,22 +1206,25 @@ int orlg_rollout_host(orlg_env *env, int steps, int policy, float *obs_host, flo
     DeviceGuard guard(env->device);
     Params &p = env->p;
     cudaStream_t s = (cudaStream_t)stream;
-    const int chunk = chunk_steps > 0 ? chunk_steps : 8;
+    const int chunk = chunk_steps > 0 ? chunk_steps : 4;
     const size_t rows = (size_t)chunk * p.n;
-    if (env->ro_pk_rows < rows) {                       // (re)allocate the double buffers
-        for (int i = 0; i < 2; i++) {
+    constexpr int NB = RO_HOST_BUFFERS, AHEAD = RO_HOST_BUFFERS - 1;      // the device runs up to AHEAD chunks ahead of the host decoder
+    if (env->ro_pk_rows < rows) {                       // (re)allocate the record buffers (device + pinned host)
+        for (int i = 0; i < NB; i++) {
             if (env->ro_pk_dev[i]) cudaFree(env->ro_pk_dev[i]);
             if (env->ro_pk_host[i]) cudaFreeHost(env->ro_pk_host[i]);
             env->ro_pk_dev[i] = nullptr; env->ro_pk_host[i] = nullptr;
             if (cudaMalloc(&env->ro_pk_dev[i], rows * 32) != cudaSuccess) return fail(ORLG_E_NOMEM, "cudaMalloc (packed records) failed");
             if (cudaHostAlloc(&env->ro_pk_host[i], rows * 32, cudaHostAllocDefault) != cudaSuccess) return fail(ORLG_E_NOMEM, "cudaHostAlloc (packed records) failed");
             if (!env->ro_pk_ev[i]) CUDA_OK(cudaEventCreateWithFlags(&env->ro_pk_ev[i], cudaEventDisableTiming));
+            if (!env->ro_k_ev[i]) CUDA_OK(cudaEventCreateWithFlags(&env->ro_k_ev[i], cudaEventDisableTiming));
         }
         env->ro_pk_rows = rows;
     }
+    if (!env->ro_copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&env->ro_copy_stream, cudaStreamNonBlocking));
     const size_t adim = (size_t)orlg_action_dim(env);
-    if (replay && env->ro_act_rows < rows) {             // device copies of the action chunks, double-buffered like the records
-        for (int i = 0; i < 2; i++) {
+    if (replay && env->ro_act_rows < rows) {             // device copies of the action chunks
+        for (int i = 0; i < NB; i++) {
             if (env->ro_act_dev[i]) cudaFree(env->ro_act_dev[i]);
             env->ro_act_dev[i] = nullptr;
             if (cudaMalloc(&env->ro_act_dev[i], rows * adim * sizeof(int32_t)) != cudaSuccess) return fail(ORLG_E_NOMEM, "cudaMalloc (action chunks) failed");
@@ -1183,28 +1233,38 @@ int orlg_rollout_host(orlg_env *env, int steps, int policy, float *obs_host, flo
     }
     const int nchunks = (steps + chunk - 1) / chunk;
     const size_t D = (size_t)p.obs_dim;
-    for (int c = 0; c <= nchunks; c++) {
-        if (c < nchunks) {                              // chunk c: device rollout, then its records start crossing PCIe
-            const int t0 = c * chunk, tc = steps - t0 < chunk ? steps - t0 : chunk;
-            if (replay)
-                CUDA_OK(cudaMemcpyAsync(env->ro_act_dev[c & 1], actions_host + (size_t)t0 * p.n * adim, (size_t)tc * p.n * adim * sizeof(int32_t),
-                                        cudaMemcpyHostToDevice, s));
-            int rc = rollout_impl(env, tc, policy, nullptr, nullptr, nullptr, replay ? env->ro_act_dev[c & 1] : nullptr,
-                                  reinterpret_cast<uint32_t *>(env->ro_pk_dev[c & 1]), stream);
-            if (rc) return rc;
-            CUDA_OK(cudaMemcpyAsync(env->ro_pk_host[c & 1], env->ro_pk_dev[c & 1], (size_t)tc * p.n * 32, cudaMemcpyDeviceToHost, s));
-            CUDA_OK(cudaEventRecord(env->ro_pk_ev[c & 1], s));
-        }
-        if (c >= 1) {                                   // chunk c - 1: expand on the host threads while the device runs chunk c
-            const int t0 = (c - 1) * chunk, tc = steps - t0 < chunk ? steps - t0 : chunk;
-            CUDA_OK(cudaEventSynchronize(env->ro_pk_ev[(c - 1) & 1]));
-            const size_t off = (size_t)t0 * p.n;
-            int rc = orlg_expand_packed(reinterpret_cast<const uint32_t *>(env->ro_pk_host[(c - 1) & 1]), (int64_t)tc * p.n, p.N, p.S,
-                                        obs_host ? obs_host + off * D : nullptr, reward_host ? reward_host + off : nullptr,
-                                        done_host ? done_host + off : nullptr, (actions_host && !replay) ? actions_host + off : nullptr, threads);
-            if (rc) return rc;
-        }
+    cudaStream_t sc = env->ro_copy_stream;
+    // chunk c: [user stream] H2D of its actions, the rollout kernel -> [copy stream] D2H of its records.  The kernel of chunk
+    // c + 1 overlaps the copy of chunk c; buffer b = c % NB is reused by chunk c + NB, whose kernel waits for the copy of
+    // chunk c (event) and which is only enqueued after the host has decoded chunk c (program order below).
+    auto enqueue = [&](int c) -> int {
+        const int b = c % NB, t0 = c * chunk, tc = steps - t0 < chunk ? steps - t0 : chunk;
+        if (replay)
+            CUDA_OK(cudaMemcpyAsync(env->ro_act_dev[b], actions_host + (size_t)t0 * p.n * adim, (size_t)tc * p.n * adim * sizeof(int32_t),
+                                    cudaMemcpyHostToDevice, s));
+        if (c >= NB) CUDA_OK(cudaStreamWaitEvent(s, env->ro_pk_ev[b], 0));
+        int rc = rollout_impl(env, tc, policy, nullptr, nullptr, nullptr, replay ? env->ro_act_dev[b] : nullptr,
+                              reinterpret_cast<uint32_t *>(env->ro_pk_dev[b]), stream);
+        if (rc) return rc;
+        CUDA_OK(cudaEventRecord(env->ro_k_ev[b], s));
+        CUDA_OK(cudaStreamWaitEvent(sc, env->ro_k_ev[b], 0));
+        CUDA_OK(cudaMemcpyAsync(env->ro_pk_host[b], env->ro_pk_dev[b], (size_t)tc * p.n * 32, cudaMemcpyDeviceToHost, sc));
+        CUDA_OK(cudaEventRecord(env->ro_pk_ev[b], sc));
+        return ORLG_OK;
+    };
+    for (int c = 0; c < AHEAD && c < nchunks; c++) { int rc = enqueue(c); if (rc) return rc; }
+    for (int c = 0; c < nchunks; c++) {
+        if (c + AHEAD < nchunks) { int rc = enqueue(c + AHEAD); if (rc) return rc; }
+        const int b = c % NB, t0 = c * chunk, tc = steps - t0 < chunk ? steps - t0 : chunk;
+        CUDA_OK(cudaEventSynchronize(env->ro_pk_ev[b]));
+        const size_t off = (size_t)t0 * p.n;
+        int rc = orlg_expand_packed(reinterpret_cast<const uint32_t *>(env->ro_pk_host[b]), (int64_t)tc * p.n, p.N, p.S,
+                                    obs_host ? obs_host + off * D : nullptr, reward_host ? reward_host + off : nullptr,
+                                    done_host ? done_host + off : nullptr, (actions_host && !replay) ? actions_host + off : nullptr, threads);
+        if (rc) return rc;
     }
+    // the user's stream must not run ahead of the copies that still read the record buffers (a later call reuses them)
+    CUDA_OK(cudaStreamWaitEvent(s, env->ro_pk_ev[(nchunks - 1) % NB], 0));
     return ORLG_OK;
 }
 

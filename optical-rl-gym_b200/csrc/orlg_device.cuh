@@ -212,6 +212,7 @@ struct Events {
     double *t;                    // [cap] release times of this env; every slot >= n holds +INF
     unsigned long long *p;        // [cap] packed services
     float *gmin;                  // [cap / EV_GROUP] lower bound of each FULL group's earliest time; +INF from the tail group on
+    unsigned short *br;           // [cap] bit rate of each service (statistics mode only: graph "throughput"), else null
 };
 
 __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
@@ -222,13 +223,14 @@ __device__ __forceinline__ float lower_f32(double x) { return __double2float_rd(
 __device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
 
 __device__ __forceinline__ void events_push(const Events &ev, unsigned &n, double &tmin, double &tail_min, double t,
-                                            unsigned long long payload) {
+                                            unsigned long long payload, unsigned bit_rate = 0) {
     if ((n & (EV_GROUP - 1)) == 0) {             // opening a new tail group: publish the previous group's bound
         if (n > 0) ev.gmin[(n / EV_GROUP) - 1] = lower_f32(tail_min);
         tail_min = ORLG_INF;
     }
     ev.t[n] = t;
     ev.p[n] = payload;
+    if (ev.br) ev.br[n] = (unsigned short)bit_rate;
     n++;
     tail_min = dmin(tail_min, t);
     tmin = dmin(tmin, t);
@@ -245,7 +247,7 @@ template <typename F>
 struct ApplyPayload {
     static constexpr bool wants_time = false;
     F f;
-    __device__ __forceinline__ void operator()(unsigned long long pl, double) const { f(pl); }
+    __device__ __forceinline__ void operator()(unsigned long long pl, double, unsigned) const { f(pl); }
 };
 template <typename F>
 __device__ __forceinline__ ApplyPayload<F> apply_payload(F f) { return ApplyPayload<F>{f}; }
@@ -254,7 +256,7 @@ template <typename F>
 struct ApplyTimed {
     static constexpr bool wants_time = true;
     F f;
-    __device__ __forceinline__ void operator()(unsigned long long pl, double t) const { f(pl, t); }
+    __device__ __forceinline__ void operator()(unsigned long long pl, double t, unsigned br) const { f(pl, t, br); }
 };
 template <typename F>
 __device__ __forceinline__ ApplyTimed<F> apply_timed(F f) { return ApplyTimed<F>{f}; }
@@ -330,16 +332,18 @@ __device__ __forceinline__ void events_release(const Events &ev, unsigned &n, do
                 const unsigned last = n - 1;
                 const unsigned long long pl = ev.p[s];
                 const double pt = Apply::wants_time ? ev.t[s] : 0.0;
+                const unsigned pb = (Apply::wants_time && ev.br) ? ev.br[s] : 0u;
                 if (s != last) {                   // fill the hole with the tail entry (never due, see above)
                     const double lt = ev.t[last];
                     const unsigned long long lp = ev.p[last];
                     ev.t[s] = lt;
                     ev.p[s] = lp;
+                    if (ev.br) ev.br[s] = ev.br[last];
                     gm = fminf(gm, lower_f32(lt));
                 }
                 ev.t[last] = ORLG_INF;             // keep "t[s] = +INF for s >= n"
                 n--;
-                apply(pl, pt);
+                apply(pl, pt, pb);
             }
             SUBPHASE_MARK(15);                     // payload fetch, hole fill, apply
             if (s0 < n) {                          // publish the bound of what is left of this group

@@ -70,6 +70,10 @@ struct Params {
     // ---- float statistics of `info` (row f1: rmsa_env.py:439-543, 699-744); allocated by orlg_enable_stats
     int stats;
     double *link_util, *link_comp, *link_last;   // [E][n] time-averaged utilisation / compactness, last update time
+    double *link_frag;                 // [E][n] time-averaged external fragmentation (rmsa_env.py:487-524)
+    double *graph_stats;               // [3][n] topology.graph["throughput"], ["compactness"], ["last_update"] (rmsa_env.py:439-462)
+    long long *run_br;                 // [n] sum of bit_rate over graph["running_services"]
+    unsigned short *ev_br;             // [n][heap_cap] bit rate of every live service (parallel to ev_pay)
     long long *sum_nh;                 // [n] sum over running services of number_slots * hops
     double *stats_out;                 // [n][4] network_compactness, its difference, avg link compactness, avg link utilisation
     const int *link_order;             // [E] link indices in topology.edges() order (np.mean over the links)
@@ -205,6 +209,8 @@ __device__ __forceinline__ void philox_request(const Params &p, const unsigned *
 // free runs inside [lambda_min, lambda_max) = popc(F & ~(F << 1)) with F = free restricted to the window.
 struct LinkShape {
     int free_cnt, used_runs, span, free_runs_in;
+    int free_runs, longest_free;       // number of free runs and the longest one (external fragmentation)
+    bool free_at_both_ends;            // slot 0 and slot S - 1 are free
 };
 __device__ __forceinline__ LinkShape link_shape(const Bits &fr, int S) {
     LinkShape r;
@@ -213,6 +219,10 @@ __device__ __forceinline__ LinkShape link_shape(const Bits &fr, int S) {
     r.free_cnt = bits_popc(fr);
     r.used_runs = bits_popc(bits_andnot(used, bits_shl1(used)));
     r.span = 0; r.free_runs_in = 0;
+    r.free_runs = bits_popc(bits_andnot(fr, bits_shl1(fr)));
+    r.longest_free = 0;
+    for (Bits x = fr; bits_popc(x) != 0; x = bits_and(x, bits_shl1(x))) r.longest_free++;      // statistics path only: not hot
+    r.free_at_both_ends = bits_popc(bits_and(fr, bits_range(0, 1))) != 0 && bits_popc(bits_and(fr, bits_range(S - 1, S))) != 0;
     if (r.used_runs > 1) {
         const int lo = bits_ffs(used), hi = bits_fls(used) + 1;
         r.span = hi - lo;
@@ -223,17 +233,19 @@ __device__ __forceinline__ LinkShape link_shape(const Bits &fr, int S) {
 }
 
 // _get_network_compactness (rmsa_env.py:699-744)
-__device__ __forceinline__ double network_compactness(const Params &p, int env, long long sum_nh) {
+// (rmcsa_env.py:825-871: the links of ONE core, number_slots * hops summed over all running services)
+__device__ __forceinline__ double network_compactness(const Params &p, int env, long long sum_nh, int core = 0) {
     long long occupied = 0, unused = 0;
     for (int l = 0; l < p.E; l++) {
-        const LinkShape s = link_shape(bits_from(p.masks[(size_t)l * p.n + env]), p.S);
+        const LinkShape s = link_shape(bits_from(p.masks[(size_t)(core * p.E + l) * p.n + env]), p.S);
         occupied += s.span; unused += s.free_runs_in;
     }
     if (unused > 0) return __dmul_rn(__ddiv_rn((double)occupied, (double)sum_nh), __ddiv_rn((double)p.E, (double)unused));
     return 1.0;
 }
 
-// _update_link_stats (rmsa_env.py:464-543) for link l whose (already updated) mask is `fr`
+// _update_link_stats (rmsa_env.py:464-543, rmcsa_env.py:591-688, rwa_env.py:365-383: utilisation only) for link l whose (already
+// updated) mask -- of the core being touched -- is `fr`; the statistics are per LINK (RMCSA's cores share them)
 __device__ __forceinline__ void update_link_stats(const Params &p, int env, int l, const Bits &fr, double now) {
     const size_t i = (size_t)l * p.n + env;
     const double last_update = p.link_last[i];
@@ -242,12 +254,32 @@ __device__ __forceinline__ void update_link_stats(const Params &p, int env, int 
         const LinkShape s = link_shape(fr, p.S);
         const double cur_util = __ddiv_rn((double)(p.S - s.free_cnt), (double)p.S);
         p.link_util[i] = __ddiv_rn(__dadd_rn(__dmul_rn(p.link_util[i], last_update), __dmul_rn(cur_util, time_diff)), now);
-        double cur_comp = 0.0;
-        if (s.free_cnt > 0)
-            cur_comp = s.used_runs > 1 ? __dmul_rn(__ddiv_rn((double)s.span, (double)(p.S - s.free_cnt)), __ddiv_rn(1.0, (double)s.used_runs)) : 1.0;
-        p.link_comp[i] = __ddiv_rn(__dadd_rn(__dmul_rn(p.link_comp[i], last_update), __dmul_rn(cur_comp, time_diff)), now);
+        if (p.kind != ORLG_RWA) {
+            double cur_comp = 0.0, cur_frag = 0.0;
+            if (s.free_cnt > 0) {
+                cur_comp = s.used_runs > 1 ? __dmul_rn(__ddiv_rn((double)s.span, (double)(p.S - s.free_cnt)), __ddiv_rn(1.0, (double)s.used_runs)) : 1.0;
+                // max_empty stays 0 for fewer than two free runs and when they are exactly the first and the last block
+                const int max_empty = (s.free_runs > 1 && !(s.free_runs == 2 && s.free_at_both_ends)) ? s.longest_free : 0;
+                cur_frag = __dadd_rn(1.0, -__ddiv_rn((double)max_empty, (double)s.free_cnt));
+            }
+            p.link_frag[i] = __ddiv_rn(__dadd_rn(__dmul_rn(p.link_frag[i], last_update), __dmul_rn(cur_frag, time_diff)), now);
+            p.link_comp[i] = __ddiv_rn(__dadd_rn(__dmul_rn(p.link_comp[i], last_update), __dmul_rn(cur_comp, time_diff)), now);
+        }
     }
     p.link_last[i] = now;
+}
+
+// _update_network_stats (rmsa_env.py:439-462, rmcsa_env.py:560-589; a no-op for RWA): called by _provision_path only, after the
+// new service joined graph["running_services"]
+__device__ __forceinline__ void update_network_stats(const Params &p, int env, long long sum_nh, long long run_br, int core, double now) {
+    double *g = p.graph_stats + env;
+    const double last_update = g[2 * (size_t)p.n];
+    const double time_diff = __dadd_rn(now, -last_update);
+    if (now > 0) {
+        g[0] = __ddiv_rn(__dadd_rn(__dmul_rn(g[0], last_update), __dmul_rn((double)run_br, time_diff)), now);
+        g[p.n] = __ddiv_rn(__dadd_rn(__dmul_rn(g[p.n], last_update), __dmul_rn(network_compactness(p, env, sum_nh, core), time_diff)), now);
+    }
+    g[2 * (size_t)p.n] = now;
 }
 
 // np.mean over the links in topology.edges() order: numpy's pairwise summation (8 partial sums), E <= 128
@@ -273,10 +305,10 @@ __device__ __forceinline__ double mean_over_links(const Params &p, const double 
 }
 
 // _provision_path / _release_path with the per-link statistics, links in hop order (rmsa_env.py:381-396, 418-436)
-__device__ __forceinline__ void path_update_stats(const Params &p, int env, int row, const Bits &rm, bool set, double now) {
+__device__ __forceinline__ void path_update_stats(const Params &p, int env, int row, int core, const Bits &rm, bool set, double now) {
     for (int h = p.path_link_ptr[row]; h < p.path_link_ptr[row + 1]; h++) {
         const int l = p.path_links16[h];
-        uint4 *m = p.masks + (size_t)l * p.n + env;
+        uint4 *m = p.masks + (size_t)(core * p.E + l) * p.n + env;
         Bits b = bits_from(*m);
         b = set ? bits_or(b, rm) : bits_andnot(b, rm);
         *m = bits_to(b);
@@ -315,7 +347,8 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
     unsigned nheap = p.nheap[e];
     double hmin = p.heap_min[e];
     unsigned err = p.errors[e];
-    const Events ev = {p.ev_time + (size_t)e * p.heap_cap, p.ev_pay + (size_t)e * p.heap_cap, p.ev_gmin + (size_t)e * p.ev_groups};
+    const Events ev = {p.ev_time + (size_t)e * p.heap_cap, p.ev_pay + (size_t)e * p.heap_cap, p.ev_gmin + (size_t)e * p.ev_groups,
+                       p.stats ? p.ev_br + (size_t)e * p.heap_cap : nullptr};
     double tailmin = p.ev_tail[e];
 
     bool accepted = false;
@@ -404,18 +437,25 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
             accepted = false;
             err |= ORLG_ERR_HEAP_OVERFLOW;
         }
-        const bool do_stats = p.stats && (KIND == ORLG_RMSA || KIND == ORLG_DEEPRMSA);
+        const bool do_stats = p.stats != 0;
+        const bool info_stats = do_stats && p.stats_out && (KIND == ORLG_RMSA || KIND == ORLG_DEEPRMSA);
         long long snh = do_stats ? p.sum_nh[env] : 0;
-        const double prev_compactness = do_stats ? network_compactness(p, env, snh) : 0.0;     // rmsa_env.py:168-170
+        const double prev_compactness = info_stats ? network_compactness(p, env, snh) : 0.0;     // rmsa_env.py:168-170
         if (accepted) {
             if (live) {
                 if (do_stats) {
-                    path_update_stats(p, env, row, bits_range(start, start + n), false, now);
+                    path_update_stats(p, env, row, core, bits_range(start, start + n), false, now);
                     snh += (long long)n * meta_hops(p.path_meta[row]);
+                    p.sum_nh[env] = snh;
+                    if (KIND != ORLG_RWA) {
+                        const long long rb = p.run_br[env] + br;
+                        p.run_br[env] = rb;
+                        update_network_stats(p, env, snh, rb, core, now);
+                    }
                 } else
                 path_update(p, env, lm, core, bits_range(start, start + n), false);
                 double rel = __dadd_rn(now, hold);          // arrival_time + holding_time (now == arrival)
-                events_push(ev, nheap, hmin, tailmin, rel, pack_service(row, start, n, core, sid));
+                events_push(ev, nheap, hmin, tailmin, rel, pack_service(row, start, n, core, sid), (unsigned)br);
             }
             cnt[1] += 1; cnt[3] += 1;                        // services_accepted (+episode)
             if (KIND != ORLG_RWA) { cnt[5] += br; cnt[7] += br; }   // bit_rate_provisioned (+episode)
@@ -438,8 +478,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
 #pragma unroll
                 for (int q = 0; q < 8; q++) io.info[(size_t)env * 8 + q] = cnt[q];
             }
-            if (do_stats) {                                     // rmsa_env.py:229-264
-                p.sum_nh[env] = snh;
+            if (info_stats) {                                   // rmsa_env.py:229-264
                 const double cur = network_compactness(p, env, snh);
                 double *so = p.stats_out + (size_t)env * 4;
                 so[0] = cur;
@@ -450,9 +489,13 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
         }
     }
 
-    if (mode == MODE_FULL_RESET && p.stats && (KIND == ORLG_RMSA || KIND == ORLG_DEEPRMSA)) {
-        for (int l = 0; l < p.E; l++) { p.link_util[(size_t)l * p.n + env] = 0.0; p.link_comp[(size_t)l * p.n + env] = 0.0; p.link_last[(size_t)l * p.n + env] = 0.0; }
-        p.sum_nh[env] = 0;
+    if (mode == MODE_FULL_RESET && p.stats) {
+        for (int l = 0; l < p.E; l++) {
+            const size_t i = (size_t)l * p.n + env;
+            p.link_util[i] = 0.0; p.link_comp[i] = 0.0; p.link_last[i] = 0.0; p.link_frag[i] = 0.0;
+        }
+        p.sum_nh[env] = 0; p.run_br[env] = 0;
+        for (int q = 0; q < 3; q++) p.graph_stats[(size_t)q * p.n + env] = 0.0;
     }
 
     if (mode == MODE_STEP || mode == MODE_FULL_RESET) {
@@ -481,22 +524,25 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
             cnt[4] += br; cnt[6] += br;                       // rmcsa_env.py:730-731
         }
         // release every service whose time has come (rmsa_env.py:591-597)
-        if (p.stats && (KIND == ORLG_RMSA || KIND == ORLG_DEEPRMSA)) {
+        if (p.stats) {
             // the reference releases in heap order (by time) and every release updates the float statistics of
             // its links, so the due services are collected, sorted by release time and applied in that order
             constexpr int MAXR = 24;
             double rt[MAXR];
             unsigned long long rp[MAXR];
             int nr = 0;
-            events_release(ev, nheap, hmin, tailmin, now, apply_timed([&](unsigned long long pl, double t) {
+            long long rel_br = 0;                                // bit rates leaving graph["running_services"]
+            events_release(ev, nheap, hmin, tailmin, now, apply_timed([&](unsigned long long pl, double t, unsigned sbr) {
+                rel_br += sbr;
                 if (nr < MAXR) { rt[nr] = t; rp[nr] = pl; nr++; }
                 else {                                           // overflow: masks stay exact, statistics order is not
                     err |= ORLG_ERR_STATS_ORDER;
                     const int rs = svc_start(pl);
-                    path_update_stats(p, env, svc_row(pl), bits_range(rs, rs + svc_slots(pl)), true, now);
+                    path_update_stats(p, env, svc_row(pl), svc_core(pl), bits_range(rs, rs + svc_slots(pl)), true, now);
                     p.sum_nh[env] -= (long long)svc_slots(pl) * meta_hops(p.path_meta[svc_row(pl)]);
                 }
             }));
+            if (rel_br) p.run_br[env] -= rel_br;
             for (int a = 1; a < nr; a++) {                       // insertion sort by release time
                 const double t = rt[a];
                 const unsigned long long q = rp[a];
@@ -508,7 +554,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const Params p, cons
             for (int a = 0; a < nr; a++) {
                 const unsigned long long pl = rp[a];
                 const int rs = svc_start(pl);
-                path_update_stats(p, env, svc_row(pl), bits_range(rs, rs + svc_slots(pl)), true, now);
+                path_update_stats(p, env, svc_row(pl), svc_core(pl), bits_range(rs, rs + svc_slots(pl)), true, now);
                 snh -= (long long)svc_slots(pl) * meta_hops(p.path_meta[svc_row(pl)]);
             }
             p.sum_nh[env] = snh;
@@ -833,6 +879,20 @@ __global__ void export_kernel(const Params p, unsigned *masks_out, int *alloc_ou
     }
     if (sid_out) sid_out[env] = (int)p.cur_req[env].y;
     if (err_out) err_out[env] = p.errors[env];
+}
+
+// row f1 read-out: the statistics the reference keeps on the topology graph.  link_out [n][E][3] = utilization,
+// external_fragmentation, compactness per link index; graph_out [n][2] = throughput, compactness
+__global__ void link_stats_kernel(const Params p, double *link_out, double *graph_out) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.n) return;
+    if (link_out)
+        for (int l = 0; l < p.E; l++) {
+            const size_t i = (size_t)l * p.n + env;
+            double *o = link_out + ((size_t)env * p.E + l) * 3;
+            o[0] = p.link_util[i]; o[1] = p.link_frag[i]; o[2] = p.link_comp[i];
+        }
+    if (graph_out) { graph_out[2 * (size_t)env] = p.graph_stats[env]; graph_out[2 * (size_t)env + 1] = p.graph_stats[(size_t)p.n + env]; }
 }
 
 // info["bit_rate_blocking_<rate>"] and info["fairness"] (rmsa_env.py:217-227, 268-273) as the reference sees them when

@@ -133,7 +133,7 @@ __device__ __forceinline__ WBits<NWV> wide_path_free(const Params &p, int env, i
         for (int i = 0; i < 4; i++) {
             const uint4 *m = p.masks + mask_index(p, core * p.E + max(l[i], 0), 0, env);
 #pragma unroll
-            for (int v = 0; v < NWV; v++) x[i][v] = l[i] >= 0 ? m[v * vs] : ones;
+            for (int v = 0; v < NWV; v++) x[i][v] = l[i] >= 0 ? __ldcg(m + v * vs) : ones;
         }
 #pragma unroll
         for (int i = 0; i < 4; i++)
@@ -145,38 +145,29 @@ __device__ __forceinline__ WBits<NWV> wide_path_free(const Params &p, int env, i
     return a;
 }
 
-// _provision_path / _release_path on the masks (only the word groups the slot range touches; loads of 4 hops in flight)
+// _provision_path / _release_path on the masks: the slot range [start, start + n) of every link of the path is cleared
+// (provision) or set (release) with fire-and-forget 32-bit reductions (RED.AND / RED.OR at the L2): no mask word is LOADED for an
+// update, so a release -- whose links were last touched many steps ago, i.e. a DRAM miss per link -- costs no round trip at
+// all, and updates of different services commute.  Every mask READ of these kernels bypasses the L1 (__ldcg), so a thread
+// that reads a link after updating it (DeepRMSA's observation) sees its own reductions.
 template <int NWV>
 __device__ __forceinline__ void wide_path_update(const Params &p, int env, int row, int core, int start, int n, bool set) {
-    const WBits<NWV> rm = wb_range<NWV>(start, start + n);
-    bool touch[NWV];
-#pragma unroll
-    for (int v = 0; v < NWV; v++) touch[v] = (rm.w[4 * v] | rm.w[4 * v + 1] | rm.w[4 * v + 2] | rm.w[4 * v + 3]) != 0u;
     const int h0 = p.path_link_ptr[row], h1 = p.path_link_ptr[row + 1];
+    const int w0 = start >> 5, w1 = (start + n - 1) >> 5;          // 32-bit words the range touches (n >= 1)
     const size_t vs = p.wstride ? 1 : (size_t)p.n;
     for (int h = h0; h < h1; h += 4) {
         int l[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) l[i] = h + i < h1 ? (int)p.path_links16[h + i] : -1;
-        uint4 x[4][NWV];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const uint4 *m = p.masks + mask_index(p, core * p.E + max(l[i], 0), 0, env);
-#pragma unroll
-            for (int v = 0; v < NWV; v++)
-                if (l[i] >= 0 && touch[v]) x[i][v] = m[v * vs];
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            uint4 *m = p.masks + mask_index(p, core * p.E + max(l[i], 0), 0, env);
-#pragma unroll
-            for (int v = 0; v < NWV; v++) {
-                if (l[i] >= 0 && touch[v]) {
-                    uint4 y = x[i][v];
-                    if (set) { y.x |= rm.w[4 * v]; y.y |= rm.w[4 * v + 1]; y.z |= rm.w[4 * v + 2]; y.w |= rm.w[4 * v + 3]; }
-                    else { y.x &= ~rm.w[4 * v]; y.y &= ~rm.w[4 * v + 1]; y.z &= ~rm.w[4 * v + 2]; y.w &= ~rm.w[4 * v + 3]; }
-                    m[v * vs] = y;
-                }
+            if (l[i] < 0) continue;
+            unsigned *m = reinterpret_cast<unsigned *>(p.masks + mask_index(p, core * p.E + l[i], 0, env));
+            for (int w = w0; w <= w1; w++) {
+                const int lo = max(start - 32 * w, 0), hi = min(start + n - 32 * w, 32);
+                const unsigned bits = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+                unsigned *addr = m + ((size_t)(w >> 2) * vs) * 4 + (w & 3);
+                if (set) atomicOr(addr, bits); else atomicAnd(addr, ~bits);
             }
         }
     }
@@ -185,8 +176,10 @@ __device__ __forceinline__ void wide_path_update(const Params &p, int env, int r
 __device__ __forceinline__ int wide_nslots(const Params &p, int se, int br) { return p.nslots[se * (p.br_max + 1) + br]; }
 
 // heuristic action sources for the wide layout: the action of env's pending request (src, dst, br) into a[0..3]
+// Returns true when the action is KNOWN to fit (it was derived from the path's free mask just now), so that the fused step
+// does not have to read the masks a second time for is_path_free.
 template <int KIND, int NWV>
-__device__ __forceinline__ void wide_heuristic(const Params &p, const int env, const int which, const int src, const int dst, const int br, int *a) {
+__device__ __forceinline__ bool wide_heuristic(const Params &p, const int env, const int which, const int src, const int dst, const int br, int *a) {
     const int pair = src * p.N + dst;
     const int first = p.pair_first[pair];
     const int npaths = min((int)p.pair_count[pair], p.k);
@@ -197,6 +190,7 @@ __device__ __forceinline__ void wide_heuristic(const Params &p, const int env, c
             for (int q = 0; q < npaths; q++)
                 if (p.cand16[(size_t)env * p.cand_stride + q * p.J] != 0xFFFFu) { act = q * p.J; break; }
         a[0] = act;
+        return false;
     } else if (KIND == ORLG_RMSA) {
         int ap = p.k, as = p.S, max_free = 0;
         const int np_ = (which == ORLG_HEUR_SP_FF) ? min(npaths, 1) : npaths;
@@ -216,6 +210,7 @@ __device__ __forceinline__ void wide_heuristic(const Params &p, const int env, c
             }
         }
         a[0] = ap; a[1] = as;
+        return ap < p.k;
     } else if (KIND == ORLG_RWA) {
         int ap = p.k, as = p.S;
         if (which == ORLG_HEUR_SP_FF) {
@@ -247,6 +242,7 @@ __device__ __forceinline__ void wide_heuristic(const Params &p, const int env, c
             }
         }
         a[0] = ap; a[1] = as;
+        return ap < p.k;
     } else {
         int a0 = p.k, a1 = p.M, a2 = p.C, a3 = p.S;
         bool found = false;
@@ -263,6 +259,7 @@ __device__ __forceinline__ void wide_heuristic(const Params &p, const int env, c
             }
         }
         a[0] = a0; a[1] = a1; a[2] = a2; a[3] = a3;
+        return found;
     }
 }
 
@@ -278,11 +275,13 @@ __global__ void heuristic_wide_kernel(const Params p, const int which, int *acti
     for (int i = 0; i < AD; i++) actions[AD * env + i] = a[i];
 }
 
+// Launch shape, A/B-ed on the B200 (profiles/r2_experiments.md): 64-thread CTAs, 8 per SM (128 registers per thread, 16 warps per
+// SM); 128 x 3, 128 x 4 and 64 x 6 are within 3 % of it -- the kernel is bound by its dependent loads, not by occupancy.
 #ifndef ORLG_WIDE_THREADS
-#define ORLG_WIDE_THREADS 128
+#define ORLG_WIDE_THREADS 64
 #endif
 #ifndef ORLG_WIDE_MIN_BLOCKS
-#define ORLG_WIDE_MIN_BLOCKS 4        // 128 registers per thread: 16 warps per SM instead of 12 (the kernel is latency-bound)
+#define ORLG_WIDE_MIN_BLOCKS 8
 #endif
 template <int KIND, int NWV>
 __global__ void __launch_bounds__(ORLG_WIDE_THREADS, ORLG_WIDE_MIN_BLOCKS) step_wide_kernel(const Params p, const StepIO io, const int mode) {
@@ -323,8 +322,9 @@ __global__ void __launch_bounds__(ORLG_WIDE_THREADS, ORLG_WIDE_MIN_BLOCKS) step_
         int row = -1, start = 0, n = 0, core = 0, mod = -1;
         constexpr int AD = KIND == ORLG_DEEPRMSA ? 1 : (KIND == ORLG_RMCSA ? 4 : 2);
         int act[4];
+        bool known_free = false;
         if (io.policy >= 0) {                                // fused rollout step: action = heuristic(env), no second launch, and
-            wide_heuristic<KIND, NWV>(p, env, io.policy, src, dst, br, act);      // the path's masks are in L1 / L2 for what follows
+            known_free = wide_heuristic<KIND, NWV>(p, env, io.policy, src, dst, br, act);      // the path's masks are in L1 / L2 for what follows
             if (io.actions_out) {
 #pragma unroll
                 for (int i = 0; i < AD; i++) io.actions_out[AD * env + i] = act[i];
@@ -355,7 +355,8 @@ __global__ void __launch_bounds__(ORLG_WIDE_THREADS, ORLG_WIDE_MIN_BLOCKS) step_
                     row = first + path;
                     n = (KIND == ORLG_RWA) ? 1 : wide_nslots(p, meta_se(p.path_meta[row]), br);
                     start = slot;
-                    if (start + n <= p.S) accepted = wb_contains(wide_path_free<NWV>(p, env, row, 0), wb_range<NWV>(start, start + n));
+                    if (known_free) accepted = true;
+                    else if (start + n <= p.S) accepted = wb_contains(wide_path_free<NWV>(p, env, row, 0), wb_range<NWV>(start, start + n));
                 } else err |= ORLG_ERR_NO_SUCH_PATH;
             }
         } else {
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(ORLG_WIDE_THREADS, ORLG_WIDE_MIN_BLOCKS) step_
                     n = wide_nslots(p, p.mod_se[am], br);
                     start = slot; core = ac; mod = am;
                     if (start + n <= p.S)
-                        accepted = wb_contains(wide_path_free<NWV>(p, env, row, core), wb_range<NWV>(start, start + n)) &&
+                        accepted = (known_free || wb_contains(wide_path_free<NWV>(p, env, row, core), wb_range<NWV>(start, start + n))) &&
                                    (p.path_length[row] < p.reach[am * (p.br_max + 1) + br]);
                 } else err |= ORLG_ERR_NO_SUCH_PATH;
             }

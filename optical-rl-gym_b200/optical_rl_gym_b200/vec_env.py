@@ -241,9 +241,12 @@ class OpticalVecEnv:
         self._trace = None
         # float statistics of info (network / link compactness, utilisation): opt-in, uses the generic kernel
         self._stats = None
-        if link_stats:
+        self._link_stats = bool(link_stats)
+        if link_stats and env_id in ("RMSA-v0", "DeepRMSA-v0"):
             self._stats = torch.zeros((n, 4), dtype=torch.float64, device=dev)
             nat.check(self._lib.orlg_enable_stats(self._h, _ptr(self._stats)))
+        elif link_stats:        # RWA / RMCSA: no float statistics in info, but the graph attributes are kept (graph_statistics())
+            nat.check(self._lib.orlg_enable_link_stats(self._h, 1))
         # discrete bit-rate selection: per-bit-rate blocking + fairness of `info` (rmsa_env.py:217-227, 268-273)
         self._brb = None
         nb = self._lib.orlg_num_bit_rates(self._h)
@@ -524,6 +527,17 @@ class OpticalVecEnv:
         nh = torch.empty(n, dtype=torch.int32, device=dev)
         nat.check(self._lib.orlg_export_state(self._h, _ptr(m), _ptr(al), _ptr(now), _ptr(nh), self._stream()))
         return m, al, now, nh
+
+    def graph_statistics(self):
+        """The time-averaged statistics the reference keeps on ``env.topology`` (needs ``link_stats=True``): ``(link, graph)`` with
+        ``link`` float64 [N, E, 3] = each link's ``utilization``, ``external_fragmentation``, ``compactness`` by link index
+        (``topology[n1][n2][...]``; rmsa_env.py:464-543, rmcsa_env.py:591-688, RWA: utilization only, rwa_env.py:365-383) and
+        ``graph`` float64 [N, 2] = ``topology.graph["throughput"]``, ``["compactness"]`` (rmsa_env.py:439-462)."""
+        assert self._link_stats, "construct the env with link_stats=True"
+        link = torch.empty((self.num_envs, self.tables.num_links, 3), dtype=torch.float64, device=self.device)
+        graph = torch.empty((self.num_envs, 2), dtype=torch.float64, device=self.device)
+        nat.check(self._lib.orlg_link_stats(self._h, _ptr(link), _ptr(graph), self._stream()))
+        return link, graph
 
     def available_slots(self):
         """``topology.graph['available_slots']`` of every env: uint8 [N, C*E, S] (1 = free)."""

@@ -66,6 +66,8 @@ def lib():
         L.oracle_get_counters.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_get_bit_rate_blocking.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_get_action_probability.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_get_link_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_get_link_stats.restype = None
         L.oracle_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 4
         L.oracle_error.argtypes = [C.c_void_p]
         L.oracle_error.restype = C.c_int
@@ -206,6 +208,14 @@ class OracleEnv:
         out = np.zeros(R + Cn, np.float64)
         self.L.oracle_get_action_probability(self.h, _ptr(out))
         return out[:R].copy(), out[R:].copy()
+
+    def link_stats(self):
+        """Row f1 graph attributes: (per link [E, 3] = utilization, external_fragmentation, compactness; [2] = graph throughput,
+        compactness) as of now."""
+        link = np.zeros((self.cfg.num_links, 3), np.float64)
+        graph = np.zeros(2, np.float64)
+        self.L.oracle_get_link_stats(self.h, _ptr(link), _ptr(graph))
+        return link, graph
 
     def state(self):
         avail = np.zeros(self.cells, np.int8)

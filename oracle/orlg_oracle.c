@@ -89,6 +89,9 @@ typedef struct {
     int error;
     /* float statistics of row f1 (rmsa_env.py:439-543, 699-744) */
     double *link_util, *link_comp, *link_last;   /* [E] time-averaged utilisation / compactness, last update time */
+    double *link_frag;                            /* [E] time-averaged external fragmentation (rmsa_env.py:487-524) */
+    double g_thr, g_comp, g_last;                 /* topology.graph["throughput" / "compactness" / "last_update"] (rmsa_env.py:439-462) */
+    long run_br;                                  /* sum of bit_rate over graph["running_services"] */
     long sum_nh;                                  /* sum over running services of number_slots * hops */
     /* discrete bit-rate selection (rmsa_env.py:88-110): bit_rate_requested_histogram / bit_rate_provisioned_histogram,
        and what step() derives from them for `info` (rmsa_env.py:217-227, 268-273) */
@@ -280,67 +283,96 @@ static int is_path_free(const oenv_t *e, int row, int core, int initial_slot, in
 static int rle(const int8_t *a, int n, int *starts, int *values, int *lengths);
 
 /* rmsa_env.py:651-665 on one link row */
-static int rle_link(const oenv_t *e, int l, int lo, int hi, int *starts, int *values, int *lengths) {
+static int rle_link(const oenv_t *e, int core, int l, int lo, int hi, int *starts, int *values, int *lengths) {
     int8_t row[1024];
-    for (int s = lo; s < hi; s++) row[s - lo] = AV(e, 0, l, s);
+    for (int s = lo; s < hi; s++) row[s - lo] = AV(e, core, l, s);
     return rle(row, hi - lo, starts, values, lengths);
 }
 
-/* rmsa_env.py:464-543 (_update_link_stats), utilisation and compactness */
-static void update_link_stats(oenv_t *e, int l) {
+/* _update_link_stats: rmsa_env.py:464-543, rmcsa_env.py:591-688 (the slot row of the core being touched; the statistics are per
+   LINK, shared by the cores), rwa_env.py:365-383 (utilisation only) */
+static void update_link_stats(oenv_t *e, int core, int l) {
     int S = e->c.num_slots;
     double last_update = e->link_last[l];
     double time_diff = e->now - e->link_last[l];
     if (e->now > 0) {
         double last_util = e->link_util[l];
         long free_sum = 0;
-        for (int s = 0; s < S; s++) free_sum += AV(e, 0, l, s);
+        for (int s = 0; s < S; s++) free_sum += AV(e, core, l, s);
         double cur_util = (double)(S - free_sum) / (double)S;
         e->link_util[l] = ((last_util * last_update) + (cur_util * time_diff)) / e->now;
-        double last_compactness = e->link_comp[l];
-        double cur_link_compactness = 0.0;
-        if (free_sum > 0) {
-            int st[1024], va[1024], le[1024];
-            int nr = rle_link(e, l, 0, S, st, va, le);
-            int n_used = 0, first = -1, last = -1;
-            for (int r = 0; r < nr; r++) if (va[r] == 0) { if (first < 0) first = r; last = r; n_used++; }
-            if (n_used > 1) {
-                int lambda_min = st[first], lambda_max = st[last] + le[last];
-                int st2[1024], va2[1024], le2[1024];
-                int nr2 = rle_link(e, l, lambda_min, lambda_max, st2, va2, le2);
-                long unused_spectrum_slots = 0;                 /* np.sum(1 - internal_values) */
-                for (int r = 0; r < nr2; r++) unused_spectrum_slots += 1 - va2[r];
-                if (unused_spectrum_slots > 0)
-                    cur_link_compactness = ((double)(lambda_max - lambda_min) / (double)(S - free_sum)) *
-                                           (1 / (double)unused_spectrum_slots);
-                else cur_link_compactness = 1.0;
-            } else cur_link_compactness = 1.0;
+        if (e->c.kind != KIND_RWA) {
+            double last_external_fragmentation = e->link_frag[l];
+            double last_compactness = e->link_comp[l];
+            double cur_external_fragmentation = 0.0;
+            double cur_link_compactness = 0.0;
+            if (free_sum > 0) {
+                int st[1024], va[1024], le[1024];
+                int nr = rle_link(e, core, l, 0, S, st, va, le);
+                /* unused_blocks = indices of the free runs; max_empty stays 0 for fewer than two of them, and when they are
+                   exactly the first and the last block of the link (unused_blocks != [0, len(values) - 1]) */
+                int n_unused = 0, u_first = -1, u_last = -1, longest = 0;
+                for (int r = 0; r < nr; r++) if (va[r] == 1) { if (u_first < 0) u_first = r; u_last = r; n_unused++; if (le[r] > longest) longest = le[r]; }
+                int max_empty = 0;
+                if (n_unused > 1 && !(n_unused == 2 && u_first == 0 && u_last == nr - 1)) max_empty = longest;
+                cur_external_fragmentation = 1.0 - ((double)max_empty / (double)free_sum);
+                int n_used = 0, first = -1, last = -1;
+                for (int r = 0; r < nr; r++) if (va[r] == 0) { if (first < 0) first = r; last = r; n_used++; }
+                if (n_used > 1) {
+                    int lambda_min = st[first], lambda_max = st[last] + le[last];
+                    int st2[1024], va2[1024], le2[1024];
+                    int nr2 = rle_link(e, core, l, lambda_min, lambda_max, st2, va2, le2);
+                    long unused_spectrum_slots = 0;                 /* np.sum(1 - internal_values) */
+                    for (int r = 0; r < nr2; r++) unused_spectrum_slots += 1 - va2[r];
+                    if (unused_spectrum_slots > 0)
+                        cur_link_compactness = ((double)(lambda_max - lambda_min) / (double)(S - free_sum)) *
+                                               (1 / (double)unused_spectrum_slots);
+                    else cur_link_compactness = 1.0;
+                } else cur_link_compactness = 1.0;
+            }
+            e->link_frag[l] = ((last_external_fragmentation * last_update) + (cur_external_fragmentation * time_diff)) / e->now;
+            e->link_comp[l] = ((last_compactness * last_update) + (cur_link_compactness * time_diff)) / e->now;
         }
-        e->link_comp[l] = ((last_compactness * last_update) + (cur_link_compactness * time_diff)) / e->now;
     }
     e->link_last[l] = e->now;
 }
 
-/* rmsa_env.py:699-744 (_get_network_compactness) */
-static double network_compactness(const oenv_t *e) {
+/* _get_network_compactness: rmsa_env.py:699-744; rmcsa_env.py:825-871 looks at the links of ONE core (but sums
+   number_slots * hops over all running services) */
+static double network_compactness_core(const oenv_t *e, int core) {
     int S = e->c.num_slots;
     long sum_occupied = 0, sum_unused_spectrum_blocks = 0;
     for (int l = 0; l < e->c.num_links; l++) {
         int st[1024], va[1024], le[1024];
-        int nr = rle_link(e, l, 0, S, st, va, le);
+        int nr = rle_link(e, core, l, 0, S, st, va, le);
         int n_used = 0, first = -1, last = -1;
         for (int r = 0; r < nr; r++) if (va[r] == 0) { if (first < 0) first = r; last = r; n_used++; }
         if (n_used > 1) {
             int lambda_min = st[first], lambda_max = st[last] + le[last];
             sum_occupied += lambda_max - lambda_min;
             int st2[1024], va2[1024], le2[1024];
-            int nr2 = rle_link(e, l, lambda_min, lambda_max, st2, va2, le2);
+            int nr2 = rle_link(e, core, l, lambda_min, lambda_max, st2, va2, le2);
             for (int r = 0; r < nr2; r++) sum_unused_spectrum_blocks += va2[r];
         }
     }
     if (sum_unused_spectrum_blocks > 0)
         return ((double)sum_occupied / (double)e->sum_nh) * ((double)e->c.num_links / (double)sum_unused_spectrum_blocks);
     return 1.0;
+}
+static double network_compactness(const oenv_t *e) { return network_compactness_core(e, 0); }
+
+/* _update_network_stats (rmsa_env.py:439-462, rmcsa_env.py:560-589; a no-op in rwa_env.py:351-363): called by
+   _provision_path only, after the new service joined graph["running_services"] */
+static void update_network_stats(oenv_t *e, int core) {
+    double last_update = e->g_last;
+    double time_diff = e->now - last_update;
+    if (e->now > 0) {
+        double last_throughput = e->g_thr, last_compactness = e->g_comp;
+        double cur_throughput = (double)e->run_br;          /* 0.0 + integer bit rates: exact */
+        e->g_thr = ((last_throughput * last_update) + (cur_throughput * time_diff)) / e->now;
+        e->g_comp = ((last_compactness * last_update) + (network_compactness_core(e, core) * time_diff)) / e->now;
+    }
+    e->g_last = e->now;
 }
 
 /* np.mean of a float64 list: numpy's pairwise summation (8 partial sums for n <= 128, recursive above) / n */
@@ -370,10 +402,12 @@ static void provision(oenv_t *e, int row, int core, int initial_slot, int n) {
     for (int h = e->t.path_link_ptr[row]; h < e->t.path_link_ptr[row + 1]; h++) {
         int l = e->t.path_links[h];
         for (int s = initial_slot; s < initial_slot + n; s++) { AV(e, core, l, s) = 0; AL(e, core, l, s) = e->cur.id; }
-        if (e->c.stats && (e->c.kind == KIND_RMSA || e->c.kind == KIND_DEEPRMSA)) update_link_stats(e, l);
+        if (e->c.stats) update_link_stats(e, core, l);
     }
     e->sum_nh += (long)n * (e->t.path_link_ptr[row + 1] - e->t.path_link_ptr[row]);
+    e->run_br += e->cur.bit_rate;
     e->cur.path_row = row; e->cur.initial_slot = initial_slot; e->cur.number_slots = n; e->cur.core = core;
+    if (e->c.stats && e->c.kind != KIND_RWA) update_network_stats(e, core);
 }
 
 /* rmsa_env.py:417-437 */
@@ -381,8 +415,9 @@ static void release(oenv_t *e, const service_t *s) {
     for (int h = e->t.path_link_ptr[s->path_row]; h < e->t.path_link_ptr[s->path_row + 1]; h++) {
         int l = e->t.path_links[h];
         for (int k = s->initial_slot; k < s->initial_slot + s->number_slots; k++) { AV(e, s->core, l, k) = 1; AL(e, s->core, l, k) = -1; }
-        if (e->c.stats && (e->c.kind == KIND_RMSA || e->c.kind == KIND_DEEPRMSA)) update_link_stats(e, l);
+        if (e->c.stats) update_link_stats(e, s->core, l);
     }
+    e->run_br -= s->bit_rate;
     e->sum_nh -= (long)s->number_slots * (e->t.path_link_ptr[s->path_row + 1] - e->t.path_link_ptr[s->path_row]);
 }
 
@@ -502,6 +537,7 @@ void *oracle_create(const ocfg_t *cfg, const otab_t *tab) {
     e->link_util = (double *)calloc((size_t)cfg->num_links, sizeof(double));
     e->link_comp = (double *)calloc((size_t)cfg->num_links, sizeof(double));
     e->link_last = (double *)calloc((size_t)cfg->num_links, sizeof(double));
+    e->link_frag = (double *)calloc((size_t)cfg->num_links, sizeof(double));
     size_t cells = (size_t)cfg->num_cores * cfg->num_links * cfg->num_slots;
     e->avail = (int8_t *)malloc(cells);
     e->alloc = (int32_t *)malloc(cells * sizeof(int32_t));
@@ -525,13 +561,14 @@ void *oracle_create_shared(const ocfg_t *cfg, const otab_t *tab) {
     e->link_util = (double *)calloc((size_t)cfg->num_links, sizeof(double));
     e->link_comp = (double *)calloc((size_t)cfg->num_links, sizeof(double));
     e->link_last = (double *)calloc((size_t)cfg->num_links, sizeof(double));
+    e->link_frag = (double *)calloc((size_t)cfg->num_links, sizeof(double));
     return e;
 }
 
 void oracle_destroy(void *p) {
     oenv_t *e = (oenv_t *)p;
     for (int i = 0; i < e->nown; i++) free(e->own[i]);
-    free(e->avail); free(e->alloc); free(e->heap); free(e->link_util); free(e->link_comp); free(e->link_last); free(e);
+    free(e->avail); free(e->alloc); free(e->heap); free(e->link_util); free(e->link_comp); free(e->link_last); free(e->link_frag); free(e);
 }
 
 void oracle_set_trace(void *p, const double *arr, const double *hold, const int32_t *src, const int32_t *dst,
@@ -562,7 +599,8 @@ void oracle_reset(void *p, int full) {
     memset(e->hist_req, 0, sizeof(e->hist_req)); memset(e->hist_prov, 0, sizeof(e->hist_prov));   /* rmsa_env.py:348-349 */
     memset(e->act_rows, 0, sizeof(e->act_rows)); memset(e->act_cols, 0, sizeof(e->act_cols)); e->act_total = 0;   /* rwa_env.py:195-201 */
     e->sum_nh = 0;
-    for (int l = 0; l < e->c.num_links; l++) { e->link_util[l] = 0.0; e->link_comp[l] = 0.0; e->link_last[l] = 0.0; }
+    e->run_br = 0; e->g_thr = 0.0; e->g_comp = 0.0; e->g_last = 0.0;
+    for (int l = 0; l < e->c.num_links; l++) { e->link_util[l] = 0.0; e->link_comp[l] = 0.0; e->link_last[l] = 0.0; e->link_frag[l] = 0.0; }
     size_t cells = (size_t)e->c.num_cores * e->c.num_links * e->c.num_slots;
     memset(e->avail, 1, cells);
     for (size_t i = 0; i < cells; i++) e->alloc[i] = -1;
@@ -898,6 +936,14 @@ void oracle_get_state(void *p, int8_t *avail, int32_t *alloc, double *now, int32
     if (alloc) memcpy(alloc, e->alloc, cells * sizeof(int32_t));
     if (now) *now = e->now;
     if (nheap) *nheap = e->nheap;
+}
+
+/* graph attributes of row f1: link [E][3] = utilization, external_fragmentation, compactness (link index order);
+   graph [2] = throughput, compactness */
+void oracle_get_link_stats(void *p, double *link, double *graph) {
+    oenv_t *e = (oenv_t *)p;
+    for (int l = 0; l < e->c.num_links; l++) { link[3 * l] = e->link_util[l]; link[3 * l + 1] = e->link_frag[l]; link[3 * l + 2] = e->link_comp[l]; }
+    graph[0] = e->g_thr; graph[1] = e->g_comp;
 }
 
 int oracle_error(void *p) { return ((oenv_t *)p)->error; }

@@ -166,6 +166,7 @@ def record(kind, env_args, policy, n_envs, T, seed0, n_mask_envs=1):
             put("req_id", i, t, s.service_id, (n_envs, T + 1), np.int32)
 
         obs = env.reset()
+        stats_slot = {}
         put_req(0)
         if kind == "DeepRMSA-v0":
             put("obs", i, 0, obs, (n_envs, T + 1, len(obs)), np.float64)
@@ -196,6 +197,21 @@ def record(kind, env_args, policy, n_envs, T, seed0, n_mask_envs=1):
                 elif key in ("path_action_probability", "wavelength_action_probability"):      # rwa_env.py:148-151
                     val = np.asarray(val, np.float64)
                     put("info_" + key, i, t, val, (n_envs, T, len(val)), np.float64)
+            if i < n_mask_envs and (t < 48 or t % 16 == 15 or t == T - 1):
+                # row f1: the time-averaged statistics the reference keeps ON the topology graph (never returned by step):
+                # per link utilization / external_fragmentation / compactness (rmsa_env.py:464-543, rmcsa_env.py:591-688,
+                # rwa_env.py:365-383) and the graph's throughput / compactness (rmsa_env.py:439-462, rmcsa_env.py:560-589),
+                # by link index; snapshots after steps 0..47, then every 16th (running averages: any error persists)
+                ls = np.zeros((E, 3), np.float64)
+                for n1, n2 in env.topology.edges():
+                    d = env.topology[n1][n2]
+                    ls[d["index"]] = (d.get("utilization", 0.0), d.get("external_fragmentation", 0.0), d.get("compactness", 0.0))
+                ts = stats_slot.setdefault(t, len(stats_slot))
+                n_snap = 48 + len([x for x in range(48, T) if x % 16 == 15 or x == T - 1])
+                put("graph_link_stats", i, ts, ls, (n_mask_envs, n_snap, E, 3), np.float64)
+                put("graph_stats", i, ts, (env.topology.graph.get("throughput", 0.0), env.topology.graph.get("compactness", 0.0)),
+                    (n_mask_envs, n_snap, 2), np.float64)
+                put("graph_stats_step", 0, ts, t, (1, n_snap), np.int32)
             if i < n_mask_envs:
                 bits = np.packbits(avail_of(env, kind).reshape(Cc * E, S).astype(np.uint8), axis=1, bitorder="little")
                 put("avail_bits", i, t, bits, (n_mask_envs, T, Cc * E, bits.shape[1]), np.uint8)

@@ -364,6 +364,31 @@ def test_info_float_statistics_bit_exact(name):
     env.close()
 
 
+@pytest.mark.parametrize("name", helpers.golden_names())
+def test_graph_statistics_bit_exact(name):
+    """Row f1, all four env kinds: the time-averaged statistics the reference keeps on the topology graph -- per link utilization /
+    external_fragmentation / compactness (rmsa_env.py:464-543, rmcsa_env.py:591-688, rwa_env.py:365-383) and the graph's
+    throughput / compactness (rmsa_env.py:439-462, rmcsa_env.py:560-589) -- float64, bit-identical to the values recorded from
+    the live reference at ~140 snapshot steps of env 0."""
+    g = helpers.load_golden(name)
+    meta = g["meta"]
+    n, T = meta["n_envs"], meta["T"]
+    env = make_env(meta, n, link_stats=True)
+    env.set_trace(g["req_arrival"], g["req_holding"], g["req_src"], g["req_dst"], g["req_bit_rate"])
+    env.reset(full=True)
+    env.reset(full=False)
+    snap = {int(t): k for k, t in enumerate(g["graph_stats_step"][0])}
+    for t in range(T):
+        env.step(torch.as_tensor(g["actions"][:, t], device="cuda"))
+        if t in snap:
+            link, graph = env.graph_statistics()
+            assert np.array_equal(link[0].cpu().numpy(), g["graph_link_stats"][0, snap[t]]), ("link statistics", t)
+            assert np.array_equal(graph[0].cpu().numpy(), g["graph_stats"][0, snap[t]]), ("graph statistics", t)
+    assert np.array_equal(env.available_slots().cpu().numpy().reshape(g["final_avail"].shape), g["final_avail"])
+    assert int(env.error_flags().abs().sum()) == 0
+    env.close()
+
+
 # ------------------------------------------------------------------ ragged batches and boundary sizes
 @pytest.mark.parametrize("kind,n_envs,env_args", [
     ("DeepRMSA-v0", 1, dict(episode_length=20)),                                   # a single env

@@ -17,6 +17,7 @@ def replay(g, i, use_heuristic=False):
     e.reset(full=False)         # evaluate_heuristic's reset() before the first episode
     hid = helpers.HEURISTIC_ID.get(meta["policy"]) if use_heuristic else None
     Cc, E, S = e.cells
+    snap = {int(t): k for k, t in enumerate(g["graph_stats_step"][0])}
     for t in range(T):
         r = e.request()
         assert r["arrival"] == g["req_arrival"][i, t] and r["src"] == g["req_src"][i, t]
@@ -58,6 +59,10 @@ def replay(g, i, use_heuristic=False):
             for b, rate in enumerate(helpers.sim_kwargs(meta)["bit_rates"]):
                 assert brb[b] == g["info_bit_rate_blocking_%d" % rate][i, t], ("bit_rate_blocking", rate, t)
             assert brb[-1] == g["info_fairness"][i, t], ("fairness", t)
+        if i < g["graph_link_stats"].shape[0] and t in snap:     # row f1: the statistics kept on the topology graph, bit-exact
+            link, graph = e.link_stats()
+            assert np.array_equal(link, g["graph_link_stats"][i, snap[t]]), ("link stats", t)
+            assert np.array_equal(graph, g["graph_stats"][i, snap[t]]), ("graph stats", t, graph, g["graph_stats"][i, snap[t]])
         if i < g["avail_bits"].shape[0] and (t % 7 == 0 or t == T - 1):
             avail = e.state()[0].reshape(Cc * E, S).astype(np.uint8)
             assert np.array_equal(np.packbits(avail, axis=1, bitorder="little"), g["avail_bits"][i, t]), ("masks", t)
