@@ -131,6 +131,11 @@ __device__ __forceinline__ void ro_tile_release(unsigned *pool_free, unsigned ti
     if (lane == 0) atomicOr(pool_free, 1u << tile);
 }
 
+constexpr int RO_SCAN = 8;          // table slots per batch of the rebuild's streaming pass
+#ifndef RO_RANK
+#define RO_RANK 2                   // entries ranked per pass of the rebuild's sort (A/B on the B200: 2 -> 15.6 us per step at 20-step
+                                    // launches, 4 -> 16.7, 8 -> 16.2, the single-entry loop 16.0: the kernel sits at its 128-register cap)
+#endif
 // Thread-per-env window rebuild on the lane-interleaved storage (every pointer already includes the lane; stride 32).
 // On entry: table = slots [0, n) (unsorted), window = win[wh, wn) (sorted), side = up to RO_SIDE entries.  Everything
 // goes back to the table, then one streaming pass moves the entries with time <= h (at most RO_WCAP) to the scratch list
@@ -142,6 +147,12 @@ __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_
                                            unsigned &n, unsigned &wh, unsigned &wn, double &tmin, double &side_min,
                                            const double h, WinEntry &head, WinEntry &nxt) {
     RPH_INIT();
+    // the streaming pass below is a chain of dependent DRAM round trips (one per 8-slot batch: the compaction stores of a
+    // batch may alias the next batch's loads, so the compiler cannot hoist them): start the first batches' lines now, and
+    // every batch asks for the lines two batches ahead
+#pragma unroll
+    for (int i = 0; i < 2 * RO_SCAN; i++)
+        if ((unsigned)i < n) { prefetch_l2(rt_t + i * 32); prefetch_l2(rt_p + i * 32); }
     for (unsigned j = wh; j < wn; j++) {                // leftover window entries
         const WinEntry w = win_load(win + j * 32);
         rt_t[n * 32] = w.t; rt_p[n * 32] = w.p; n++;
@@ -158,6 +169,9 @@ __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_
     for (unsigned s0 = 0; s0 < n; s0 += 8) {            // 16 independent (coalesced) loads per pass
         double tt[8];
         unsigned long long pp[8];
+#pragma unroll
+        for (int i = 0; i < RO_SCAN; i++)
+            if (s0 + 2 * RO_SCAN + i < n) { prefetch_l2(rt_t + (s0 + 2 * RO_SCAN + i) * 32); prefetch_l2(rt_p + (s0 + 2 * RO_SCAN + i) * 32); }
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const bool in = s0 + i < n;
@@ -181,19 +195,29 @@ __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_
     tmin = mn;
     RPH_MARK(12);                                       // rebuild: streaming pass
     head.t = ORLG_INF; nxt.t = ORLG_INF;
-    for (unsigned j = 0; j < c; j++) {                  // rank sort (c is ~15: quadratic is fine, the loads coalesce)
-        const double tj = sc_t[j * 32];
-        unsigned rank = 0;
-#pragma unroll 4
+    // rank sort, RO_RANK entries at a time in registers: one pass over the list ranks all of them (c * c compares, but only
+    // c * c / RO_RANK loads -- the loads' latency, not the compares, is what the quadratic sort costs)
+    for (unsigned j0 = 0; j0 < c; j0 += RO_RANK) {
+        double tj[RO_RANK];
+        unsigned rank[RO_RANK];
+#pragma unroll
+        for (int i = 0; i < RO_RANK; i++) { tj[i] = j0 + i < c ? sc_t[(j0 + i) * 32] : ORLG_INF; rank[i] = 0; }
+#pragma unroll 2
         for (unsigned q = 0; q < c; q++) {
             const double tq = sc_t[q * 32];
-            rank += (tq < tj || (tq == tj && q < j)) ? 1u : 0u;
+#pragma unroll
+            for (int i = 0; i < RO_RANK; i++) rank[i] += (tq < tj[i] || (tq == tj[i] && q < j0 + i)) ? 1u : 0u;
         }
-        WinEntry w;
-        w.t = tj; w.p = sc_p[j * 32];
-        win[rank * 32] = w;
-        if (rank == 0) head = w;
-        if (rank == 1) nxt = w;
+#pragma unroll
+        for (int i = 0; i < RO_RANK; i++) {
+            if (j0 + i < c) {
+                WinEntry w;
+                w.t = tj[i]; w.p = sc_p[(j0 + i) * 32];
+                win[rank[i] * 32] = w;
+                if (rank[i] == 0) head = w;
+                if (rank[i] == 1) nxt = w;
+            }
+        }
     }
     wh = 0; wn = c;
     RPH_MARK(13);                                       // rebuild: rank sort

@@ -24,9 +24,17 @@ from .wrappers import VecWrapper
 class VecMonitor(VecWrapper):
     EXT = "monitor.csv"
 
-    def __init__(self, venv, filename: Optional[str] = None, info_keywords: Sequence[str] = (), max_rows_per_flush: int = 0):
+    def __init__(self, venv, filename: Optional[str] = None, info_keywords: Sequence[str] = ()):
         super().__init__(venv)
         self.info_keywords = tuple(info_keywords)
+        if self.info_keywords:           # fail at construction, not at the first episode end
+            base0 = self.unwrapped
+            if getattr(base0, "_info", None) is None:
+                raise ValueError("info_keywords need the venv's info: construct it with collect_info=True")
+            known = set(getattr(base0, "info_keys", ()) or ())
+            missing = [k for k in self.info_keywords if known and k not in known]
+            if missing:
+                raise ValueError("info_keywords %s are not in this env's info (%s)" % (missing, sorted(known)))
         self.t_start = time.time()
         base = self.unwrapped
         n, dev = base.num_envs, base.device
@@ -35,7 +43,6 @@ class VecMonitor(VecWrapper):
         self.episode_returns, self.episode_lengths, self.episode_times = [], [], []
         self.episode_infos = {k: [] for k in self.info_keywords}
         self.total_steps = 0
-        self._max_rows = int(max_rows_per_flush)
         self._fh = None
         if filename is not None:
             if not filename.endswith(self.EXT):
@@ -67,9 +74,9 @@ class VecMonitor(VecWrapper):
             for k, c in zip(self.info_keywords, cols):
                 self.episode_infos[k].extend(c.tolist())
             if self._fh is not None:
-                rows = len(r) if not self._max_rows else min(len(r), self._max_rows)
-                for i in range(rows):
-                    self._fh.write(",".join([repr(float(r[i])), str(int(l[i])), repr(t)] + [repr(float(c[i])) for c in cols]) + "\n")
+                # every finished episode gets its row (SB3's Monitor writes one per episode): one buffered write per step
+                self._fh.write("".join(",".join([repr(float(r[i])), str(int(l[i])), repr(t)] + [repr(float(c[i])) for c in cols]) + "\n"
+                                       for i in range(len(r))))
                 self._fh.flush()
             self._ret[idx] = 0.0
             self._len[idx] = 0

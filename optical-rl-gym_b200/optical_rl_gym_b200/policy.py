@@ -29,13 +29,16 @@ class MlpPolicy(torch.nn.Module):
         self.shared_net = torch.nn.Sequential(*layers)
         self.action_net = torch.nn.Linear(d, n_actions)
         self.value_net = torch.nn.Linear(d, 1)
+        self.critic_net = None          # the critic's own trunk when the checkpoint has separate ones (SB3 >= 1.8)
 
     @classmethod
     def from_state_dict(cls, sd) -> "MlpPolicy":
         """``policy.pth`` of an SB3 ``ActorCriticPolicy`` with a shared trunk (keys ``mlp_extractor.shared_net.<2i>``)
-        or with separate actor/critic trunks (``mlp_extractor.policy_net`` / ``value_net``, SB3 >= 1.8: the actor's
-        trunk is kept)."""
-        trunk = "mlp_extractor.shared_net." if any(k.startswith("mlp_extractor.shared_net.") for k in sd) else "mlp_extractor.policy_net."
+        or with separate actor/critic trunks (``mlp_extractor.policy_net`` / ``mlp_extractor.value_net``, SB3 >= 1.8: the
+        actor's trunk becomes ``shared_net``, the critic's is kept as ``critic_net`` so that ``forward`` returns the right value;
+        the fused kernel then evaluates the actor only and its value output is not meaningful)."""
+        shared = any(k.startswith("mlp_extractor.shared_net.") for k in sd)
+        trunk = "mlp_extractor.shared_net." if shared else "mlp_extractor.policy_net."
         idx = sorted({int(k[len(trunk):].split(".")[0]) for k in sd if k.startswith(trunk)})
         widths = [sd["%s%d.weight" % (trunk, i)].shape[0] for i in idx]
         obs_dim = sd["%s%d.weight" % (trunk, idx[0])].shape[1]
@@ -47,6 +50,16 @@ class MlpPolicy(torch.nn.Module):
         for k in ("action_net.weight", "action_net.bias", "value_net.weight", "value_net.bias"):
             mine[k] = sd[k]
         pol.load_state_dict(mine)
+        vtrunk = "mlp_extractor.value_net."
+        if not shared and any(k.startswith(vtrunk) for k in sd):
+            vidx = sorted({int(k[len(vtrunk):].split(".")[0]) for k in sd if k.startswith(vtrunk)})
+            layers = []
+            for i in vidx:
+                w = sd["%s%d.weight" % (vtrunk, i)]
+                lin = torch.nn.Linear(w.shape[1], w.shape[0])
+                lin.load_state_dict({"weight": w, "bias": sd["%s%d.bias" % (vtrunk, i)]})
+                layers += [lin, torch.nn.Tanh()]
+            pol.critic_net = torch.nn.Sequential(*layers)
         return pol
 
     @classmethod
@@ -99,8 +112,10 @@ class MlpPolicy(torch.nn.Module):
     def forward(self, obs: torch.Tensor):
         """(logits [N, n_actions], value [N]) -- observations are used as they are (SB3 ``preprocess_obs`` of a
         Box space is a cast to float)."""
-        latent = self.shared_net(obs.to(self.action_net.weight.dtype))
-        return self.action_net(latent), self.value_net(latent).squeeze(-1)
+        x = obs.to(self.action_net.weight.dtype)
+        latent = self.shared_net(x)
+        latent_vf = latent if self.critic_net is None else self.critic_net(x)
+        return self.action_net(latent), self.value_net(latent_vf).squeeze(-1)
 
     @torch.no_grad()
     def act(self, obs: torch.Tensor, deterministic: bool = True, generator=None) -> torch.Tensor:

@@ -348,6 +348,14 @@ class OpticalVecEnv:
         self.step_async(actions)
         return self.step_wait()
 
+    @property
+    def info_keys(self):
+        """The keys ``info`` carries for this env and configuration (empty with ``collect_info=False``)."""
+        if self._info is None:
+            return []
+        return StepInfo(self._info, self.metadata["metrics"], self._stats, self._brb, self.bit_rates, self._ap,
+                        self.k_paths + self.reject_action).keys()
+
     def step_raw(self, actions_i32: torch.Tensor):
         """Hot-loop variant: ``actions_i32`` must already be a contiguous int32 CUDA tensor ``[N, action_dim]``."""
         rc = self._lib.orlg_step(self._h, C.c_void_p(actions_i32.data_ptr()), *self._out_ptrs, self._stream())

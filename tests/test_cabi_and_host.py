@@ -136,3 +136,72 @@ def test_integration_md_stub_matches_the_header_structs():
         assert C.sizeof(doc) == C.sizeof(real), name
         for f in real._fields_:
             assert getattr(doc, f[0]).offset == getattr(real, f[0]).offset, (name, f[0])
+
+
+def test_spaces_sample_seed_contains():
+    """gym 0.21 space protocol of the stand-ins (what SB3's VecEnv consumers call): seed() makes sample() reproducible, samples
+    are members, shapes / dtypes as the reference declares them (deeprmsa_env.py:38-43, rmsa_env.py:138-149, rmcsa_env.py:181-188)."""
+    from optical_rl_gym_b200 import spaces
+
+    d = spaces.Discrete(6)
+    d.seed(3)
+    a = [d.sample() for _ in range(200)]
+    d.seed(3)
+    assert a == [d.sample() for _ in range(200)] and set(a) == set(range(6)) and all(x in d for x in a)
+    assert 6 not in d and -1 not in d and 2.5 not in d
+    m = spaces.MultiDiscrete((6, 101))
+    m.seed(1)
+    xs = np.stack([m.sample() for _ in range(500)])
+    assert xs.dtype == np.int64 and xs.shape == (500, 2) and (xs >= 0).all() and (xs < [6, 101]).all() and xs[:, 1].max() > 90
+    assert m.contains(xs[0]) and not m.contains(np.array([6, 0])) and not m.contains(np.array([1, 2, 3]))
+    b = spaces.Box(0, 1, (54,), np.float32)
+    b.seed(0)
+    y = b.sample()
+    assert y.shape == (54,) and y.dtype == np.float32 and b.contains(y) and not b.contains(y + 2)
+    dd = spaces.Dict({"a": spaces.Discrete(3), "b": spaces.Box(0, 1, (2,), np.uint8)})
+    dd.seed(5)
+    s = dd.sample()
+    assert dd.contains(s) and s["b"].dtype == np.uint8
+
+
+def test_policy_loader_shared_and_separate_trunks():
+    """MlpPolicy.from_state_dict: the SB3 < 1.8 layout (shared trunk: the shipped best_model.zip) and the >= 1.8 layout with
+    separate actor / critic trunks -- the value must come from the critic's own trunk."""
+    import torch
+
+    from optical_rl_gym_b200.policy import MlpPolicy
+
+    torch.manual_seed(0)
+    obs_dim, width, n_act = 54, 16, 5
+
+    def lin(i, o):
+        return torch.nn.Linear(i, o)
+
+    pi = [lin(obs_dim, width), lin(width, width)]
+    vf = [lin(obs_dim, width), lin(width, width)]
+    act, val = lin(width, n_act), lin(width, 1)
+    x = torch.randn(7, obs_dim)
+
+    def trunk(ls, v):
+        for layer in ls:
+            v = torch.tanh(layer(v))
+        return v
+
+    sd = {"action_net.weight": act.weight, "action_net.bias": act.bias, "value_net.weight": val.weight, "value_net.bias": val.bias}
+    for j, layer in enumerate(pi):
+        sd["mlp_extractor.policy_net.%d.weight" % (2 * j)] = layer.weight
+        sd["mlp_extractor.policy_net.%d.bias" % (2 * j)] = layer.bias
+    for j, layer in enumerate(vf):
+        sd["mlp_extractor.value_net.%d.weight" % (2 * j)] = layer.weight
+        sd["mlp_extractor.value_net.%d.bias" % (2 * j)] = layer.bias
+    pol = MlpPolicy.from_state_dict({k: v.detach() for k, v in sd.items()})
+    logits, value = pol(x)
+    assert torch.allclose(logits, act(trunk(pi, x)), atol=1e-6) and torch.allclose(value, val(trunk(vf, x)).squeeze(-1), atol=1e-6)
+    assert not torch.allclose(value, val(trunk(pi, x)).squeeze(-1), atol=1e-3)
+    shared = {"action_net.weight": act.weight, "action_net.bias": act.bias, "value_net.weight": val.weight, "value_net.bias": val.bias}
+    for j, layer in enumerate(pi):
+        shared["mlp_extractor.shared_net.%d.weight" % (2 * j)] = layer.weight
+        shared["mlp_extractor.shared_net.%d.bias" % (2 * j)] = layer.bias
+    pol2 = MlpPolicy.from_state_dict({k: v.detach() for k, v in shared.items()})
+    l2, v2 = pol2(x)
+    assert pol2.critic_net is None and torch.allclose(l2, logits, atol=1e-6) and torch.allclose(v2, val(trunk(pi, x)).squeeze(-1), atol=1e-6)
