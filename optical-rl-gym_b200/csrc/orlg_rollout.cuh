@@ -132,30 +132,38 @@ __device__ __forceinline__ void ro_tile_release(unsigned *pool_free, unsigned ti
 }
 
 constexpr int RO_SCAN = 8;          // table slots per batch of the rebuild's streaming pass
-#ifndef RO_RANK
-#define RO_RANK 2                   // entries ranked per pass of the rebuild's sort (A/B on the B200: 2 -> 15.6 us per step at 20-step
-                                    // launches, 4 -> 16.7, 8 -> 16.2, the single-entry loop 16.0: the kernel sits at its 128-register cap)
-#endif
-// Thread-per-env window rebuild on the lane-interleaved storage (every pointer already includes the lane; stride 32).
-// On entry: table = slots [0, n) (unsorted), window = win[wh, wn) (sorted), side = up to RO_SIDE entries.  Everything
-// goes back to the table, then one streaming pass moves the entries with time <= h (at most RO_WCAP) to the scratch list
-// and compacts the others in place (forward, stable), and the scratch list is rank-sorted into the window.  Leaves
-// tmin = exact minimum of the table.  If more than RO_WCAP entries lie below the horizon the rest stays in the table
+// Window rebuild of a warp's 32 envs on the lane-interleaved storage (every pointer already includes the lane; stride 32).
+// Called by ALL 32 lanes together (a lane without an env arrives with an empty table, window and side buffer).
+// On entry: table = slots [0, n) (unsorted), window = win[wh, wn) (sorted), side = up to RO_SIDE entries.
+//   1. thread per env: everything goes back to the table (window loads four at a time);
+//   2. thread per env: one streaming pass moves the entries with time <= h (at most RO_WCAP) to the scratch list and
+//      compacts the others in place (forward, stable).  The pass is branch-free per entry (the destination is selected,
+//      not branched on): lanes extract different entries, and the divergent form cost ~5 x the instructions;
+//   3. the WARP sorts the 32 scratch lists one after the other: lane q takes entries q and q + 32 of list L (a strided read
+//      of lines the owner just wrote: 16 lists share each line, so all but two lists hit L1), ranks them against the list
+//      through shuffles (no memory in the loop: the thread-per-env rank sort was c * c / 2 dependent L2 round trips) and
+//      stores them at their rank in L's window.
+// Leaves tmin = exact minimum of the table.  If more than RO_WCAP entries lie below the horizon the rest stays in the table
 // (the caller retries with a shorter horizon while a table entry is still due).
 __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_p, double *sc_t, unsigned long long *sc_p,
                                            WinEntry *win, double *side_t, unsigned long long *side_p,
                                            unsigned &n, unsigned &wh, unsigned &wn, double &tmin, double &side_min,
-                                           const double h, WinEntry &head, WinEntry &nxt) {
+                                           const double h, WinEntry &head, WinEntry &nxt, const int lane) {
     RPH_INIT();
-    // the streaming pass below is a chain of dependent DRAM round trips (one per 8-slot batch: the compaction stores of a
+    // the streaming pass below is a chain of dependent round trips (one per 8-slot batch: the compaction stores of a
     // batch may alias the next batch's loads, so the compiler cannot hoist them): start the first batches' lines now, and
     // every batch asks for the lines two batches ahead
 #pragma unroll
     for (int i = 0; i < 2 * RO_SCAN; i++)
         if ((unsigned)i < n) { prefetch_l2(rt_t + i * 32); prefetch_l2(rt_p + i * 32); }
-    for (unsigned j = wh; j < wn; j++) {                // leftover window entries
-        const WinEntry w = win_load(win + j * 32);
-        rt_t[n * 32] = w.t; rt_p[n * 32] = w.p; n++;
+    for (unsigned j = wh; j < wn; j += 4) {             // leftover window entries, four loads in flight
+        WinEntry w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (j + i < wn) w[i] = win_load(win + (j + i) * 32);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (j + i < wn) { rt_t[n * 32] = w[i].t; rt_p[n * 32] = w[i].p; n++; }
     }
 #pragma unroll
     for (int s = 0; s < RO_SIDE; s++) {                 // side buffer
@@ -166,59 +174,70 @@ __device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_
     RPH_MARK(11);                                       // rebuild: window + side back to the table
     unsigned k = 0, c = 0;
     double mn = ORLG_INF;
-    for (unsigned s0 = 0; s0 < n; s0 += 8) {            // 16 independent (coalesced) loads per pass
-        double tt[8];
-        unsigned long long pp[8];
+    for (unsigned s0 = 0; s0 < n; s0 += RO_SCAN) {      // 16 independent (coalesced) loads per pass
+        double tt[RO_SCAN];
+        unsigned long long pp[RO_SCAN];
 #pragma unroll
         for (int i = 0; i < RO_SCAN; i++)
             if (s0 + 2 * RO_SCAN + i < n) { prefetch_l2(rt_t + (s0 + 2 * RO_SCAN + i) * 32); prefetch_l2(rt_p + (s0 + 2 * RO_SCAN + i) * 32); }
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < RO_SCAN; i++) {
             const bool in = s0 + i < n;
             tt[i] = in ? rt_t[(s0 + i) * 32] : ORLG_INF;
             pp[i] = in ? rt_p[(s0 + i) * 32] : 0ULL;
         }
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            if (s0 + i < n) {
-                if (tt[i] <= h && c < (unsigned)RO_WCAP) {
-                    sc_t[c * 32] = tt[i]; sc_p[c * 32] = pp[i]; c++;
-                } else {
-                    if (k != s0 + i) { rt_t[k * 32] = tt[i]; rt_p[k * 32] = pp[i]; }
-                    k++;
-                    mn = dmin(mn, tt[i]);
-                }
-            }
+        for (int i = 0; i < RO_SCAN; i++) {
+            const bool in = s0 + i < n;
+            const bool ext = in && tt[i] <= h && c < (unsigned)RO_WCAP;
+            const bool keep = in && !ext;
+            double *dt = ext ? sc_t + c * 32 : rt_t + k * 32;
+            unsigned long long *dp = ext ? sc_p + c * 32 : rt_p + k * 32;
+            if (in) { *dt = tt[i]; *dp = pp[i]; }
+            c += ext ? 1u : 0u;
+            k += keep ? 1u : 0u;
+            mn = keep ? dmin(mn, tt[i]) : mn;
         }
     }
     n = k;
     tmin = mn;
     RPH_MARK(12);                                       // rebuild: streaming pass
-    head.t = ORLG_INF; nxt.t = ORLG_INF;
-    // rank sort, RO_RANK entries at a time in registers: one pass over the list ranks all of them (c * c compares, but only
-    // c * c / RO_RANK loads -- the loads' latency, not the compares, is what the quadratic sort costs)
-    for (unsigned j0 = 0; j0 < c; j0 += RO_RANK) {
-        double tj[RO_RANK];
-        unsigned rank[RO_RANK];
-#pragma unroll
-        for (int i = 0; i < RO_RANK; i++) { tj[i] = j0 + i < c ? sc_t[(j0 + i) * 32] : ORLG_INF; rank[i] = 0; }
-#pragma unroll 2
-        for (unsigned q = 0; q < c; q++) {
-            const double tq = sc_t[q * 32];
-#pragma unroll
-            for (int i = 0; i < RO_RANK; i++) rank[i] += (tq < tj[i] || (tq == tj[i] && q < j0 + i)) ? 1u : 0u;
-        }
-#pragma unroll
-        for (int i = 0; i < RO_RANK; i++) {
-            if (j0 + i < c) {
-                WinEntry w;
-                w.t = tj[i]; w.p = sc_p[(j0 + i) * 32];
-                win[rank[i] * 32] = w;
-                if (rank[i] == 0) head = w;
-                if (rank[i] == 1) nxt = w;
+    __syncwarp();
+    {
+        const double *sct_w = sc_t - lane;
+        const unsigned long long *scp_w = sc_p - lane;
+        WinEntry *win_w = win - lane;
+        unsigned todo = __ballot_sync(0xffffffffu, c > 0);
+        while (todo) {
+            const int L = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const unsigned cL = __shfl_sync(0xffffffffu, c, L);
+            const bool h0 = (unsigned)lane < cL, h1 = (unsigned)lane + 32u < cL;
+            const double t0 = h0 ? sct_w[lane * 32 + L] : ORLG_INF;
+            const unsigned long long p0 = h0 ? scp_w[lane * 32 + L] : 0ULL;
+            const double t1 = h1 ? sct_w[(lane + 32) * 32 + L] : ORLG_INF;
+            const unsigned long long p1 = h1 ? scp_w[(lane + 32) * 32 + L] : 0ULL;
+            unsigned r0 = 0, r1 = 0;
+            const unsigned c_lo = cL < 32u ? cL : 32u;
+#pragma unroll 4
+            for (unsigned r = 0; r < c_lo; r++) {       // entries 0..31 of the list against this lane's two
+                const double tr = __shfl_sync(0xffffffffu, t0, (int)r);
+                r0 += (tr < t0 || (tr == t0 && r < (unsigned)lane)) ? 1u : 0u;
+                r1 += (tr <= t1) ? 1u : 0u;              // r < lane + 32 always
             }
+            for (unsigned r = 32; r < cL; r++) {        // entries 32..63
+                const double tr = __shfl_sync(0xffffffffu, t1, (int)(r - 32u));
+                r0 += (tr < t0) ? 1u : 0u;               // r > lane always
+                r1 += (tr < t1 || (tr == t1 && r < (unsigned)lane + 32u)) ? 1u : 0u;
+            }
+            if (h0) { WinEntry w; w.t = t0; w.p = p0; win_w[r0 * 32 + L] = w; }
+            if (h1) { WinEntry w; w.t = t1; w.p = p1; win_w[r1 * 32 + L] = w; }
         }
     }
+    __syncwarp();
+    head.t = ORLG_INF; nxt.t = ORLG_INF;
+    if (c > 0) head = win_load(win);
+    if (c > 1) nxt = win_load(win + 32);
     wh = 0; wn = c;
     RPH_MARK(13);                                       // rebuild: rank sort
 }
@@ -298,7 +317,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     int ep_req = (int)p.counters[(size_t)6 * p.n + e], ep_prov = (int)p.counters[(size_t)7 * p.n + e];
     int d_proc = 0, d_acc = 0, d_req = 0, d_prov = 0;        // deltas of the four running totals over this launch
     unsigned ridx = p.req_index[e];
-    unsigned nlive = p.nheap[e];                              // live services = table + window + side
+    unsigned nlive = live ? p.nheap[e] : 0u;                  // live services = table + window + side (a lane without an env: none)
     unsigned n_tab = nlive;
     unsigned err = p.errors[e];
     unsigned long long candw = KIND == ORLG_DEEPRMSA ? *reinterpret_cast<const unsigned long long *>(p.cand + (size_t)e * 8) : 0xFFFFFFFFFFFFFFFFULL;
@@ -354,7 +373,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                     rt_p[(s0 + 2 * i) * 32] = b[i].x; rt_p[(s0 + 2 * i + 1) * 32] = b[i].y;
                 }
             }
-            ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt);
+            if (n_tab) tmin_tab = 0.0;       // "a table entry is due": the first step of the launch builds the window (one rebuild site)
         }
     }
     int npaths_cur = min((int)s_pair_count[src * p.N + dst], KM);       // candidate paths of the pending request
@@ -382,22 +401,11 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     for (int t = (KIND == ORLG_DEEPRMSA ? 0 : -1); t < ra.T; t++) {
         bool done = false;
         int npaths = 0;
-        unsigned pm[KM];
-        int ns[KM];
         unsigned rec_flags = 0;          // action (low 16 bits) | accepted << 28, for the packed record
         if (t < 0) {
             // ---- first pass of a non-DeepRMSA launch: only the candidate cache of the pending request is built
             if (live) {
-                const int pair = src * p.N + dst;
-                const int first = s_pair_first[pair];
-                npaths = min((int)s_pair_count[pair], KM);
-#pragma unroll
-                for (int q = 0; q < KM; q++) {
-                    const bool have = q < npaths;
-                    const int row = have ? first + q : first;
-                    ns[q] = KIND == ORLG_RWA ? 1 : s_nslots[s_path_se[row] * 128 + br];
-                    pm[q] = have ? s_path_lm[row] : 0u;
-                }
+                npaths = min((int)s_pair_count[src * p.N + dst], KM);
                 npaths_cur = npaths;
             }
         } else if (live) {
@@ -433,16 +441,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                     p_br = p.br_lo + (int)__umulhi(rd_[0], (unsigned)p.br_span);
                 }
             }
-            const int npair = p_src * p.N + p_dst;
-            const int p_first = s_pair_first[npair];
-            npaths = min((int)s_pair_count[npair], KM);
-#pragma unroll
-            for (int q = 0; q < KM; q++) {
-                const bool have = q < npaths;
-                const int row = have ? p_first + q : p_first;
-                ns[q] = KIND == ORLG_RWA ? 1 : s_nslots[s_path_se[row] * 128 + p_br];
-                pm[q] = have ? s_path_lm[row] : 0u;
-            }
+            npaths = min((int)s_pair_count[p_src * p.N + p_dst], KM);
 
             RPH_MARK(0);             // request draw
             // ---- the policy's action on the pending request: DeepRMSA a path index (j = 1), RMSA / RWA (path, slot)
@@ -603,10 +602,8 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             RPH_COUNT(15);
             // a retry means the window filled up before every due service was reached: shorter horizon, down to the clock itself
             hzn = tries < 60 ? __dadd_rn(now, __dmul_rn(ra.span, __longlong_as_double((long long)(1023 - tries) << 52))) : now;
-            if (live) {
-                ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt);
-                RO_POP_DUE();
-            }
+            ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt, lane);
+            RO_POP_DUE();
         }
         RPH_MARK(3);                 // rebuild
         if (live && t >= 0) {
@@ -619,70 +616,56 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
         }
 
         // ---- Phase C: free-slot mask of every candidate path of the pending request (get_available_slots,
-        // rmsa_env.py:638-649), then DeepRMSA's block features (deeprmsa_env.py:60-121) / the heuristics' first-fit starts
+        // rmsa_env.py:638-649), then DeepRMSA's block features (deeprmsa_env.py:60-121) / the heuristics' first-fit starts.
+        // One ROLLED loop over the candidate paths (AND over the path's own hops, then its features): the unrolled
+        // link-sweep form was ~1300 instructions of straight-line code in a loop body that overflows the 32 KB
+        // instruction cache; this one is a quarter of that and executes fewer instructions as well.
         unsigned feat[KM];
 #pragma unroll
         for (int q = 0; q < KM; q++) feat[q] = 0;
         if (live) {
-            Bits A[KM];
-#pragma unroll
-            for (int q = 0; q < KM; q++) A[q] = (q < npaths) ? bits_ones() : Bits{{0u, 0u, 0u, 0u}};
-            if (ET > 0) {
-#pragma unroll
-                for (int l = 0; l < (ET > 0 ? ET : 1); l++) {
+            unsigned long long cand_out = 0xFFFFFFFFFFFFFFFFULL, tot_out = 0;
+            unsigned hops_out = 0;
+            const int first = s_pair_first[src * p.N + dst];
+#pragma unroll 1
+            for (int q = 0; q < KM; q++) {
+                const bool have = q < npaths;
+                const int row = have ? first + q : first;
+                unsigned lm = have ? s_path_lm[row] : 0u;
+                Bits A = have ? bits_ones() : Bits{{0u, 0u, 0u, 0u}};
+                while (lm) {
+                    const int l = __ffs(lm) - 1;
+                    lm &= lm - 1;
                     const uint4 v = sm[l * 32];
-#pragma unroll
-                    for (int q = 0; q < KM; q++)
-                        if (pm[q] & (1u << l)) { A[q].w[0] &= v.x; A[q].w[1] &= v.y; A[q].w[2] &= v.z; A[q].w[3] &= v.w; }
+                    A.w[0] &= v.x; A.w[1] &= v.y; A.w[2] &= v.z; A.w[3] &= v.w;
                 }
-            } else {
-                unsigned un = 0;
-#pragma unroll
-                for (int q = 0; q < KM; q++) un |= pm[q];
-                while (un) {
-                    const int l = __ffs(un) - 1;
-                    un &= un - 1;
-                    const uint4 v = sm[l * 32];
-#pragma unroll
-                    for (int q = 0; q < KM; q++)
-                        if (pm[q] & (1u << l)) { A[q].w[0] &= v.x; A[q].w[1] &= v.y; A[q].w[2] &= v.z; A[q].w[3] &= v.w; }
-                }
-            }
-            RPH_MARK(10);            // candidate-path AND
-            unsigned long long cand_out = 0xFFFFFFFFFFFFFFFFULL;
-            if (KIND == ORLG_DEEPRMSA) {
-#pragma unroll
-                for (int q = 0; q < KM; q++) {
-                    const int n = ns[q];
-                    const Bits B = bits_runs_ge_sched(A[q], s_dbl[n]);
-                    const int st = bits_ffs_flat(B);
+                int st;
+                unsigned f = 0;
+                if (KIND == ORLG_DEEPRMSA) {
+                    const int n = s_nslots[s_path_se[row] * 128 + br];
+                    const Bits B = bits_runs_ge_sched(A, s_dbl[n]);
+                    st = bits_ffs_flat(B);
                     const int fe = bits_ffs_flat(bits_andnot(B, bits_shr1(B)));
-                    const int total = bits_popc(A[q]);
-                    const int runs = bits_popc(bits_andnot(A[q], bits_shl1(A[q])));
-                    cand_out = st >= 0 ? ((cand_out & ~(0xFFULL << (8 * q))) | ((unsigned long long)st << (8 * q))) : cand_out;
-                    feat[q] = feat_pack(st, fe - st + n, total, runs, n);
-                }
-            } else {
-                unsigned long long tot_out = 0;
-                unsigned hops_out = 0;
-                const int first = s_pair_first[src * p.N + dst];
-#pragma unroll
-                for (int q = 0; q < KM; q++) {
-                    int st;
+                    const int total = bits_popc(A);
+                    const int runs = bits_popc(bits_andnot(A, bits_shl1(A)));
+                    f = feat_pack(st, fe - st + n, total, runs, n);
+                } else {
                     if (KIND == ORLG_RWA) {
-                        if (POLICY == RO_POLICY_SAP_LF) { Bits L = A[q]; L.w[0] &= ~1u; st = bits_fls(L); }     // range(W - 1, 0, -1): never wavelength 0
-                        else st = bits_ffs_flat(A[q]);
+                        if (POLICY == RO_POLICY_SAP_LF) { Bits L = A; L.w[0] &= ~1u; st = bits_fls(L); }     // range(W - 1, 0, -1): never wavelength 0
+                        else st = bits_ffs_flat(A);
+                        if (have) hops_out |= (unsigned)(s_path_ll[row] >> 60) << (4 * q);
                     } else {                                     // first fit over range(0, S - n): the last feasible start is never tried
-                        const int n = ns[q];
-                        const Bits B = bits_and(bits_runs_ge_sched(A[q], s_dbl[n]), bits_range(0, max(p.S - n, 0)));
+                        const int n = s_nslots[s_path_se[row] * 128 + br];
+                        const Bits B = bits_and(bits_runs_ge_sched(A, s_dbl[n]), bits_range(0, max(p.S - n, 0)));
                         st = bits_ffs_flat(B);
                     }
-                    cand_out = st >= 0 ? ((cand_out & ~(0xFFULL << (8 * q))) | ((unsigned long long)st << (8 * q))) : cand_out;
-                    tot_out |= (unsigned long long)(bits_popc(A[q]) & 0xff) << (8 * q);
-                    if (KIND == ORLG_RWA && q < npaths) hops_out |= (unsigned)(s_path_ll[first + q] >> 60) << (4 * q);
+                    tot_out |= (unsigned long long)(bits_popc(A) & 0xff) << (8 * q);
                 }
-                candt = tot_out; candh = hops_out;
+                cand_out = st >= 0 ? ((cand_out & ~(0xFFULL << (8 * q))) | ((unsigned long long)st << (8 * q))) : cand_out;
+#pragma unroll
+                for (int i = 0; i < KM; i++) feat[i] = i == q ? f : feat[i];
             }
+            if (KIND != ORLG_DEEPRMSA) { candt = tot_out; candh = hops_out; }
             candw = cand_out;
         }
         RPH_MARK(5);                 // features
