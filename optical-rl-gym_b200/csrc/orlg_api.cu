@@ -55,9 +55,7 @@ struct orlg_env {
     std::vector<std::pair<void *, size_t>> state_allocs;
     bool alloc_is_state = false;
     // T-steps-per-launch rollout path (orlg_rollout.cuh): window / scratch buffers, allocated by the first call
-    WinEntry *ro_win = nullptr;
-    double *ro_sc_t = nullptr, *ro_rt_t = nullptr;
-    unsigned long long *ro_sc_p = nullptr, *ro_rt_p = nullptr;
+    WinEntry *ro_ev = nullptr;
     unsigned *ro_st_u32 = nullptr;             // [4][n] table size, window head, window end, canonical size
     double *ro_st_f64 = nullptr;               // [2 + RO_SIDE][n] table minimum, horizon, side-buffer times
     unsigned long long *ro_st_u64 = nullptr;   // [RO_SIDE][n] side-buffer payloads
@@ -254,7 +252,7 @@ int launch_step(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s)
 
 void rollout_state_args(const orlg_env *env, RolloutArgs *ra) {
     const size_t n = (size_t)env->p.n;
-    ra->win = env->ro_win; ra->sc_t = env->ro_sc_t; ra->sc_p = env->ro_sc_p; ra->rt_t = env->ro_rt_t; ra->rt_p = env->ro_rt_p;
+    ra->ev = env->ro_ev;
     ra->st_ntab = env->ro_st_u32; ra->st_wh = env->ro_st_u32 + n; ra->st_wn = env->ro_st_u32 + 2 * n; ra->st_ncanon = env->ro_st_u32 + 3 * n;
     ra->st_tmin = env->ro_st_f64; ra->st_hzn = env->ro_st_f64 + n; ra->st_side_t = env->ro_st_f64 + 2 * n;
     ra->st_side_p = env->ro_st_u64;
@@ -961,14 +959,10 @@ static int rollout_impl(orlg_env *env, int steps, int policy, void *obs_dev, flo
     int wpc = 0;
     size_t smem = 0;
     if (persistent && rollout_plan(env, &wpc, &ra, &smem)) {
-        if (!env->ro_win) {
+        if (!env->ro_ev) {
             const size_t n = (size_t)p.n;
             const size_t warps = (n + 31) / 32;
-            int rc = dev_alloc(env, &env->ro_win, warps * 32 * RO_WCAP, false);
-            if (!rc) rc = dev_alloc(env, &env->ro_sc_t, warps * 32 * RO_WCAP, false);
-            if (!rc) rc = dev_alloc(env, &env->ro_sc_p, warps * 32 * RO_WCAP, false);
-            if (!rc) rc = dev_alloc(env, &env->ro_rt_t, warps * 32 * (size_t)p.heap_cap, false);
-            if (!rc) rc = dev_alloc(env, &env->ro_rt_p, warps * 32 * (size_t)p.heap_cap, false);
+            int rc = dev_alloc(env, &env->ro_ev, warps * 32 * ((size_t)p.heap_cap + 2 * RO_WCAP), false);
             if (!rc) rc = dev_alloc(env, &env->ro_st_u32, 4 * n, false);
             if (!rc) rc = dev_alloc(env, &env->ro_st_f64, (2 + RO_SIDE) * n, false);
             if (!rc) rc = dev_alloc(env, &env->ro_st_u64, RO_SIDE * n, false);

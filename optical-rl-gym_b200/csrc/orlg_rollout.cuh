@@ -71,12 +71,10 @@ struct RolloutArgs {
     int *actions;                // [T][n]            (NULL: skip; RO_POLICY_REPLAY: the INPUT action sequence)
     uint4 *packed;               // [T][n][2]         (NULL: skip) 32-byte record per env-step: the integer pre-image of the
                                  //                   observation + request + action / accepted / done (orlg.h, orlg_expand_packed)
-    // launch-private event storage, lane-interleaved per warp of 32 envs: element (slot s, lane) of warp w at (w * cap + s) * 32 + lane
-    double *rt_t;                // [warps][heap_cap][32]  table: release times
-    unsigned long long *rt_p;    // [warps][heap_cap][32]  table: packed services
-    double *sc_t;                // [warps][RO_WCAP][32]   rebuild scratch: candidate times
-    unsigned long long *sc_p;    // [warps][RO_WCAP][32]   rebuild scratch: candidate payloads
-    WinEntry *win;               // [warps][RO_WCAP][32]   the sorted window
+    // launch-private event storage, lane-interleaved per warp of 32 envs: one slab of (heap_cap + 2 * RO_WCAP) rows of 32
+    // 16-byte entries (release time, packed service) per warp -- rows [0, heap_cap) the unsorted table, the next RO_WCAP the
+    // rebuild's scratch list, the last RO_WCAP the sorted window; element (row r, lane) of warp w at (w * rows + r) * 32 + lane
+    WinEntry *ev;
     // window state kept between launches (the event storage stays in the launch-private form until another entry point
     // needs the canonical tables: ro_canonicalize_kernel)
     int resume;                  // 1: continue from the saved window state; 0: convert the canonical tables first
@@ -131,107 +129,136 @@ __device__ __forceinline__ void ro_tile_release(unsigned *pool_free, unsigned ti
     if (lane == 0) atomicOr(pool_free, 1u << tile);
 }
 
-constexpr int RO_SCAN = 8;          // table slots per batch of the rebuild's streaming pass
-// Window rebuild of a warp's 32 envs on the lane-interleaved storage (every pointer already includes the lane; stride 32).
-// Called by ALL 32 lanes together (a lane without an env arrives with an empty table, window and side buffer).
-// On entry: table = slots [0, n) (unsorted), window = win[wh, wn) (sorted), side = up to RO_SIDE entries.
+constexpr int RO_SCAN = 8;          // table rows per batch of the rebuild's streaming pass
+__device__ __forceinline__ void win_store(WinEntry *w, double t, unsigned long long pl) {
+    *reinterpret_cast<uint4 *>(w) = make_uint4((unsigned)__double2loint(t), (unsigned)__double2hiint(t), (unsigned)pl, (unsigned)(pl >> 32));
+}
+// Window rebuild of a warp's 32 envs on its slab of the lane-interleaved storage (`ev` already includes the lane; row
+// stride 32 entries; `cap` = table rows).  Called by ALL 32 lanes together (a lane without an env arrives with an empty
+// table, window and side buffer).
+// On entry: table = rows [0, n) (unsorted), window = rows win[wh, wn) (sorted), side = up to RO_SIDE entries.
 //   1. thread per env: everything goes back to the table (window loads four at a time);
-//   2. thread per env: one streaming pass moves the entries with time <= h (at most RO_WCAP) to the scratch list and
-//      compacts the others in place (forward, stable).  The pass is branch-free per entry (the destination is selected,
-//      not branched on): lanes extract different entries, and the divergent form cost ~5 x the instructions;
-//   3. the WARP sorts the 32 scratch lists one after the other: lane q takes entries q and q + 32 of list L (a strided read
-//      of lines the owner just wrote: 16 lists share each line, so all but two lists hit L1), ranks them against the list
-//      through shuffles (no memory in the loop: the thread-per-env rank sort was c * c / 2 dependent L2 round trips) and
-//      stores them at their rank in L's window.
+//   2. thread per env: one streaming pass moves the entries with time <= h (at most RO_WCAP) to the scratch rows and
+//      compacts the others in place (forward, stable).  Branch-free per entry: the destination ROW is selected (table
+//      and scratch share the slab, so that is one 32-bit select), the loads are unpredicated (the table is a multiple
+//      of 16 rows: a batch never leaves it) -- lanes extract different entries, and the divergent form cost 3 x the
+//      instructions;
+//   3. the WARP sorts the 32 scratch lists: lane q takes entry q (and q + 32) of list L -- a strided read of rows the owner
+//      just wrote, 8 lists per 128-byte line -- ranks it against the rest of the list through shuffles (no memory in the
+//      loop: the thread-per-env rank sort was c * c / 2 dependent L2 round trips) and stores it at its rank in L's
+//      window.  Equal release times keep their list order (__match_any_sync gives the tie groups).  Two lists of at
+//      most 16 entries are ranked together, one per half-warp.
 // Leaves tmin = exact minimum of the table.  If more than RO_WCAP entries lie below the horizon the rest stays in the table
 // (the caller retries with a shorter horizon while a table entry is still due).
-__device__ __forceinline__ void ro_rebuild(double *rt_t, unsigned long long *rt_p, double *sc_t, unsigned long long *sc_p,
-                                           WinEntry *win, double *side_t, unsigned long long *side_p,
+__device__ __forceinline__ void ro_rebuild(WinEntry *ev, const unsigned cap, double *side_t, unsigned long long *side_p,
                                            unsigned &n, unsigned &wh, unsigned &wn, double &tmin, double &side_min,
                                            const double h, WinEntry &head, WinEntry &nxt, const int lane) {
     RPH_INIT();
-    // the streaming pass below is a chain of dependent round trips (one per 8-slot batch: the compaction stores of a
-    // batch may alias the next batch's loads, so the compiler cannot hoist them): start the first batches' lines now, and
-    // every batch asks for the lines two batches ahead
+    WinEntry *const win = ev + (cap + RO_WCAP) * 32;
+    // the streaming pass below is a chain of dependent round trips (one per 8-row batch): start the first batches' lines
+    // now, and every batch asks for the lines two batches ahead
 #pragma unroll
     for (int i = 0; i < 2 * RO_SCAN; i++)
-        if ((unsigned)i < n) { prefetch_l2(rt_t + i * 32); prefetch_l2(rt_p + i * 32); }
+        if ((unsigned)i < n) prefetch_l2(ev + i * 32);
     for (unsigned j = wh; j < wn; j += 4) {             // leftover window entries, four loads in flight
-        WinEntry w[4];
+        uint4 w[4];
 #pragma unroll
         for (int i = 0; i < 4; i++)
-            if (j + i < wn) w[i] = win_load(win + (j + i) * 32);
+            if (j + i < wn) w[i] = *reinterpret_cast<const uint4 *>(win + (j + i) * 32);
 #pragma unroll
         for (int i = 0; i < 4; i++)
-            if (j + i < wn) { rt_t[n * 32] = w[i].t; rt_p[n * 32] = w[i].p; n++; }
+            if (j + i < wn) { *reinterpret_cast<uint4 *>(ev + n * 32) = w[i]; n++; }
     }
 #pragma unroll
     for (int s = 0; s < RO_SIDE; s++) {                 // side buffer
         const double t = side_t[s * 32];
-        if (t < ORLG_INF) { rt_t[n * 32] = t; rt_p[n * 32] = side_p[s * 32]; n++; side_t[s * 32] = ORLG_INF; }
+        if (t < ORLG_INF) { win_store(ev + n * 32, t, side_p[s * 32]); n++; side_t[s * 32] = ORLG_INF; }
     }
     side_min = ORLG_INF;
     RPH_MARK(11);                                       // rebuild: window + side back to the table
-    unsigned k = 0, c = 0;
+    unsigned k = 0, cs = cap;                           // next table row of the compaction, next scratch row
     double mn = ORLG_INF;
-    for (unsigned s0 = 0; s0 < n; s0 += RO_SCAN) {      // 16 independent (coalesced) loads per pass
-        double tt[RO_SCAN];
-        unsigned long long pp[RO_SCAN];
+    {
+        const WinEntry *rd = ev;
+        for (unsigned s0 = 0; s0 < n; s0 += RO_SCAN, rd += RO_SCAN * 32) {
+            const unsigned rem = n - s0;
+            uint4 v[RO_SCAN];
 #pragma unroll
-        for (int i = 0; i < RO_SCAN; i++)
-            if (s0 + 2 * RO_SCAN + i < n) { prefetch_l2(rt_t + (s0 + 2 * RO_SCAN + i) * 32); prefetch_l2(rt_p + (s0 + 2 * RO_SCAN + i) * 32); }
+            for (int i = 0; i < RO_SCAN; i++)
+                if ((unsigned)(2 * RO_SCAN + i) < rem) prefetch_l2(rd + (2 * RO_SCAN + i) * 32);
 #pragma unroll
-        for (int i = 0; i < RO_SCAN; i++) {
-            const bool in = s0 + i < n;
-            tt[i] = in ? rt_t[(s0 + i) * 32] : ORLG_INF;
-            pp[i] = in ? rt_p[(s0 + i) * 32] : 0ULL;
-        }
+            for (int i = 0; i < RO_SCAN; i++) v[i] = *reinterpret_cast<const uint4 *>(rd + i * 32);
 #pragma unroll
-        for (int i = 0; i < RO_SCAN; i++) {
-            const bool in = s0 + i < n;
-            const bool ext = in && tt[i] <= h && c < (unsigned)RO_WCAP;
-            const bool keep = in && !ext;
-            double *dt = ext ? sc_t + c * 32 : rt_t + k * 32;
-            unsigned long long *dp = ext ? sc_p + c * 32 : rt_p + k * 32;
-            if (in) { *dt = tt[i]; *dp = pp[i]; }
-            c += ext ? 1u : 0u;
-            k += keep ? 1u : 0u;
-            mn = keep ? dmin(mn, tt[i]) : mn;
+            for (int i = 0; i < RO_SCAN; i++) {
+                const double t = __hiloint2double((int)v[i].y, (int)v[i].x);
+                const bool in = (unsigned)i < rem;
+                const bool ext = in && t <= h && cs < cap + (unsigned)RO_WCAP;
+                const bool keep = in && !ext;
+                const unsigned row = ext ? cs : k;
+                if (in) *reinterpret_cast<uint4 *>(ev + row * 32) = v[i];
+                cs += ext ? 1u : 0u;
+                k += keep ? 1u : 0u;
+                mn = (keep && t < mn) ? t : mn;
+            }
         }
     }
     n = k;
     tmin = mn;
+    const unsigned c = cs - cap;
     RPH_MARK(12);                                       // rebuild: streaming pass
     __syncwarp();
     {
-        const double *sct_w = sc_t - lane;
-        const unsigned long long *scp_w = sc_p - lane;
-        WinEntry *win_w = win - lane;
+        const WinEntry *scw = ev + cap * 32 - lane;      // the warp's scratch rows, lane 0
+        WinEntry *winw = win - lane;
+        const unsigned lt_mask = (1u << lane) - 1u;
         unsigned todo = __ballot_sync(0xffffffffu, c > 0);
         while (todo) {
             const int L = __ffs(todo) - 1;
             todo &= todo - 1;
             const unsigned cL = __shfl_sync(0xffffffffu, c, L);
-            const bool h0 = (unsigned)lane < cL, h1 = (unsigned)lane + 32u < cL;
-            const double t0 = h0 ? sct_w[lane * 32 + L] : ORLG_INF;
-            const unsigned long long p0 = h0 ? scp_w[lane * 32 + L] : 0ULL;
-            const double t1 = h1 ? sct_w[(lane + 32) * 32 + L] : ORLG_INF;
-            const unsigned long long p1 = h1 ? scp_w[(lane + 32) * 32 + L] : 0ULL;
-            unsigned r0 = 0, r1 = 0;
-            const unsigned c_lo = cL < 32u ? cL : 32u;
+            const int LB = todo ? __ffs(todo) - 1 : L;
+            const unsigned cB = __shfl_sync(0xffffffffu, c, LB);
+            if (todo && cL <= 16u && cB <= 16u) {       // two short lists, one per half-warp
+                todo &= todo - 1;
+                const bool hi = lane >= 16;
+                const int q = lane & 15, myL = hi ? LB : L;
+                const unsigned myc = hi ? cB : cL;
+                uint4 v = make_uint4(0u, 0x7ff00000u, 0u, 0u);
+                if ((unsigned)q < myc) v = *reinterpret_cast<const uint4 *>(scw + q * 32 + myL);
+                const double t = __hiloint2double((int)v.y, (int)v.x);
+                const unsigned cm = cL > cB ? cL : cB;
+                const int base = lane & 16;
+                unsigned r = 0;
 #pragma unroll 4
-            for (unsigned r = 0; r < c_lo; r++) {       // entries 0..31 of the list against this lane's two
-                const double tr = __shfl_sync(0xffffffffu, t0, (int)r);
-                r0 += (tr < t0 || (tr == t0 && r < (unsigned)lane)) ? 1u : 0u;
-                r1 += (tr <= t1) ? 1u : 0u;              // r < lane + 32 always
+                for (unsigned i = 0; i < cm; i++) r += (__shfl_sync(0xffffffffu, t, base + (int)i) < t) ? 1u : 0u;
+                const unsigned same = __match_any_sync(0xffffffffu, (unsigned long long)__double_as_longlong(t));
+                r += __popc(same & lt_mask & (hi ? 0xffff0000u : 0x0000ffffu));
+                if ((unsigned)q < myc) *reinterpret_cast<uint4 *>(winw + r * 32 + myL) = v;
+            } else {                                    // one list of up to 64 entries: lane q ranks entries q and q + 32
+                const bool h0 = (unsigned)lane < cL, h1 = (unsigned)lane + 32u < cL;
+                uint4 v0 = make_uint4(0u, 0x7ff00000u, 0u, 0u), v1 = v0;
+                if (h0) v0 = *reinterpret_cast<const uint4 *>(scw + lane * 32 + L);
+                if (h1) v1 = *reinterpret_cast<const uint4 *>(scw + (lane + 32) * 32 + L);
+                const double t0 = __hiloint2double((int)v0.y, (int)v0.x), t1 = __hiloint2double((int)v1.y, (int)v1.x);
+                unsigned r0 = 0, r1 = 0;
+                const unsigned c_lo = cL < 32u ? cL : 32u;
+#pragma unroll 2
+                for (unsigned i = 0; i < c_lo; i++) {   // entries 0..31 against this lane's two (they precede every entry 32..63)
+                    const double tr = __shfl_sync(0xffffffffu, t0, (int)i);
+                    r0 += (tr < t0) ? 1u : 0u;
+                    r1 += (tr <= t1) ? 1u : 0u;
+                }
+#pragma unroll 2
+                for (unsigned i = 32; i < cL; i++) {    // entries 32..63
+                    const double tr = __shfl_sync(0xffffffffu, t1, (int)(i - 32u));
+                    r0 += (tr < t0) ? 1u : 0u;
+                    r1 += (tr < t1) ? 1u : 0u;
+                }
+                r0 += __popc(__match_any_sync(0xffffffffu, (unsigned long long)__double_as_longlong(t0)) & lt_mask);
+                r1 += __popc(__match_any_sync(0xffffffffu, (unsigned long long)__double_as_longlong(t1)) & lt_mask);
+                if (h0) *reinterpret_cast<uint4 *>(winw + r0 * 32 + L) = v0;
+                if (h1) *reinterpret_cast<uint4 *>(winw + r1 * 32 + L) = v1;
             }
-            for (unsigned r = 32; r < cL; r++) {        // entries 32..63
-                const double tr = __shfl_sync(0xffffffffu, t1, (int)(r - 32u));
-                r0 += (tr < t0) ? 1u : 0u;               // r > lane always
-                r1 += (tr < t1 || (tr == t1 && r < (unsigned)lane + 32u)) ? 1u : 0u;
-            }
-            if (h0) { WinEntry w; w.t = t0; w.p = p0; win_w[r0 * 32 + L] = w; }
-            if (h1) { WinEntry w; w.t = t1; w.p = p1; win_w[r1 * 32 + L] = w; }
         }
     }
     __syncwarp();
@@ -321,12 +348,9 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     unsigned n_tab = nlive;
     unsigned err = p.errors[e];
     unsigned long long candw = KIND == ORLG_DEEPRMSA ? *reinterpret_cast<const unsigned long long *>(p.cand + (size_t)e * 8) : 0xFFFFFFFFFFFFFFFFULL;
-    const size_t gw = (size_t)(env0 >> 5);                       // this warp's slice of the launch-private event storage
-    double *const rt_t = ra.rt_t + gw * p.heap_cap * 32 + lane;
-    unsigned long long *const rt_p = ra.rt_p + gw * p.heap_cap * 32 + lane;
-    double *const sc_t = ra.sc_t + gw * RO_WCAP * 32 + lane;
-    unsigned long long *const sc_p = ra.sc_p + gw * RO_WCAP * 32 + lane;
-    WinEntry *const win = ra.win + gw * RO_WCAP * 32 + lane;
+    const size_t gw = (size_t)(env0 >> 5);                       // this warp's slab of the launch-private event storage
+    WinEntry *const ev = ra.ev + gw * (size_t)(p.heap_cap + 2 * RO_WCAP) * 32 + lane;       // table rows [0, heap_cap)
+    WinEntry *const win = ev + (size_t)(p.heap_cap + RO_WCAP) * 32;
 #pragma unroll
     for (int s = 0; s < RO_SIDE; s++) side_t[s * 32] = ORLG_INF;
     if (ridx != p.lockstep_ridx) err |= ORLG_ERR_LOCKSTEP;
@@ -369,8 +393,8 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                 }
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    rt_t[(s0 + 2 * i) * 32] = a[i].x; rt_t[(s0 + 2 * i + 1) * 32] = a[i].y;
-                    rt_p[(s0 + 2 * i) * 32] = b[i].x; rt_p[(s0 + 2 * i + 1) * 32] = b[i].y;
+                    win_store(ev + (s0 + 2 * i) * 32, a[i].x, b[i].x);
+                    win_store(ev + (s0 + 2 * i + 1) * 32, a[i].y, b[i].y);
                 }
             }
             if (n_tab) tmin_tab = 0.0;       // "a table entry is due": the first step of the launch builds the window (one rebuild site)
@@ -552,7 +576,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                                 if (in_side) side_min = dmin(side_min, rel);
                             }
                             if (!in_side) {                      // table push: two stores
-                                rt_t[n_tab * 32] = rel; rt_p[n_tab * 32] = pl; n_tab++;
+                                win_store(ev + n_tab * 32, rel, pl); n_tab++;
                                 tmin_tab = dmin(tmin_tab, rel);
                             }
                             nlive++;
@@ -602,7 +626,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             RPH_COUNT(15);
             // a retry means the window filled up before every due service was reached: shorter horizon, down to the clock itself
             hzn = tries < 60 ? __dadd_rn(now, __dmul_rn(ra.span, __longlong_as_double((long long)(1023 - tries) << 52))) : now;
-            ro_rebuild(rt_t, rt_p, sc_t, sc_p, win, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt, lane);
+            ro_rebuild(ev, (unsigned)p.heap_cap, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt, lane);
             RO_POP_DUE();
         }
         RPH_MARK(3);                 // rebuild
@@ -786,20 +810,19 @@ __global__ void __launch_bounds__(128) ro_canonicalize_kernel(const Params p, co
     if (env >= p.n) return;
     const int lane = threadIdx.x & 31;
     const size_t gw = (size_t)(env >> 5);
-    double *const rt_t = ra.rt_t + gw * p.heap_cap * 32 + lane;
-    unsigned long long *const rt_p = ra.rt_p + gw * p.heap_cap * 32 + lane;
-    const WinEntry *const win = ra.win + gw * RO_WCAP * 32 + lane;
+    WinEntry *const ev = ra.ev + gw * (size_t)(p.heap_cap + 2 * RO_WCAP) * 32 + lane;
+    const WinEntry *const win = ev + (size_t)(p.heap_cap + RO_WCAP) * 32;
     unsigned n_tab = ra.st_ntab[env];
     const unsigned wh = ra.st_wh[env], wn = ra.st_wn[env], n_entry = ra.st_ncanon[env];
     unsigned err = 0;
     for (unsigned j = wh; j < wn; j++) {                         // window + side entries back to the table
         const WinEntry w = win_load(win + j * 32);
-        rt_t[n_tab * 32] = w.t; rt_p[n_tab * 32] = w.p; n_tab++;
+        win_store(ev + n_tab * 32, w.t, w.p); n_tab++;
     }
 #pragma unroll
     for (int s = 0; s < RO_SIDE; s++) {
         const double ts = ra.st_side_t[(size_t)s * p.n + env];
-        if (ts < ORLG_INF) { rt_t[n_tab * 32] = ts; rt_p[n_tab * 32] = ra.st_side_p[(size_t)s * p.n + env]; n_tab++; }
+        if (ts < ORLG_INF) { win_store(ev + n_tab * 32, ts, ra.st_side_p[(size_t)s * p.n + env]); n_tab++; }
     }
     if (n_tab != p.nheap[env]) err |= ORLG_ERR_LOCKSTEP;        // internal consistency (never expected)
     // lane-interleaved -> canonical [env][slot]: coalesced loads, each thread writes its own rows (16-byte stores)
@@ -813,8 +836,10 @@ __global__ void __launch_bounds__(128) ro_canonicalize_kernel(const Params p, co
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const bool in = s0 + i < n_tab;
-            tt[i] = in ? rt_t[(s0 + i) * 32] : ORLG_INF;
-            pp[i] = in ? rt_p[(s0 + i) * 32] : 0ULL;
+            WinEntry w;
+            w.t = ORLG_INF; w.p = 0ULL;
+            if (in) w = win_load(ev + (s0 + i) * 32);
+            tt[i] = w.t; pp[i] = w.p;
         }
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -830,7 +855,7 @@ __global__ void __launch_bounds__(128) ro_canonicalize_kernel(const Params p, co
 #pragma unroll
         for (int q = 0; q < EV_GROUP; q++) {
             const unsigned sl = (unsigned)(g * EV_GROUP + q);
-            m = dmin(m, sl < n_tab ? rt_t[sl * 32] : ORLG_INF);
+            m = dmin(m, sl < n_tab ? *reinterpret_cast<const double *>(ev + sl * 32) : ORLG_INF);
         }
         if (g < tail_g) gmin[g] = lower_f32(m); else tail_min = m;
         all_min = dmin(all_min, g < tail_g ? (double)lower_f32(m) : m);
