@@ -87,13 +87,16 @@ struct RolloutArgs {
 // apply a release / an allocation to the path's links in the warp's shared-memory mask tile
 template <bool SET>
 __device__ __forceinline__ void ro_path_update(uint4 *sm, unsigned lm, const Bits &rm) {
-    while (lm) {
-        const int l = __ffs(lm) - 1;
+    while (lm) {                         // two hops per pass: both loads in flight before either store (a repeated hop is harmless)
+        const int l0 = __ffs(lm) - 1;
         lm &= lm - 1;
-        uint4 v = sm[l * 32];
-        if (SET) { v.x |= rm.w[0]; v.y |= rm.w[1]; v.z |= rm.w[2]; v.w |= rm.w[3]; }
-        else { v.x &= ~rm.w[0]; v.y &= ~rm.w[1]; v.z &= ~rm.w[2]; v.w &= ~rm.w[3]; }
-        sm[l * 32] = v;
+        const int l1 = lm ? __ffs(lm) - 1 : l0;
+        lm &= lm - 1;
+        uint4 v = sm[l0 * 32], u = sm[l1 * 32];
+        if (SET) { v.x |= rm.w[0]; v.y |= rm.w[1]; v.z |= rm.w[2]; v.w |= rm.w[3]; u.x |= rm.w[0]; u.y |= rm.w[1]; u.z |= rm.w[2]; u.w |= rm.w[3]; }
+        else { v.x &= ~rm.w[0]; v.y &= ~rm.w[1]; v.z &= ~rm.w[2]; v.w &= ~rm.w[3]; u.x &= ~rm.w[0]; u.y &= ~rm.w[1]; u.z &= ~rm.w[2]; u.w &= ~rm.w[3]; }
+        sm[l0 * 32] = v;
+        sm[l1 * 32] = u;
     }
 }
 
@@ -657,11 +660,18 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
                 const int row = have ? first + q : first;
                 unsigned lm = have ? s_path_lm[row] : 0u;
                 Bits A = have ? bits_ones() : Bits{{0u, 0u, 0u, 0u}};
-                while (lm) {
-                    const int l = __ffs(lm) - 1;
+                while (lm) {                     // four hops per pass, their loads in flight together (AND is idempotent: a short
+                    const int l0 = __ffs(lm) - 1;  // path repeats its first hop)
                     lm &= lm - 1;
-                    const uint4 v = sm[l * 32];
-                    A.w[0] &= v.x; A.w[1] &= v.y; A.w[2] &= v.z; A.w[3] &= v.w;
+                    const int l1 = lm ? __ffs(lm) - 1 : l0;
+                    lm &= lm - 1;
+                    const int l2 = lm ? __ffs(lm) - 1 : l0;
+                    lm &= lm - 1;
+                    const int l3 = lm ? __ffs(lm) - 1 : l0;
+                    lm &= lm - 1;
+                    const uint4 v0 = sm[l0 * 32], v1 = sm[l1 * 32], v2 = sm[l2 * 32], v3 = sm[l3 * 32];
+                    A.w[0] &= v0.x & v1.x; A.w[1] &= v0.y & v1.y; A.w[2] &= v0.z & v1.z; A.w[3] &= v0.w & v1.w;
+                    A.w[0] &= v2.x & v3.x; A.w[1] &= v2.y & v3.y; A.w[2] &= v2.z & v3.z; A.w[3] &= v2.w & v3.w;
                 }
                 int st;
                 unsigned f = 0;
