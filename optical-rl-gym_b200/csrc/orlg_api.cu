@@ -831,6 +831,17 @@ int orlg_debug_warp_timeline(unsigned long long *out, int n_warps) {
 #endif
 }
 
+// debug (instrumented builds only): per-warp timeline of the last orlg_rollout launch (8 words per warp, orlg_rollout.cuh)
+int orlg_debug_rollout_timeline(unsigned long long *out, int n_warps) {
+#ifdef ORLG_RO_TIMELINE
+    CUDA_OK(cudaMemcpyFromSymbol(out, g_ro_timeline, (size_t)8 * (n_warps < 4096 ? n_warps : 4096) * sizeof(unsigned long long)));
+    return ORLG_OK;
+#else
+    (void)out; (void)n_warps;
+    return fail(ORLG_E_UNSUPPORTED, "built without -DORLG_RO_TIMELINE");
+#endif
+}
+
 static int stats_alloc(orlg_env *env) {
     Params &p = env->p;
     if (env->wide || p.E > 128) return fail(ORLG_E_UNSUPPORTED, "statistics path handles <= 32 links and <= 128 slots");

@@ -54,6 +54,26 @@ enum { RO_POLICY_RANDOM = 0, RO_POLICY_SP_FF = 1, RO_POLICY_SAP_FF = 2, RO_POLIC
 #define RPH_COUNT(k) do { } while (0)
 #endif
 
+// per-warp wall-clock timeline of one launch (instrumented builds: -DORLG_RO_TIMELINE, tools/rollout_timeline.py):
+// globaltimer (ns) at kernel entry / first step / after the last step / exit, rebuilds taken and the ns spent in them
+#ifdef ORLG_RO_TIMELINE
+__device__ unsigned long long g_ro_timeline[8 * 4096];
+__device__ __forceinline__ unsigned long long ro_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define RTL_DECL() unsigned long long rtl_[8] = {ro_gtime(), 0, 0, 0, 0, 0, 0, 0}
+#define RTL_SET(k) rtl_[k] = ro_gtime()
+#define RTL_REBUILD_BEGIN() const unsigned long long rtl_b_ = ro_gtime()
+#define RTL_REBUILD_END() do { rtl_[4] += 1; rtl_[5] += ro_gtime() - rtl_b_; rtl_[6] += g_rtl_scan_; rtl_[7] += g_rtl_sort_; } while (0)
+#define RTL_IN_REBUILD(var) var = ro_gtime()
+#define RTL_FLUSH(w) do { if ((threadIdx.x & 31) == 0 && (w) < 4096) { for (int i_ = 0; i_ < 8; i_++) g_ro_timeline[8 * (w) + i_] = rtl_[i_]; } } while (0)
+#else
+#define RTL_DECL() do { } while (0)
+#define RTL_SET(k) do { } while (0)
+#define RTL_REBUILD_BEGIN() do { } while (0)
+#define RTL_REBUILD_END() do { } while (0)
+#define RTL_IN_REBUILD(var) do { } while (0)
+#define RTL_FLUSH(w) do { } while (0)
+#endif
+
 struct __align__(16) WinEntry {
     double t;
     unsigned long long p;
@@ -133,6 +153,7 @@ __device__ __forceinline__ void ro_tile_release(unsigned *pool_free, unsigned ti
 }
 
 constexpr int RO_SCAN = 8;          // table rows per batch of the rebuild's streaming pass
+__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 __device__ __forceinline__ void win_store(WinEntry *w, double t, unsigned long long pl) {
     *reinterpret_cast<uint4 *>(w) = make_uint4((unsigned)__double2loint(t), (unsigned)__double2hiint(t), (unsigned)pl, (unsigned)(pl >> 32));
 }
@@ -155,14 +176,14 @@ __device__ __forceinline__ void win_store(WinEntry *w, double t, unsigned long l
 // (the caller retries with a shorter horizon while a table entry is still due).
 __device__ __forceinline__ void ro_rebuild(WinEntry *ev, const unsigned cap, double *side_t, unsigned long long *side_p,
                                            unsigned &n, unsigned &wh, unsigned &wn, double &tmin, double &side_min,
-                                           const double h, WinEntry &head, WinEntry &nxt, const int lane) {
+                                           const double h, WinEntry &head, WinEntry &nxt, const int lane, unsigned long long &g_rtl_scan_, unsigned long long &g_rtl_sort_) {
     RPH_INIT();
     WinEntry *const win = ev + (cap + RO_WCAP) * 32;
     // the streaming pass below is a chain of dependent round trips (one per 8-row batch): start the first batches' lines
     // now, and every batch asks for the lines two batches ahead
 #pragma unroll
     for (int i = 0; i < 2 * RO_SCAN; i++)
-        if ((unsigned)i < n) prefetch_l2(ev + i * 32);
+        if ((unsigned)i < n) prefetch_l1(ev + i * 32);
     for (unsigned j = wh; j < wn; j += 4) {             // leftover window entries, four loads in flight
         uint4 w[4];
 #pragma unroll
@@ -179,6 +200,8 @@ __device__ __forceinline__ void ro_rebuild(WinEntry *ev, const unsigned cap, dou
     }
     side_min = ORLG_INF;
     RPH_MARK(11);                                       // rebuild: window + side back to the table
+    unsigned long long rtl_t1_ = 0, rtl_t2_ = 0, rtl_t3_ = 0;
+    RTL_IN_REBUILD(rtl_t1_);
     unsigned k = 0, cs = cap;                           // next table row of the compaction, next scratch row
     double mn = ORLG_INF;
     {
@@ -188,7 +211,7 @@ __device__ __forceinline__ void ro_rebuild(WinEntry *ev, const unsigned cap, dou
             uint4 v[RO_SCAN];
 #pragma unroll
             for (int i = 0; i < RO_SCAN; i++)
-                if ((unsigned)(2 * RO_SCAN + i) < rem) prefetch_l2(rd + (2 * RO_SCAN + i) * 32);
+                if ((unsigned)(2 * RO_SCAN + i) < rem) prefetch_l1(rd + (2 * RO_SCAN + i) * 32);
 #pragma unroll
             for (int i = 0; i < RO_SCAN; i++) v[i] = *reinterpret_cast<const uint4 *>(rd + i * 32);
 #pragma unroll
@@ -209,8 +232,14 @@ __device__ __forceinline__ void ro_rebuild(WinEntry *ev, const unsigned cap, dou
     tmin = mn;
     const unsigned c = cs - cap;
     RPH_MARK(12);                                       // rebuild: streaming pass
+    RTL_IN_REBUILD(rtl_t2_);
     __syncwarp();
     {
+        // the lists are read across the lanes below (32-byte sectors of rows this warp just wrote through to L2): pull the
+        // rows into L1 whole, every lane asking for its own entries, so that only the first list waits for a round trip
+        const unsigned cmax = __reduce_max_sync(0xffffffffu, c);
+        for (unsigned q = 0; q < cmax; q++)
+            if (q < c) prefetch_l1(ev + (cap + q) * 32);
         const WinEntry *scw = ev + cap * 32 - lane;      // the warp's scratch rows, lane 0
         WinEntry *winw = win - lane;
         const unsigned lt_mask = (1u << lane) - 1u;
@@ -234,9 +263,14 @@ __device__ __forceinline__ void ro_rebuild(WinEntry *ev, const unsigned cap, dou
                 unsigned r = 0;
 #pragma unroll 4
                 for (unsigned i = 0; i < cm; i++) r += (__shfl_sync(0xffffffffu, t, base + (int)i) < t) ? 1u : 0u;
-                const unsigned same = __match_any_sync(0xffffffffu, (unsigned long long)__double_as_longlong(t));
-                r += __popc(same & lt_mask & (hi ? 0xffff0000u : 0x0000ffffu));
-                if ((unsigned)q < myc) *reinterpret_cast<uint4 *>(winw + r * 32 + myL) = v;
+                // equal release times would share a rank: the ranks then do not cover cL + cB window rows (one warp reduction
+                // checks it); only then are the tie groups looked up and ordered by list position
+                const bool mine = (unsigned)q < myc;
+                if (__popc(__reduce_or_sync(0xffffffffu, mine ? 1u << (base + (int)r) : 0u)) != (int)(cL + cB)) {
+                    const unsigned same = __match_any_sync(0xffffffffu, (unsigned long long)__double_as_longlong(t));
+                    r += __popc(same & lt_mask & (hi ? 0xffff0000u : 0x0000ffffu));
+                }
+                if (mine) *reinterpret_cast<uint4 *>(winw + r * 32 + myL) = v;
             } else {                                    // one list of up to 64 entries: lane q ranks entries q and q + 32
                 const bool h0 = (unsigned)lane < cL, h1 = (unsigned)lane + 32u < cL;
                 uint4 v0 = make_uint4(0u, 0x7ff00000u, 0u, 0u), v1 = v0;
@@ -257,8 +291,12 @@ __device__ __forceinline__ void ro_rebuild(WinEntry *ev, const unsigned cap, dou
                     r0 += (tr < t0) ? 1u : 0u;
                     r1 += (tr < t1) ? 1u : 0u;
                 }
-                r0 += __popc(__match_any_sync(0xffffffffu, (unsigned long long)__double_as_longlong(t0)) & lt_mask);
-                r1 += __popc(__match_any_sync(0xffffffffu, (unsigned long long)__double_as_longlong(t1)) & lt_mask);
+                const unsigned lo_bits = (h0 && r0 < 32u ? 1u << r0 : 0u) | (h1 && r1 < 32u ? 1u << r1 : 0u);
+                const unsigned hi_bits = (h0 && r0 >= 32u ? 1u << (r0 - 32u) : 0u) | (h1 && r1 >= 32u ? 1u << (r1 - 32u) : 0u);
+                if (__popc(__reduce_or_sync(0xffffffffu, lo_bits)) + __popc(__reduce_or_sync(0xffffffffu, hi_bits)) != (int)cL) {
+                    r0 += __popc(__match_any_sync(0xffffffffu, (unsigned long long)__double_as_longlong(t0)) & lt_mask);      // ties (see above)
+                    r1 += __popc(__match_any_sync(0xffffffffu, (unsigned long long)__double_as_longlong(t1)) & lt_mask);
+                }
                 if (h0) *reinterpret_cast<uint4 *>(winw + r0 * 32 + L) = v0;
                 if (h1) *reinterpret_cast<uint4 *>(winw + r1 * 32 + L) = v1;
             }
@@ -270,6 +308,8 @@ __device__ __forceinline__ void ro_rebuild(WinEntry *ev, const unsigned cap, dou
     if (c > 1) nxt = win_load(win + 32);
     wh = 0; wn = c;
     RPH_MARK(13);                                       // rebuild: rank sort
+    RTL_IN_REBUILD(rtl_t3_);
+    g_rtl_scan_ = rtl_t2_ - rtl_t1_; g_rtl_sort_ = rtl_t3_ - rtl_t2_;
 }
 
 // packed integer pre-image of one path's features: start (7, 127 = no block) | length (7) | total free (7) | free runs (6) | slots (5)
@@ -306,6 +346,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
 
     pdl_launch_dependents();
     RPH_INIT();
+    RTL_DECL();
     // ---------------- tables: one bulk copy per CTA
     if (tid == 0) {
         mbar_init(tab_bar, 1);
@@ -409,7 +450,9 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     const unsigned k0 = (unsigned)p.seed, k1 = (unsigned)(p.seed >> 32);
     const unsigned n_act = (unsigned)(p.k) + (p.allow_rejection ? 1u : 0u);     // path actions (DeepRMSA: j = 1)
 
-    // release of the window head; the entry after it was requested one pop earlier
+    // release of the window head; the entry after it was requested one pop earlier.  (Tried and measured slower: a
+    // straight-line "head, then nxt, then a synchronous loop" form that never waits on its own load -- the lanes of a warp
+    // then pop in different copies of the release code: 9.4 -> 10.3 us per step.)
 #define RO_POP_DUE()                                                                                              \
     while (head.t <= now) {                                                                                      \
         const int rs_ = svc_start(head.p);                                                                       \
@@ -420,6 +463,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     }
 
     RPH_MARK(8);                     // entry: state in + first window build
+    RTL_SET(1);
     // cached per candidate path of the PENDING request: first-fit start as the policy defines it (candw, one byte per path,
     // CAND_NONE = none), free slots (candt) and hop count (candh) for the least-loaded / fewest-hops heuristics.
     // DeepRMSA-v0 handles keep candw in the canonical state; the other kinds compute it in an extra phase-C pass (t = -1).
@@ -629,8 +673,11 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
             RPH_COUNT(15);
             // a retry means the window filled up before every due service was reached: shorter horizon, down to the clock itself
             hzn = tries < 60 ? __dadd_rn(now, __dmul_rn(ra.span, __longlong_as_double((long long)(1023 - tries) << 52))) : now;
-            ro_rebuild(ev, (unsigned)p.heap_cap, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt, lane);
+            RTL_REBUILD_BEGIN();
+            unsigned long long g_rtl_scan_ = 0, g_rtl_sort_ = 0;
+            ro_rebuild(ev, (unsigned)p.heap_cap, side_t, side_p, n_tab, wh, wn, tmin_tab, side_min, hzn, head, nxt, lane, g_rtl_scan_, g_rtl_sort_);
             RO_POP_DUE();
+            RTL_REBUILD_END();
         }
         RPH_MARK(3);                 // rebuild
         if (live && t >= 0) {
@@ -780,6 +827,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
         RPH_MARK(7);                 // observation rows: tile write + copy out
     }
 #undef RO_POP_DUE
+    RTL_SET(2);
 
     // ---------------- state out: masks, scalars and the window state.  The event storage stays in the launch-private form
     // (the next orlg_rollout resumes from it; ro_canonicalize_kernel rebuilds the canonical tables for everybody else).
@@ -796,12 +844,16 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
         p.now[env] = now;
         p.cur_hold[env] = hold;
         p.cur_req[env] = make_uint2((unsigned)src | ((unsigned)dst << 8) | ((unsigned)br << 16), (unsigned)sid);
-        p.counters[(size_t)0 * p.n + env] += d_proc;
-        p.counters[(size_t)1 * p.n + env] += d_acc;
+        {                                // the four running totals: all loads before the first store (one round trip, not four)
+            const auto c0 = p.counters[(size_t)0 * p.n + env], c1 = p.counters[(size_t)1 * p.n + env];
+            const auto c4 = p.counters[(size_t)4 * p.n + env], c5 = p.counters[(size_t)5 * p.n + env];
+            p.counters[(size_t)0 * p.n + env] = c0 + d_proc;
+            p.counters[(size_t)1 * p.n + env] = c1 + d_acc;
+            p.counters[(size_t)4 * p.n + env] = c4 + d_req;
+            p.counters[(size_t)5 * p.n + env] = c5 + d_prov;
+        }
         p.counters[(size_t)2 * p.n + env] = ep_proc;
         p.counters[(size_t)3 * p.n + env] = ep_acc;
-        p.counters[(size_t)4 * p.n + env] += d_req;
-        p.counters[(size_t)5 * p.n + env] += d_prov;
         p.counters[(size_t)6 * p.n + env] = ep_req;
         p.counters[(size_t)7 * p.n + env] = ep_prov;
         p.req_index[env] = ridx;
@@ -810,6 +862,8 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
         if (KIND == ORLG_DEEPRMSA) *reinterpret_cast<unsigned long long *>(p.cand + (size_t)env * 8) = candw;
     }
     RPH_MARK(9);                     // exit: state out
+    RTL_SET(3);
+    RTL_FLUSH((unsigned)(env0 >> 5));
 }
 
 // Launch-private event storage -> canonical release-event tables (orlg_device.cuh): window and side entries go back to the
