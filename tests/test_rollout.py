@@ -332,3 +332,55 @@ def test_state_dict_round_trip_continues_bit_for_bit(kind, env_args, policy):
         assert (x is None and y is None) or torch.equal(x, y)
     _final_state_equal(a, b)
     a.close(); b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("quantum,iat,lifetime", [(4.0, 0.5, 20.0), (1.0, 0.125, 3.0), (16.0, 0.5, 24.0)])
+def test_rollout_equal_release_times(quantum, iat, lifetime):
+    """Services that expire at EXACTLY the same time (the reference's heapq orders them by insertion, App. B-9: the order
+    does not change the masks, but every one of them must leave in the right step).  Release times are multiples of
+    `quantum`, so groups of quantum / iat consecutive arrivals tie; the window rebuild's warp-cooperative rank sort has to
+    keep tied entries apart (one window row each) on its short-list, single-list and > 32-entry paths."""
+    from optical_rl_gym_b200 import OpticalVecEnv
+    from oracle import oracle
+
+    tables = helpers.golden_tables()
+    n, T = 96, 400
+    rng = np.random.default_rng(int(quantum * 8))
+    arrival = np.tile(iat * np.arange(1, T + 3, dtype=np.float64), (n, 1))
+    arrival += iat * rng.integers(0, 3, size=(n, 1))                      # env clocks are not aligned
+    holding = quantum * np.ceil((arrival + lifetime) / quantum) - arrival   # exact: everything is a multiple of 2^-3
+    assert np.all(arrival + holding == quantum * np.ceil((arrival + lifetime) / quantum))
+    src = rng.integers(0, tables.num_nodes, size=arrival.shape).astype(np.int32)
+    dst = (src + rng.integers(1, tables.num_nodes, size=arrival.shape).astype(np.int32)) % tables.num_nodes
+    br = rng.integers(25, 101, size=arrival.shape).astype(np.int32)
+    actions = rng.integers(0, tables.k_paths, size=(T, n, 1)).astype(np.int32)
+    kw = dict(episode_length=150, mean_service_holding_time=lifetime, mean_service_inter_arrival_time=iat)
+    env = OpticalVecEnv("DeepRMSA-v0", n, tables, traffic="trace", **kw)
+    env.set_trace(arrival, holding, src, dst, br)
+    env.reset(full=True)
+    refs = []
+    for i in range(n):
+        o = oracle.OracleEnv("DeepRMSA-v0", tables, num_slots=100, episode_length=150, mean_holding=lifetime, mean_iat=iat)
+        o.set_trace(arrival[i], holding[i], src[i], dst[i], br[i])
+        o.reset(full=True)
+        refs.append((o, o.rollout(T, policy=0, actions=actions[:, i], want_obs=True)))
+    act_dev = torch.as_tensor(actions, device="cuda")
+    t0 = 0
+    for chunk in (3, 37, 160, T):
+        t1 = min(T, t0 + chunk)
+        if t1 <= t0:
+            break
+        obs, rew, done, _ = env.rollout(t1 - t0, "replay", actions=act_dev[t0:t1])
+        assert np.array_equal(rew.cpu().numpy().astype(np.float64), np.stack([r["rewards"][t0:t1] for _, r in refs], 1)), t0
+        assert np.array_equal(done.cpu().numpy(), np.stack([r["dones"][t0:t1] for _, r in refs], 1)), t0
+        np.testing.assert_allclose(obs.cpu().numpy(), np.stack([r["obs"][t0:t1] for _, r in refs], 1), rtol=OBS_RTOL, atol=0)
+        t0 = t1
+    avail = env.available_slots().cpu().numpy()
+    _, _, now, nheap = env.export_state(allocation=True)
+    for i, (o, _) in enumerate(refs):
+        oa, _, onow, onh = o.state()
+        assert np.array_equal(avail[i].reshape(oa.shape), oa), ("masks", i)
+        assert now[i].item() == onow and nheap[i].item() == onh, ("clock / live services", i)
+    assert int(env.error_flags().abs().sum()) == 0
+    env.close()
