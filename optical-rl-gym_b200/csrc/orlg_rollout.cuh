@@ -34,7 +34,10 @@
 namespace orlg {
 
 constexpr int RO_WCAP = 64;            // window entries per env
-constexpr int RO_SIDE = 3;             // side-buffer entries per env (shared memory)
+#ifndef ORLG_RO_SIDE
+#define ORLG_RO_SIDE 4        // 3 -> 4: no warp takes two rebuilds inside a 20-step launch any more (side-buffer overflow forced them); 5, 6 cost more in the step loop
+#endif
+constexpr int RO_SIDE = ORLG_RO_SIDE;             // side-buffer entries per env (shared memory)
 constexpr int RO_MAX_THREADS = 448;    // 14 warps x 148 SMs >= 65536 envs in one wave
 enum { RO_POLICY_RANDOM = 0, RO_POLICY_SP_FF = 1, RO_POLICY_SAP_FF = 2, RO_POLICY_REPLAY = 3, RO_POLICY_LLP_FF = 4, RO_POLICY_SAP_LF = 5 };
 
