@@ -1342,7 +1342,7 @@ int orlg_policy_act(orlg_policy *pol, const float *obs_dev, int n, int32_t *acti
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pol->device);
     const int pairs = ((n + PL_TILE - 1) / PL_TILE + PL_GROUPS - 1) / PL_GROUPS;       // each CTA walks PL_GROUPS tile streams
-    cudaLaunchConfig_t cfg = pdl_config(pairs < sms ? pairs : sms, 128 * PL_GROUPS, pol->smem, (cudaStream_t)stream);
+    cudaLaunchConfig_t cfg = pdl_config(pairs < sms ? pairs : sms, PL_WG * PL_GROUPS, pol->smem, (cudaStream_t)stream);
     int *actions = actions_dev;
     CUDA_OK(cudaLaunchKernelEx(&cfg, mlp_policy_kernel, pol->pp, obs_dev, n, actions, logits_dev));
     return ORLG_OK;

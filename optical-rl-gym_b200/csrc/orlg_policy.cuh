@@ -76,6 +76,18 @@ __device__ __forceinline__ void pl_tmem_ld32(unsigned taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
+// the same without the wait: several loads in flight, one pl_tmem_wait() before the first use
+__device__ __forceinline__ void pl_tmem_ld32_nowait(unsigned taddr, unsigned (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void pl_tmem_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void pl_tmem_ld16(unsigned taddr, float (&v)[16]) {
     unsigned r[16];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -88,19 +100,24 @@ __device__ __forceinline__ void pl_tmem_ld16(unsigned taddr, float (&v)[16]) {
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
-// Two warpgroups per CTA, each walking its own stream of 128-environment tiles with its own A buffer, TMEM accumulator and
-// mbarrier (they only share the weights): one warpgroup's tensor-core work and TMEM reads overlap the other's epilogue math.
+// Two groups of EIGHT warps per CTA, each walking its own stream of 128-environment tiles with its own A buffer, TMEM accumulator
+// and mbarrier (they only share the weights): one group's tensor-core work and TMEM reads overlap the other's epilogue math.
+// Inside a group warp w reads TMEM lanes 32 (w % 4) .. + 31 (the hardware's lane quarter of a warp) and takes columns
+// 64 (w / 4) .. + 63: thread t owns row t % 128 and one half of its columns, so the epilogue of a layer (128 x 128 tanh, the
+// chain that bounds this kernel) is spread over 8 warps with both of a thread's TMEM loads in flight before the first use.
 // smem: [weights w_bytes][2 x A tile 128 x 128 bf16 = 64 KB][bias floats][mbarriers][tmem base]
 constexpr int PL_GROUPS = 2;
-__device__ __forceinline__ void pl_group_sync(int group) {          // named barrier of one warpgroup (ids 1, 2; 0 = __syncthreads)
-    asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+constexpr int PL_WG = 256;            // threads per group
+__device__ __forceinline__ void pl_group_sync(int group) {          // named barrier of one group (ids 1, 2; 0 = __syncthreads)
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(PL_WG) : "memory");
 }
 
-__global__ void __launch_bounds__(128 * PL_GROUPS, 1)
+__global__ void __launch_bounds__(PL_WG * PL_GROUPS, 1)
 mlp_policy_kernel(const PolicyParams pp, const float *__restrict__ obs, const int n, int *__restrict__ actions,
                   float *__restrict__ logits_out /* [n, 6] = 5 logits + value, or NULL */) {
     extern __shared__ __align__(128) unsigned char psm[];
-    const int group = threadIdx.x >> 7, tid = threadIdx.x & 127, warp = tid >> 5;      // warp = index inside the warpgroup: its TMEM lane quarter
+    const int group = threadIdx.x / PL_WG, tid = threadIdx.x % PL_WG, warp = (tid >> 5) & 3;     // warp = TMEM lane quarter of this warp
+    const int half = tid >> 7;        // which 64 of the 128 columns (K elements of the next layer) this thread produces
     unsigned char *s_w = psm;
     unsigned char *s_a = psm + pp.w_bytes + (size_t)group * PL_TILE * PL_H * 2;
     float *s_bias = reinterpret_cast<float *>(psm + pp.w_bytes + (size_t)PL_GROUPS * PL_TILE * PL_H * 2);
@@ -121,7 +138,7 @@ mlp_policy_kernel(const PolicyParams pp, const float *__restrict__ obs, const in
                            "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(&bars[0])) : "memory");
         }
     }
-    for (int i = threadIdx.x; i < PL_LAYERS * PL_H + PL_NOUT; i += 128 * PL_GROUPS) s_bias[i] = pp.bias[i];
+    for (int i = threadIdx.x; i < PL_LAYERS * PL_H + PL_NOUT; i += PL_WG * PL_GROUPS) s_bias[i] = pp.bias[i];
     if (threadIdx.x < 32) {     // TMEM: 128 columns (one 128 x 128 fp32 accumulator tile) per warpgroup
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"((unsigned)__cvta_generic_to_shared(s_tmem)), "r"(128u * PL_GROUPS) : "memory");
@@ -139,31 +156,62 @@ mlp_policy_kernel(const PolicyParams pp, const float *__restrict__ obs, const in
     const unsigned a_addr = (unsigned)__cvta_generic_to_shared(s_a);
     const unsigned w_addr = (unsigned)__cvta_generic_to_shared(s_w);
     unsigned phase = 0;
-    const int row = tid;              // thread t owns row t of the tile: TMEM lane t, A-operand row t
+    const int row = tid & 127;        // thread t owns row t % 128 of the tile: TMEM lane, A-operand row
     unsigned char *a_row = s_a + (row >> 3) * 128 + (row & 7) * 16;        // + (k >> 3) * 2048 + (k & 7) * 2
 
     unsigned long long *bar = &bars[1 + group];
     for (int tile = blockIdx.x * PL_GROUPS + group; tile * PL_TILE < n; tile += gridDim.x * PL_GROUPS) {
         const int env = tile * PL_TILE + row;
-        // ---- layer-0 input: this row's observation as bf16, K padded to 64 with zeros
+        // ---- layer-0 input: the tile's observation rows as bf16, K padded to 64 with zeros.  The 128 rows are one contiguous
+        // 27 KB run of obs: they are fetched with coalesced 16-byte loads, 64 rows at a time, into the upper half of the A
+        // buffer (k blocks 8..15: unused by layer 0), and each thread then converts its 32 of a row's 64 elements from there.
+        // (A thread reading its own 216-byte row from global memory cost 32 sectors per load instruction: 42 % of the kernel's
+        // stall samples were lg_throttle / long scoreboard on those loads.)
         {
-            float x[PL_K0];
+            constexpr int KH = PL_K0 / 2;
+            unsigned char *stage = s_a + 8 * 2048;                          // 16 KB
+            const bool fast = (pp.obs_dim * 4 * 64) % 16 == 0 && (reinterpret_cast<size_t>(obs) & 15) == 0 && pp.obs_dim * 4 * 64 <= 16384;
+            for (int hseg = 0; hseg < 2; hseg++) {
+                const int r0 = tile * PL_TILE + hseg * 64;                  // first env of this half tile
+                const int rows_here = min(64, n - r0);                      // may be <= 0 in the last tile
+                float x[KH];
 #pragma unroll
-            for (int k = 0; k < PL_K0; k++) x[k] = 0.0f;
-            if (env < n) {
-                const float2 *src = reinterpret_cast<const float2 *>(obs + (size_t)env * pp.obs_dim);     // obs_dim is even: rows are 8-byte aligned
+                for (int k = 0; k < KH; k++) x[k] = 0.0f;
+                if (fast) {
+                    const int vec_total = rows_here > 0 ? (rows_here * pp.obs_dim) / 4 : 0;          // whole 16-byte vectors available
+                    const int tail = rows_here > 0 ? rows_here * pp.obs_dim - 4 * vec_total : 0;     // (a ragged last tile: 0..3 floats)
+                    const uint4 *g = reinterpret_cast<const uint4 *>(obs + (size_t)r0 * pp.obs_dim);
 #pragma unroll
-                for (int k = 0; k < PL_K0 / 2; k++)
-                    if (2 * k < pp.obs_dim) { const float2 v = src[k]; x[2 * k] = v.x; x[2 * k + 1] = v.y; }
-            }
+                    for (int it = 0; it < 4; it++) {
+                        const int v = tid + it * PL_WG;
+                        if (v < vec_total) *reinterpret_cast<uint4 *>(stage + v * 16) = g[v];
+                    }
+                    if (tid < tail) reinterpret_cast<float *>(stage)[4 * vec_total + tid] = obs[(size_t)r0 * pp.obs_dim + 4 * vec_total + tid];
+                    pl_group_sync(group);
+                    if ((row >> 6) == hseg && env < n) {
+                        const float2 *src = reinterpret_cast<const float2 *>(stage + (row & 63) * pp.obs_dim * 4) + half * (KH / 2);
 #pragma unroll
-            for (int j = 0; j < PL_K0 / 8; j++) {
-                uint4 pk;
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(x[8 * j], x[8 * j + 1]), h1 = __floats2bfloat162_rn(x[8 * j + 2], x[8 * j + 3]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(x[8 * j + 4], x[8 * j + 5]), h3 = __floats2bfloat162_rn(x[8 * j + 6], x[8 * j + 7]);
-                pk.x = *reinterpret_cast<unsigned *>(&h0); pk.y = *reinterpret_cast<unsigned *>(&h1);
-                pk.z = *reinterpret_cast<unsigned *>(&h2); pk.w = *reinterpret_cast<unsigned *>(&h3);
-                *reinterpret_cast<uint4 *>(a_row + j * 2048) = pk;
+                        for (int k = 0; k < KH / 2; k++)
+                            if (half * KH + 2 * k < pp.obs_dim) { const float2 v = src[k]; x[2 * k] = v.x; x[2 * k + 1] = v.y; }
+                    }
+                } else if ((row >> 6) == hseg && env < n) {
+                    const float2 *src = reinterpret_cast<const float2 *>(obs + (size_t)env * pp.obs_dim) + half * (KH / 2);     // obs_dim is even: rows are 8-byte aligned
+#pragma unroll
+                    for (int k = 0; k < KH / 2; k++)
+                        if (half * KH + 2 * k < pp.obs_dim) { const float2 v = src[k]; x[2 * k] = v.x; x[2 * k + 1] = v.y; }
+                }
+                if ((row >> 6) == hseg) {
+#pragma unroll
+                    for (int j = 0; j < KH / 8; j++) {
+                        uint4 pk;
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(x[8 * j], x[8 * j + 1]), h1 = __floats2bfloat162_rn(x[8 * j + 2], x[8 * j + 3]);
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(x[8 * j + 4], x[8 * j + 5]), h3 = __floats2bfloat162_rn(x[8 * j + 6], x[8 * j + 7]);
+                        pk.x = *reinterpret_cast<unsigned *>(&h0); pk.y = *reinterpret_cast<unsigned *>(&h1);
+                        pk.z = *reinterpret_cast<unsigned *>(&h2); pk.w = *reinterpret_cast<unsigned *>(&h3);
+                        *reinterpret_cast<uint4 *>(a_row + (half * (KH / 8) + j) * 2048) = pk;
+                    }
+                }
+                if (fast) pl_group_sync(group);                             // the stage is refilled (or becomes operand space) next
             }
         }
         int w_off = 0;                 // byte offset of the current layer's weights in s_w
@@ -191,40 +239,50 @@ mlp_policy_kernel(const PolicyParams pp, const float *__restrict__ obs, const in
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const float *b = s_bias + layer * PL_H;
             if (layer < PL_LAYERS) {
-                // ---- epilogue: bias + tanh, next layer's A operand (bf16) back into shared memory
-#pragma unroll 1
-                for (int c0 = 0; c0 < PL_H; c0 += 32) {
-                    float v[32];
-                    pl_tmem_ld32(t_lane + (unsigned)c0, v);
+                // ---- epilogue: bias + tanh, next layer's A operand (bf16) back into shared memory; this thread's 64 columns
+                unsigned r0[32], r1[32];
+                const int cb = half * 64;
+                pl_tmem_ld32_nowait(t_lane + (unsigned)cb, r0);
+                pl_tmem_ld32_nowait(t_lane + (unsigned)cb + 32u, r1);
+                pl_tmem_wait();
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        uint4 pk;
+                        const int c0 = cb + 32 * hh + 8 * j;
+                        const float4 b0 = *reinterpret_cast<const float4 *>(b + c0), b1 = *reinterpret_cast<const float4 *>(b + c0 + 4);
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                         unsigned w4[4];
 #pragma unroll
-                        const float4 b0 = *reinterpret_cast<const float4 *>(b + c0 + 8 * j), b1 = *reinterpret_cast<const float4 *>(b + c0 + 8 * j + 4);
-                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                         for (int q = 0; q < 4; q++) {
-                            __nv_bfloat162 h = __floats2bfloat162_rn(pl_tanh(v[8 * j + 2 * q] + bb[2 * q]), pl_tanh(v[8 * j + 2 * q + 1] + bb[2 * q + 1]));
+                            const float v0 = __uint_as_float(hh ? r1[8 * j + 2 * q] : r0[8 * j + 2 * q]);
+                            const float v1 = __uint_as_float(hh ? r1[8 * j + 2 * q + 1] : r0[8 * j + 2 * q + 1]);
+                            __nv_bfloat162 h = __floats2bfloat162_rn(pl_tanh(v0 + bb[2 * q]), pl_tanh(v1 + bb[2 * q + 1]));
                             w4[q] = *reinterpret_cast<unsigned *>(&h);
                         }
-                        pk.x = w4[0]; pk.y = w4[1]; pk.z = w4[2]; pk.w = w4[3];
-                        *reinterpret_cast<uint4 *>(a_row + ((c0 >> 3) + j) * 2048) = pk;
+                        *reinterpret_cast<uint4 *>(a_row + (c0 >> 3) * 2048) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                     }
                 }
             } else {
                 // ---- output layer: 5 logits (+ value); deterministic action = argmax (first maximum, like torch.argmax)
-                float v[16];
-                pl_tmem_ld16(t_lane, v);
-                if (env < n) {
-                    int best = 0;
-                    float bv = v[0] + b[0];
-                    for (int a = 1; a < pp.n_actions; a++) {
-                        const float l = v[a] + b[a];
-                        if (l > bv) { bv = l; best = a; }
+                if (half == 0) {                                   // warp-uniform: the four warps of the first half hold the 128 rows
+                    float v[16];
+                    pl_tmem_ld16(t_lane, v);
+                    if (env < n) {
+                        int best = 0;
+                        float bv = v[0] + b[0];
+#pragma unroll
+                        for (int a = 1; a < PL_NOUT - 1; a++) {          // static indices: the accumulator row stays in registers
+                            const float l = v[a] + b[a];
+                            if (a < pp.n_actions && l > bv) { bv = l; best = a; }
+                        }
+                        actions[env] = best;
+                        if (logits_out) {
+#pragma unroll
+                            for (int a = 0; a < PL_NOUT; a++)
+                                if (a <= pp.n_actions) logits_out[(size_t)env * (pp.n_actions + 1) + a] = v[a] + b[a];
+                        }
                     }
-                    actions[env] = best;
-                    if (logits_out)
-                        for (int a = 0; a <= pp.n_actions; a++) logits_out[(size_t)env * (pp.n_actions + 1) + a] = v[a] + b[a];
                 }
             }
             w_off += N * K * 2;
