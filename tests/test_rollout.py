@@ -384,3 +384,36 @@ def test_rollout_equal_release_times(quantum, iat, lifetime):
         assert now[i].item() == onow and nheap[i].item() == onh, ("clock / live services", i)
     assert int(env.error_flags().abs().sum()) == 0
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fraction", [None, "0.5", "0.9"])
+def test_host_rollout_with_pinned_result_buffer(monkeypatch, fraction):
+    """orlg_rollout_host with a page-locked observation buffer: the rows of a share of the envs arrive by DMA (written by the
+    kernel), the rest is expanded from the packed records by the host threads -- the result must be the device rollout's,
+    bit for bit, whatever the share (fixed or adaptive) and across chunk boundaries / a ragged last chunk."""
+    from optical_rl_gym_b200 import OpticalVecEnv
+
+    if fraction is not None:
+        monkeypatch.setenv("ORLG_HOST_DMA_FRACTION", fraction)
+    else:
+        monkeypatch.setenv("ORLG_HOST_DMA", "auto")
+    tables = helpers.golden_tables()
+    n, T = 8192 + 4096 + 37, 50
+    kw = dict(seed=11, episode_length=30, collect_info=False)
+    a = OpticalVecEnv("DeepRMSA-v0", n, tables, **kw)
+    b = OpticalVecEnv("DeepRMSA-v0", n, tables, **kw)
+    o1, r1, d1, a1 = a.rollout(T, "random")
+    obs = torch.full((T, n, a.obs_dim), 7.0, dtype=torch.float32).pin_memory()
+    o2, r2, d2, a2 = b.rollout_host(T, "random", obs=obs.numpy(), chunk=8, threads=3)
+    assert fraction is None or b.host_dma_fraction() == float(fraction)
+    assert b.host_dma_fraction() > 0.0
+    assert np.array_equal(o1.cpu().numpy(), o2)
+    assert np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(d1.cpu().numpy(), d2)
+    assert np.array_equal(a1.cpu().numpy()[..., 0], a2)
+    # a second call continues from the same state (and with whatever share the first call settled on)
+    o1, r1, d1, _ = a.rollout(T, "random")
+    o2, r2, d2, _ = b.rollout_host(T, "random", obs=obs.numpy(), chunk=3, threads=2)
+    assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(d1.cpu().numpy(), d2)
+    _final_state_equal(a, b)
+    a.close(); b.close()
