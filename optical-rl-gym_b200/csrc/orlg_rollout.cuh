@@ -8,20 +8,24 @@
 //     stay in shared memory and the scalar block (clock, pending request, counters, cached block starts)
 //     stays in registers; HBM sees them once at entry and once at exit;
 //   * for the duration of the launch the release-event tables of the warp's 32 envs are held LANE-INTERLEAVED
-//     ([slot][lane], copied in at entry and back at exit), so that a thread-per-env pass over "slot s of every
-//     env" is one coalesced access.  The table is consulted through a per-env WINDOW: every ~span steps each
-//     thread streams its table once, moves the services that expire before a horizon into a small list sorted
-//     by release time (HBM / L2, 16-byte entries) and compacts the rest in place.  A step then only compares
-//     the list head (registers; the following entry is fetched one pop ahead) with the clock: the directory ->
-//     group -> payload fetch chain of the per-step kernel is gone.  Services accepted with a release time
-//     inside the horizon wait in a 3-entry side buffer in shared memory.  The exact minimum of what is left in
+//     (rows of 32 16-byte entries: [row][lane], converted at the first launch and kept until another entry point
+//     needs the canonical form), so that a thread-per-env pass over "row r of every env" is one coalesced access.
+//     The table is consulted through a per-env WINDOW: every ~30 steps the warp rebuilds it -- each thread
+//     streams its table once, moves the services that expire before a horizon into a scratch list and compacts
+//     the rest in place; the warp then sorts the 32 lists by release time through shuffles (ro_rebuild).  A
+//     step then only compares the list head (registers; the following entry is fetched one pop ahead) with
+//     the clock: the directory -> group -> payload fetch chain of the per-step kernel is gone.  Services
+//     accepted with a release time inside the horizon wait in a 4-entry side buffer in shared memory.  The exact minimum of what is left in
 //     the table gates the next rebuild, so the scheme is exact whatever the horizon (which only tunes how
 //     often the tables are streamed); rebuilds are taken by the whole warp together (ballot);
 //   * the 32 observation rows of a warp are assembled in a shared-memory tile taken from a small per-CTA
 //     pool (held only while the rows are written and copied out with coalesced 16-byte stores); the topology
 //     tables arrive by one bulk (TMA) copy per CTA;
-//   * at exit the window / side entries go back to the table and its directory is rebuilt, so that every
-//     other entry point of the library (per-step kernels, export, heuristics) sees the canonical state.
+//   * the window state persists between launches (st_* arrays); ro_canonicalize_kernel puts the window / side
+//     entries back and rebuilds the canonical tables and their directory the first time another entry point of
+//     the library (per-step kernels, export, heuristics) needs them;
+//   * phase C (free-slot masks and features of the candidate paths) is ONE rolled loop over the paths: the loop
+//     body of a step has to fit the 32 KB instruction cache that 14 de-synchronised warps share.
 // Release order inside a step is irrelevant (masks only); what must be exact is WHICH
 // services are due, and that is decided on the float64 times.
 #pragma once
