@@ -257,8 +257,17 @@ int launch_step(const orlg_env *env, const StepIO &io, int mode, cudaStream_t s)
     return ORLG_OK;
 }
 
+// envs per warp of the rollout kernel: a batch that would leave most SMs with one or two warps is spread over more warps
+// with fewer lanes in use (less divergence per warp, more warps to hide latency); fixed per handle (the event slabs follow it)
+int rollout_lpw(const orlg_env *env) {
+    static const int forced = [] { const char *v = std::getenv("ORLG_RO_LPW"); const int w = v ? std::atoi(v) : 0; return (w == 8 || w == 32) ? w : 0; }();
+    if (forced) return forced;
+    return env->p.n >= 16384 ? 32 : 8;
+}
+
 void rollout_state_args(const orlg_env *env, RolloutArgs *ra) {
     const size_t n = (size_t)env->p.n;
+    ra->lpw = rollout_lpw(env);
     ra->ev = env->ro_ev;
     ra->st_ntab = env->ro_st_u32; ra->st_wh = env->ro_st_u32 + n; ra->st_wn = env->ro_st_u32 + 2 * n; ra->st_ncanon = env->ro_st_u32 + 3 * n;
     ra->st_tmin = env->ro_st_f64; ra->st_hzn = env->ro_st_f64 + n; ra->st_side_t = env->ro_st_f64 + 2 * n;
@@ -282,7 +291,8 @@ int ensure_canonical(orlg_env *env, cudaStream_t s) {
 // its mask tile + side buffer, plus a pool of observation tiles
 bool rollout_plan(const orlg_env *env, int *wpc_out, RolloutArgs *ra, size_t *smem_out) {
     const Params &p = env->p;
-    const int warps = (p.n + 31) / 32;
+    const int lpw = rollout_lpw(env);
+    const int warps = (p.n + lpw - 1) / lpw;
     int wpc = (warps + 147) / 148;
     if (wpc > RO_MAX_THREADS / 32) wpc = RO_MAX_THREADS / 32;
     if (wpc < 1) wpc = 1;
@@ -307,15 +317,17 @@ bool rollout_plan(const orlg_env *env, int *wpc_out, RolloutArgs *ra, size_t *sm
 
 template <int ET, int KIND>
 cudaError_t launch_rollout_kind(const orlg_env *env, const RolloutArgs &ra, int policy, int wpc, size_t smem, cudaStream_t s) {
-    const int threads = wpc * 32, blocks = (env->p.n + threads - 1) / threads;
+    const int warps = (env->p.n + ra.lpw - 1) / ra.lpw;
+    const int threads = wpc * 32, blocks = (warps + wpc - 1) / wpc;
     cudaLaunchConfig_t cfg = pdl_config(blocks, threads, smem, s);
     cudaError_t e = cudaErrorInvalidValue;
     const bool trace = env->p.traffic == ORLG_TRAFFIC_TRACE;
-#define ORLG_RO_LAUNCH(POL, TR)                                                                                          \
+#define ORLG_RO_LAUNCH1(POL, TR, LP)                                                                                     \
     do {                                                                                                                 \
-        e = cudaFuncSetAttribute(deeprmsa_rollout_kernel<ET, POL, TR, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, deeprmsa_rollout_kernel<ET, POL, TR, KIND>, env->p, ra);     \
+        e = cudaFuncSetAttribute(deeprmsa_rollout_kernel<ET, POL, TR, KIND, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, deeprmsa_rollout_kernel<ET, POL, TR, KIND, LP>, env->p, ra); \
     } while (0)
+#define ORLG_RO_LAUNCH(POL, TR) do { if (ra.lpw == 32) ORLG_RO_LAUNCH1(POL, TR, 32); else ORLG_RO_LAUNCH1(POL, TR, 8); } while (0)
     if (policy == ORLG_POLICY_REPLAY) {
         if (trace) ORLG_RO_LAUNCH(RO_POLICY_REPLAY, true); else ORLG_RO_LAUNCH(RO_POLICY_REPLAY, false);
     } else if (trace) {
@@ -326,6 +338,7 @@ cudaError_t launch_rollout_kind(const orlg_env *env, const RolloutArgs &ra, int 
     else if (policy == ORLG_HEUR_LLP_FF) { if (KIND != ORLG_DEEPRMSA) ORLG_RO_LAUNCH(RO_POLICY_LLP_FF, false); }
     else if (policy == ORLG_HEUR_SAP_LF) { if (KIND == ORLG_RWA) ORLG_RO_LAUNCH(RO_POLICY_SAP_LF, false); }
 #undef ORLG_RO_LAUNCH
+#undef ORLG_RO_LAUNCH1
     return e;
 }
 
@@ -981,7 +994,8 @@ static int rollout_impl(orlg_env *env, int steps, int policy, void *obs_dev, flo
     if (persistent && rollout_plan(env, &wpc, &ra, &smem)) {
         if (!env->ro_ev) {
             const size_t n = (size_t)p.n;
-            const size_t warps = (n + 31) / 32;
+            const size_t lpw = (size_t)rollout_lpw(env);
+            const size_t warps = (n + lpw - 1) / lpw;
             int rc = dev_alloc(env, &env->ro_ev, warps * 32 * ((size_t)p.heap_cap + 2 * RO_WCAP), false);
             if (!rc) rc = dev_alloc(env, &env->ro_st_u32, 4 * n, false);
             if (!rc) rc = dev_alloc(env, &env->ro_st_f64, (2 + RO_SIDE) * n, false);

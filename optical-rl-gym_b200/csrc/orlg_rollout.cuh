@@ -91,6 +91,8 @@ struct RolloutArgs {
     int pool_tiles;              // observation tiles shared by the CTA's warps
     int tile_bytes;              // 32 rows x obs_dim floats, rounded up to 128 bytes
     int warp_bytes;              // per-warp shared memory: E x 512 (masks) + RO_SIDE x 512 (side buffer)
+    int lpw;                     // envs (lanes in use) per warp: 32, or 8 for small batches -- more warps per SM and less
+                                 // divergence per warp when the batch would not fill the machine (fixed per handle)
     double span;                 // window horizon (time units ahead of the clock)
     float *obs;                  // [T][n][obs_dim]   (NULL: skip)
     float *reward;               // [T][n]            (NULL: skip)
@@ -328,17 +330,20 @@ __device__ __forceinline__ unsigned feat_pack(int st, int len, int total, int ru
 // RO_POLICY_REPLAY (actions given up front) this replays a reference run through the persistent kernel.
 // KIND: DeepRMSA-v0 (block-feature observation, path action), RMSA-v0 or RWA-v0 (no tensor observation, (path, slot) action,
 // the reference's first-fit heuristics evaluated on the cached free-slot masks of the candidate paths).
-template <int ET, int POLICY, bool TRACE = false, int KIND = ORLG_DEEPRMSA>
+// LPW: envs (lanes in use) per warp, 32 or 8 (compile-time: the 32-lane instances are the code they were before the small-batch
+// mapping existed -- a run-time lane count cost the headline instance 3 % through register allocation alone).
+template <int ET, int POLICY, bool TRACE = false, int KIND = ORLG_DEEPRMSA, int LPW = 32>
 __global__ void __launch_bounds__(RO_MAX_THREADS, 1)
 deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     constexpr int KM = 5;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int wpc = blockDim.x >> 5;
-    const int env0 = blockIdx.x * blockDim.x + wid * 32;           // first env of this warp
+    const int gwarp = blockIdx.x * wpc + wid;                      // warp index over the launch = index of its event slab
+    const int env0 = gwarp * LPW;                                  // first env of this warp
     const int env = env0 + lane;
-    const bool live = env < p.n;
-    const int nvalid = min(32, p.n - env0);
+    const bool live = (LPW == 32 || lane < LPW) && env < p.n;
+    const int nvalid = min(LPW, p.n - env0);
     const int e = live ? env : p.n - 1;
     const int E = ET > 0 ? ET : p.E;
     unsigned char *warp_area = smem + p.tab_vec * 16 + (size_t)wid * ra.warp_bytes;
@@ -399,7 +404,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     unsigned n_tab = nlive;
     unsigned err = p.errors[e];
     unsigned long long candw = KIND == ORLG_DEEPRMSA ? *reinterpret_cast<const unsigned long long *>(p.cand + (size_t)e * 8) : 0xFFFFFFFFFFFFFFFFULL;
-    const size_t gw = (size_t)(env0 >> 5);                       // this warp's slab of the launch-private event storage
+    const size_t gw = (size_t)gwarp;                             // this warp's slab of the launch-private event storage
     WinEntry *const ev = ra.ev + gw * (size_t)(p.heap_cap + 2 * RO_WCAP) * 32 + lane;       // table rows [0, heap_cap)
     WinEntry *const win = ev + (size_t)(p.heap_cap + RO_WCAP) * 32;
 #pragma unroll
@@ -870,7 +875,7 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
     }
     RPH_MARK(9);                     // exit: state out
     RTL_SET(3);
-    RTL_FLUSH((unsigned)(env0 >> 5));
+    RTL_FLUSH((unsigned)gwarp);
 }
 
 // Launch-private event storage -> canonical release-event tables (orlg_device.cuh): window and side entries go back to the
@@ -879,8 +884,8 @@ deeprmsa_rollout_kernel(const Params p, const RolloutArgs ra) {
 __global__ void __launch_bounds__(128) ro_canonicalize_kernel(const Params p, const RolloutArgs ra) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.n) return;
-    const int lane = threadIdx.x & 31;
-    const size_t gw = (size_t)(env >> 5);
+    const int lane = env % ra.lpw;                               // the rollout kernel's mapping: slab env / lpw, lane env % lpw
+    const size_t gw = (size_t)(env / ra.lpw);
     WinEntry *const ev = ra.ev + gw * (size_t)(p.heap_cap + 2 * RO_WCAP) * 32 + lane;
     const WinEntry *const win = ev + (size_t)(p.heap_cap + RO_WCAP) * 32;
     unsigned n_tab = ra.st_ntab[env];
