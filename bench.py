@@ -498,7 +498,7 @@ def main():
                 tj = json.load(f)
             # per launch like `achieved`: the ncu capture (65536 envs x 20 steps per launch) scaled to this launch's env-steps
             roofline["traffic"] = tj.get("rollout_kernel_bytes_per_env_step") * n * chunk
-            roofline["traffic_source"] = "ncu --set full capture of a %s-step launch (profiles/r2c_rollout_ncu_full.csv), %.0f B per env-step" % (
+            roofline["traffic_source"] = "ncu --set full capture of a %s-step launch (profiles/r2d_rollout_ncu_full.csv), %.0f B per env-step" % (
                 tj.get("rollout_kernel_steps_per_launch"), tj.get("rollout_kernel_bytes_per_env_step"))
         except Exception:  # noqa: BLE001
             pass
